@@ -1,0 +1,78 @@
+"""Runs the command sequences of tests/golden/reference_vectors.json against the host
+mirror (inverted_index_2_b200.host) with an injected backend — the Python twin of the
+reference's TestingMachine (helper_test.go:13-103)."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from inverted_index_2_b200.host import InvertedIndex, Shard
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")
+
+
+def load_vectors() -> dict:
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def _b(x):
+    return None if x is None else x.encode()
+
+
+class OracleBackend:
+    """Backend protocol of host.py on the CPU oracle (tests only)."""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def merge(self, segs, removed):
+        return self.orc.merge(segs, removed=np.asarray(removed, dtype=np.uint32), decoded=False)
+
+    def read_range(self, segs, min_term, max_term):
+        return self.orc.read_range(segs, min_term, max_term)
+
+
+def run_steps(target, steps, is_index: bool):
+    for cmd, arg in steps:
+        if cmd == "put":
+            target.put([t.encode() for t in arg[0]], arg[1])
+        elif cmd == "ingest":
+            for val in sorted(arg, key=int):
+                target.put([t.encode() for t in arg[val]], int(val))
+        elif cmd == "compare":
+            expected = sorted((t.encode(), v) for t, v in arg.items())
+            assert list(target.read(None, None)) == expected
+        elif cmd == "read":
+            lo, hi, exp = arg
+            assert list(target.read(_b(lo), _b(hi))) == [(t.encode(), v) for t, v in exp]
+        elif cmd == "merge":
+            req, mx, exp = arg
+            got = target.merge(req, mx, 2) if is_index else target.merge(req, mx)
+            if exp >= 0:
+                assert got == exp
+        elif cmd == "remove":
+            (target.put_removed if is_index else target.remove)(arg)
+        elif cmd == "count_segments":
+            assert target.count_segments() == arg
+        elif cmd == "removed_values":
+            assert target.removed_list.values().tolist() == arg
+        elif cmd == "minmax":
+            assert target.min_max() == [_b(arg[0]), _b(arg[1])]
+        elif cmd == "prefix":
+            got = target.prefix_search([p.encode() for p in arg[0]])
+            assert got == {k.encode(): v for k, v in arg[1].items()}
+        elif cmd == "shards":
+            assert len(target.shards) == arg
+        else:
+            raise ValueError(cmd)
+
+
+def run_shard_scenario(backend, sc):
+    run_steps(Shard("0000", backend), sc["steps"], False)
+
+
+def run_index_scenario(backend, sc):
+    run_steps(InvertedIndex(backend), sc["steps"], True)
