@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py — merged postings/s of segment compaction on B200 (BASELINE.json configs[1]:
+"compaction of 64 segments, 1M terms, 100M postings on 1 B200"), one JSON line on stdout.
+
+A step = ONE compaction (ii2_merge_dev: k-way term merge + per-term union/dedup + removed
+filter + intcomp encode, shard.go:158-212) of all resident segments of this rank's shard range.
+  value      whole-job merged INPUT postings/s, segments resident in HBM, CUDA-event timed
+  e2e        the same through the host-buffer C-ABI call ii2_merge (what cgo calls from
+             Shard.Merge): pinned host inputs -> H2D -> kernels -> D2H of the new segment
+  roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs measured HBM peak
+  cpu_baseline  the CPU oracle (C restatement of the Go path) on a bounded sample, rank 0, N=1
+Multi-GPU: shards are independent (shard.go:19-20) -> one process per GPU, each compacting its
+own term range, no data-path collective; weak scaling.  `--impl reference` times the CPU oracle
+with all host threads (InvertedIndex.Merge's worker pool over shards, inverted_index.go:83-103).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from inverted_index_2_b200 import synth  # noqa: E402
+from inverted_index_2_b200.flat import FlatSegment  # noqa: E402
+
+METRIC = "merged postings/s"
+UNIT = "postings/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--terms", type=int, default=1_000_000)
+    ap.add_argument("--segments", type=int, default=64)
+    ap.add_argument("--postings", type=int, default=100_000_000)
+    ap.add_argument("--removed-frac", type=float, default=0.05)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0,
+                    help="target CPU time of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="check the full-size result against an independent numpy union")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"compaction of {a.segments} segments, {a.terms} terms, {a.postings} postings, "
+            f"{a.removed_frac:g} of the id universe removed (synthetic terms.1m stand-in)")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- CPU legs
+def slice_prefix(w: synth.Workload, n_terms: int, first: int = 0) -> list[FlatSegment]:
+    """Segments restricted to global term ids [first, first+n_terms) — a term-range shard."""
+    out = []
+    for seg, ids in zip(w.segments, w.seg_term_ids):
+        a, b = np.searchsorted(ids, [first, first + n_terms])
+        toff = seg.term_off[a:b + 1]
+        poff = seg.post_off[a:b + 1]
+        out.append(FlatSegment(seg.term_bytes[int(toff[0]):int(toff[-1])].copy(),
+                               (toff - toff[0]).astype(np.uint32), seg.mode,
+                               post=seg.post[int(poff[0]):int(poff[-1])].copy(),
+                               post_off=(poff - poff[0]).astype(np.uint64)))
+    return out
+
+
+def cpu_rate_single(w: synth.Workload, target_s: float):
+    """One oracle thread = one Shard.Merge (single goroutine per shard, shard.go:168-212)."""
+    from oracle import orc
+    n_terms = len(w.term_off) - 1
+    probe = min(n_terms, 2000)
+    segs = slice_prefix(w, probe)
+    t0 = time.perf_counter()
+    r = orc.merge(segs, w.removed, decoded=False)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rate = r.postings_in / dt
+    want = int(min(n_terms, max(probe, probe * target_s / dt)))
+    segs = slice_prefix(w, want)
+    t0 = time.perf_counter()
+    r = orc.merge(segs, w.removed, decoded=False)
+    dt = time.perf_counter() - t0
+    return r.postings_in / dt, f"first {want} of {n_terms} terms over all {len(w.segments)} " \
+                               f"segments ({r.postings_in} postings, {dt:.1f} s, 1 thread)"
+
+
+def cpu_step_parallel(shards, removed, threads):
+    """All shards merged by `threads` workers (InvertedIndex.Merge, inverted_index.go:83-103)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import orc
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside orc_merge
+        n = sum(r.postings_in for r in ex.map(lambda s: orc.merge(s, removed, decoded=False), shards))
+    return n, time.perf_counter() - t0
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    orc.lib()
+    cores = os.cpu_count() or 1
+    w = synth.make_workload(min(a.terms, 200_000), a.segments,
+                            int(a.postings * min(a.terms, 200_000) / a.terms),
+                            removed_frac=a.removed_frac)
+    n_terms = len(w.term_off) - 1
+    # calibrate one shard, then size a step to ~10 s of wall time on all cores
+    probe = slice_prefix(w, 1000)
+    t0 = time.perf_counter()
+    r = orc.merge(probe, w.removed, decoded=False)
+    per_term = (time.perf_counter() - t0) / 1000
+    budget = 240.0 / max(1, a.steps + a.warmup)
+    step_terms = int(min(n_terms, max(cores * 200, min(10.0, budget) * cores / per_term)))
+    per_shard = max(1, step_terms // (cores * 4))
+    shards = [slice_prefix(w, per_shard, f) for f in range(0, step_terms - per_shard + 1, per_shard)]
+    for _ in range(min(a.warmup, 1)):
+        cpu_step_parallel(shards[:cores], w.removed, cores)
+    tot_n = tot_t = 0
+    for _ in range(a.steps):
+        n, dt = cpu_step_parallel(shards, w.removed, cores)
+        tot_n += n
+        tot_t += dt
+    value = tot_n / tot_t
+    sample = (f"{len(shards)} term-range shards x {per_shard} terms over {a.segments} segments "
+              f"({tot_n // a.steps} postings per step), {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev: int):
+        self.dev, self.proc, self.lines = dev, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def pin(arr: np.ndarray):
+    """Copy into page-locked host memory (torch owns it); returns (numpy view, keep-alive)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t.numpy(), t
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from inverted_index_2_b200.engine import Engine
+    eng = Engine(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+
+    # this rank's term-range shard: its own term set and postings (weak scaling)
+    w = synth.make_workload(a.terms, a.segments, a.postings, removed_frac=a.removed_frac,
+                            seed=0xC2 + 1000 * rank, terms_seed=0x1EE7 + rank)
+    dsegs = [eng.upload(s) for s in w.segments]
+    drem = eng.upload_removed(w.removed)
+    eng.sync()
+
+    def step():
+        res = eng.merge_dev(dsegs, drem, encode=True)
+        info = res.info()
+        out = (int(info.postings_in), int(info.postings_out), int(info.terms_count),
+               int(info.term_bytes), int(info.val_size))
+        res.release()
+        return out
+
+    for _ in range(a.warmup):
+        stats = step()
+    n_in, n_out, t_out, t_out_bytes, val_size = stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    eng.prof_enable(True)
+    barrier()
+    clocks.start()
+    l0 = eng.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    launches = eng.kernel_launches() - l0
+    clk = clocks.stop()
+    prof = eng.prof_read()
+    eng.prof_enable(False)
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([n_in], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_in = float(tot.item())
+    else:
+        total_in = float(n_in)
+    value = total_in * a.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (per launch, live CUDA events) ----
+    t_in = w.term_instances
+    t_in_bytes = int(sum(int(s.term_off[-1]) for s in w.segments))
+    alg = {
+        # K1: term bytes + term offsets + posting offsets in, 18 B of plan per instance out
+        "k1_merge_tiles": t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 18 * t_in,
+        # K2: plan + postings in, unioned postings + 16 B per group out
+        "k2_union": 14 * t_in + 4 * n_in + 4 * n_out + 16 * t_in + 4 * len(w.removed),
+        # K6: unioned postings in; term bytes/offsets, decoded postings and `_val` out
+        "k6_emit": 4 * n_out + 16 * t_in + t_out_bytes + 12 * t_out + 4 * n_out + val_size + 8 * t_out,
+    }
+    peak, peak_src = peaks()
+    roof = None
+    if prof:
+        top = max(prof, key=lambda e: e["ms"])
+        per_launch_ms = top["ms"] / max(1, top["count"])
+        b = alg.get(top["name"])
+        if b is not None and per_launch_ms > 0:
+            ach = b / (per_launch_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms}
+    pipeline_bytes = synth.algorithmic_bytes(n_in, n_out, t_in, t_in_bytes, a.segments, t_out,
+                                             t_out_bytes, len(w.removed))
+    pipe = {"algorithmic_bytes_per_step": pipeline_bytes,
+            "achieved_gbs": pipeline_bytes / (ms * 1e-3 / a.steps) / 1e9}
+    pipe["frac_of_peak"] = pipe["achieved_gbs"] / peak
+
+    # ---- end to end through the host-buffer C-ABI call (rank-local, same workload) ----
+    e2e = None
+    if not a.no_e2e:
+        keep, hsegs = [], []
+        for s in w.segments:
+            arrs = {}
+            for f in ("term_bytes", "term_off", "post", "post_off"):
+                arrs[f], k = pin(getattr(s, f))
+                keep.append(k)
+            hsegs.append(FlatSegment(arrs["term_bytes"], arrs["term_off"], s.mode, post=arrs["post"],
+                                     post_off=arrs["post_off"]))
+        hrem, k = pin(w.removed)
+        keep.append(k)
+        h2d = sum(x.term_bytes.nbytes + x.term_off.nbytes + x.post.nbytes + x.post_off.nbytes
+                  for x in hsegs) + hrem.nbytes
+        import ctypes as C
+
+        from inverted_index_2_b200 import _abi as A
+        from inverted_index_2_b200.flat import views_array
+        arr = views_array(hsegs)
+        out = A.MergeOut()
+
+        def e2e_step():
+            eng._check(eng.lib.ii2_merge(arr, len(hsegs), A.np_ptr(hrem, A.u32p), len(hrem), 0,
+                                         C.byref(out)), "merge")
+            d2h = (int(out.val_size) + 8 * int(out.terms_count) + 4 * (int(out.terms_count) + 1) +
+                   int(out.term_off[int(out.terms_count)]))
+            eng.lib.ii2_merge_out_free(C.byref(out))
+            return d2h
+        e_steps = max(1, min(a.steps, 5))
+        for _ in range(2):
+            d2h = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": total_in * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / e_steps,
+               "steps": e_steps, "api": "ii2_merge (host buffers, pinned)"}
+
+    verified = None
+    if a.verify and rank == 0:
+        res = eng.merge_dev(dsegs, drem, encode=True).download_merge(decoded=True)
+        terms, vals, poff = w.expected_union(w.removed)
+        etb, eoff = synth.gather_terms(w.term_bytes, w.term_off, terms)
+        verified = bool(np.array_equal(res.post, vals) and np.array_equal(res.post_off, poff) and
+                        np.array_equal(res.term_bytes, etb) and np.array_equal(res.term_off, eoff))
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, sample = cpu_rate_single(w, a.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "per_gpu": True,
+                       "l2": "inputs (>= 1.3 GB per step) larger than the 126 MB L2",
+                       "postings_in": n_in, "postings_out": n_out, "terms_out": t_out,
+                       "term_instances": t_in},
+            "roofline": roof, "pipeline": pipe, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clk,
+            "kernels": prof,
+        }
+        if verified is not None:
+            line["verified_full_size"] = verified
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,338 @@
+// runtime.cu — context / streams / memory pools / scan utility for libii2.
+#include <cstdarg>
+#include <map>
+#include <mutex>
+
+#include "runtime.cuh"
+
+namespace ii2 {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+static thread_local char t_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_last_error, sizeof(t_last_error), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------ context
+struct Ctx {
+  std::mutex m;
+  bool ready = false;
+  int device = -1;
+};
+static Ctx g_ctx;
+
+bool ctx_ready() { return g_ctx.ready; }
+
+int ctx_require() {
+  if (!g_ctx.ready) {
+    set_last_error("ii2_init has not succeeded: no CUDA device bound (there is no CPU fallback)");
+    return II2_ERR_NO_DEVICE;
+  }
+  // Each host thread needs the device current.
+  cudaError_t e = cudaSetDevice(g_ctx.device);
+  if (e != cudaSuccess) {
+    set_last_error("cudaSetDevice(%d): %s", g_ctx.device, cudaGetErrorString(e));
+    return II2_ERR_CUDA;
+  }
+  return II2_OK;
+}
+
+struct ThreadStream {
+  cudaStream_t own = nullptr;
+  cudaStream_t user = nullptr;
+  bool use_user = false;
+  ~ThreadStream() {
+    // Streams are intentionally not destroyed at thread exit: the CUDA context may
+    // already be torn down when thread-local destructors run at process exit.
+  }
+};
+static thread_local ThreadStream t_stream;
+
+cudaStream_t cur_stream() {
+  if (t_stream.use_user) return t_stream.user;
+  if (!t_stream.own) cudaStreamCreateWithFlags(&t_stream.own, cudaStreamNonBlocking);
+  return t_stream.own;
+}
+
+// ------------------------------------------------------------------ pinned pool
+struct PinnedPool {
+  std::mutex m;
+  std::map<void*, size_t> live;                    // ptr -> class bytes
+  std::map<size_t, std::vector<void*>> free_list;  // class bytes -> ptrs
+  size_t cached = 0;
+  static constexpr size_t kMaxCached = size_t(8) << 30;
+};
+static PinnedPool g_pinned;
+
+static size_t size_class(size_t bytes) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  // above 64 MiB round to 16 MiB granularity instead of doubling
+  if (c > (size_t(64) << 20)) {
+    const size_t g = size_t(16) << 20;
+    c = (bytes + g - 1) / g * g;
+  }
+  return c;
+}
+
+void* pinned_alloc(size_t bytes) {
+  size_t c = size_class(bytes ? bytes : 1);
+  {
+    std::lock_guard<std::mutex> lk(g_pinned.m);
+    auto it = g_pinned.free_list.find(c);
+    if (it != g_pinned.free_list.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      g_pinned.cached -= c;
+      g_pinned.live[p] = c;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, c, cudaHostAllocDefault) != cudaSuccess) {
+    set_last_error("cudaHostAlloc(%zu) failed", c);
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_pinned.m);
+  g_pinned.live[p] = c;
+  return p;
+}
+
+void pinned_free(void* p) {
+  if (!p) return;
+  size_t c = 0;
+  bool release = false;
+  {
+    std::lock_guard<std::mutex> lk(g_pinned.m);
+    auto it = g_pinned.live.find(p);
+    if (it == g_pinned.live.end()) return;  // not ours
+    c = it->second;
+    g_pinned.live.erase(it);
+    if (g_pinned.cached + c <= PinnedPool::kMaxCached) {
+      g_pinned.free_list[c].push_back(p);
+      g_pinned.cached += c;
+    } else {
+      release = true;
+    }
+  }
+  if (release) cudaFreeHost(p);
+}
+
+static void pinned_drain() {
+  std::lock_guard<std::mutex> lk(g_pinned.m);
+  for (auto& kv : g_pinned.free_list)
+    for (void* p : kv.second) cudaFreeHost(p);
+  g_pinned.free_list.clear();
+  g_pinned.cached = 0;
+}
+
+// ------------------------------------------------------------------ scan (3 phases)
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint64_t* __restrict__ d,
+                                                              uint64_t n,
+                                                              uint64_t* __restrict__ bsum) {
+  __shared__ uint64_t ws[kScanThreads / 32 + 2];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    uint64_t idx = base + (uint64_t)i * kScanThreads + threadIdx.x;
+    if (idx < n) acc += d[idx];
+  }
+  uint64_t total;
+  block_exclusive_scan(acc, ws, total);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of bsum[0..nb) in place, total -> *d_total
+__global__ void __launch_bounds__(1024) k_scan_single(uint64_t* __restrict__ a, uint64_t nb,
+                                                      uint64_t* __restrict__ d_total) {
+  __shared__ uint64_t ws[1024 / 32 + 2];
+  uint64_t carry = 0;
+  for (uint64_t base = 0; base < nb; base += 1024) {
+    uint64_t idx = base + threadIdx.x;
+    uint64_t v = idx < nb ? a[idx] : 0;
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan(v, ws, total);
+    if (idx < nb) a[idx] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && d_total) *d_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(uint64_t* __restrict__ d, uint64_t n,
+                                                             const uint64_t* __restrict__ bsum) {
+  __shared__ uint64_t ws[kScanThreads / 32 + 2];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint64_t v[kScanItems];
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    v[i] = (base + i < n) ? d[base + i] : 0;
+    acc += v[i];
+  }
+  uint64_t total;
+  uint64_t ex = block_exclusive_scan(acc, ws, total) + bsum[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    if (base + i < n) d[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+// single CTA: m arrays of length n laid out back to back, each scanned independently
+__global__ void __launch_bounds__(1024) k_scan_multi(const uint64_t* a, uint64_t* out, uint64_t n,
+                                                     int m, uint64_t* __restrict__ totals) {
+  __shared__ uint64_t ws[1024 / 32 + 2];
+  for (int j = 0; j < m; j++) {
+    const uint64_t* arr = a + (uint64_t)j * n;
+    uint64_t* dst = out + (uint64_t)j * n;
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < n; base += 1024) {
+      uint64_t idx = base + threadIdx.x;
+      uint64_t v = idx < n ? arr[idx] : 0;
+      uint64_t total;
+      uint64_t ex = block_exclusive_scan(v, ws, total);
+      if (idx < n) dst[idx] = carry + ex;
+      carry += total;
+    }
+    if (threadIdx.x == 0 && totals) totals[j] = carry;
+  }
+}
+
+int exclusive_scan_multi_u64(const uint64_t* in, uint64_t* out, uint64_t n, int m,
+                             uint64_t* d_totals, cudaStream_t s) {
+  k_scan_multi<<<1, 1024, 0, s>>>(in, out, n, m, d_totals);
+  II2_LAUNCHED();
+  return II2_OK;
+}
+
+int exclusive_scan_u64(uint64_t* d, uint64_t n, uint64_t* d_total, cudaStream_t s) {
+  if (n == 0) {
+    if (d_total) II2_CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(uint64_t), s));
+    return II2_OK;
+  }
+  if (n <= 16384) {
+    k_scan_single<<<1, 1024, 0, s>>>(d, n, d_total);
+    II2_LAUNCHED();
+    return II2_OK;
+  }
+  uint64_t nb = (n + kScanTile - 1) / kScanTile;
+  DevBuf<uint64_t> bsum;
+  II2_TRY(bsum.alloc(nb, s));
+  // k_scan_reduce reads strided (coalesced), k_scan_apply reads blocked per thread
+  k_scan_reduce<<<(unsigned)nb, kScanThreads, 0, s>>>(d, n, bsum.p);
+  II2_LAUNCHED();
+  k_scan_single<<<1, 1024, 0, s>>>(bsum.p, nb, d_total);
+  II2_LAUNCHED();
+  k_scan_apply<<<(unsigned)nb, kScanThreads, 0, s>>>(d, n, bsum.p);
+  II2_LAUNCHED();
+  return II2_OK;
+}
+
+}  // namespace ii2
+
+// ------------------------------------------------------------------ C-ABI: lifecycle
+using namespace ii2;
+
+extern "C" {
+
+int ii2_abi_version(void) { return II2_ABI_VERSION; }
+
+const char* ii2_strerror(int code) {
+  switch (code) {
+    case II2_OK: return "ok";
+    case II2_ERR_INVALID: return "invalid argument";
+    case II2_ERR_NOMEM: return "out of memory";
+    case II2_ERR_CUDA: return "CUDA error";
+    case II2_ERR_NO_DEVICE: return "no CUDA device (ii2_init missing or failed; there is no CPU fallback)";
+    case II2_ERR_BITMASK_OOB: return "bitmask is out of bound";
+    case II2_ERR_CORRUPT: return "corrupt encoded data";
+    case II2_ERR_UNSUPPORTED: return "input exceeds an implementation limit";
+    default: return "unknown error";
+  }
+}
+
+const char* ii2_last_error(void) { return t_last_error; }
+
+int ii2_init(const int* devices, int ndev) {
+  std::lock_guard<std::mutex> lk(g_ctx.m);
+  if (ndev > 1) {
+    set_last_error("one process drives one GPU: pass exactly one device (got %d)", ndev);
+    return II2_ERR_INVALID;
+  }
+  int dev = (devices && ndev == 1) ? devices[0] : 0;
+  if (g_ctx.ready) {
+    if (g_ctx.device == dev) return II2_OK;
+    set_last_error("already initialised on device %d", g_ctx.device);
+    return II2_ERR_INVALID;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_last_error("no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    return II2_ERR_NO_DEVICE;
+  }
+  if (dev < 0 || dev >= count) {
+    set_last_error("device %d out of range (have %d)", dev, count);
+    return II2_ERR_INVALID;
+  }
+  II2_CUDA_TRY(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  II2_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) {
+    set_last_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
+                   prop.minor);
+    return II2_ERR_NO_DEVICE;
+  }
+  // Keep freed stream-ordered memory in the pool instead of returning it to the driver.
+  cudaMemPool_t pool;
+  II2_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thresh = UINT64_MAX;
+  II2_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  g_ctx.device = dev;
+  g_ctx.ready = true;
+  return II2_OK;
+}
+
+int ii2_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_ctx.m);
+  if (!g_ctx.ready) return II2_OK;
+  cudaDeviceSynchronize();
+  pinned_drain();
+  g_ctx.ready = false;
+  return II2_OK;
+}
+
+int ii2_set_stream(void* cuda_stream) {
+  t_stream.user = static_cast<cudaStream_t>(cuda_stream);
+  t_stream.use_user = cuda_stream != nullptr;
+  return II2_OK;
+}
+
+uint64_t ii2_kernel_launches(void) { return g_kernel_launches.load(); }
+
+void ii2_free(void* p) { pinned_free(p); }
+
+int ii2_sync(void) {
+  II2_TRY(ctx_require());
+  II2_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
+  return II2_OK;
+}
+
+uint32_t ii2_shard_key(const uint8_t* term, size_t len) {
+  // shardKey, shard.go:362-378
+  uint16_t key = 0;
+  if (len >= 2) key = (uint16_t)(((uint16_t)term[0] << 8) + term[1]);
+  return (uint32_t)(key >> 6);
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+"""GPU parity tests: the CUDA path behind the C-ABI (libii2.so) against the CPU oracle on the
+same seeded inputs, bit-exact (integer / byte work — no tolerance anywhere), plus the
+reference's own known-answer vectors run through the host mirror on the CUDA engine."""
+import threading
+
+import numpy as np
+import pytest
+
+from inverted_index_2_b200 import _abi as A
+from inverted_index_2_b200 import synth
+from inverted_index_2_b200.flat import FlatSegment
+from scenario import load_vectors, run_index_scenario, run_shard_scenario
+
+pytestmark = pytest.mark.gpu
+V = load_vectors()
+
+
+def assert_merge_equal(got, exp, decoded=True):
+    assert got.terms_count == exp.terms_count
+    assert np.array_equal(got.term_off, exp.term_off)
+    assert np.array_equal(got.term_bytes, exp.term_bytes)
+    assert got.val_size == exp.val_size
+    assert np.array_equal(got.val_off, exp.val_off)
+    assert np.array_equal(got.val_bytes, exp.val_bytes)
+    assert got.min_term == exp.min_term and got.max_term == exp.max_term
+    assert got.terms_merged == exp.terms_merged
+    assert got.postings_in == exp.postings_in
+    assert got.postings_out == exp.postings_out
+    if decoded:
+        assert np.array_equal(got.post_off, exp.post_off)
+        assert np.array_equal(got.post, exp.post)
+
+
+def assert_read_equal(got, exp):
+    assert got.n_terms == exp.n_terms
+    assert np.array_equal(got.term_off, exp.term_off)
+    assert np.array_equal(got.term_bytes, exp.term_bytes)
+    assert np.array_equal(got.post_off, exp.post_off)
+    assert np.array_equal(got.post, exp.post)
+
+
+# ---------------------------------------------------------------- reference known answers
+@pytest.mark.parametrize("sc", V["shard_scenarios"], ids=lambda s: s["name"])
+def test_shard_scenarios(engine, sc):
+    run_shard_scenario(engine, sc)
+
+
+@pytest.mark.parametrize("sc", V["index_scenarios"], ids=lambda s: s["name"])
+def test_index_scenarios(engine, sc):
+    run_index_scenario(engine, sc)
+
+
+@pytest.mark.parametrize("w", V["writer"], ids=lambda s: s["name"])
+def test_writer_reader_roundtrip(engine, w):
+    items = [(t.encode(), v) for t, v in w["items"]]
+    if w["mode"] == "direct":
+        seg = FlatSegment(*FlatSegment._pack_terms([t for t, _ in items]), A.II2_SEG_DIRECT,
+                          val_off=np.array([v[0] for _, v in items], dtype=np.uint64))
+    else:
+        seg = FlatSegment.from_items(items).to_val(engine.intcomp_encode_batch)
+        assert seg.val_off[1] == seg.val_off[2]  # empty list -> zero bytes (writer_test.go:15)
+    assert engine.read_range([seg]).items() == items
+
+
+@pytest.mark.parametrize("b", V["bitmask"], ids=lambda s: s["name"])
+def test_bitmask_known_answers(engine, b):
+    bm = engine.bitmask(b["init"])
+    enc = [bm.put(p) for p in b["puts"]]
+    assert bm.get(enc[0] + enc[1]).tolist() == b["get_concat_first"]
+    assert bm.get(enc[1]).tolist() == b["get_second_index_order"]
+    assert sorted(bm.get(enc[1]).tolist()) == b["get_second_sorted"]
+    assert bm.all_values().tolist() == b["all_values"]
+
+
+# ---------------------------------------------------------------- merge vs oracle
+MERGE_CASES = [
+    # terms, segs, postings, universe, removed_frac, presence
+    (50, 2, 200, 1 << 8, 0.0, 0.7),
+    (50, 3, 400, 1 << 8, 0.3, 0.7),
+    (3000, 4, 20000, 1 << 12, 0.05, 0.5),
+    (3000, 64, 150000, 1 << 16, 0.05, 0.5),
+    (20000, 8, 400000, 1 << 16, 0.05, 0.5),
+    (1000, 256, 300000, 1 << 14, 0.05, 0.3),
+    (200, 16, 400000, 1 << 20, 0.05, 0.9),   # long lists: warp + CTA union paths
+    (100000, 5, 600000, 1 << 24, 0.0, 0.5),
+    (100000, 5, 600000, 1 << 24, 0.05, 0.5),  # removed set answered from the bitmap
+]
+
+
+@pytest.mark.parametrize("case", MERGE_CASES, ids=lambda c: "t%d_s%d_p%d_u%d_r%g" % c[:5])
+def test_merge_matches_oracle(engine, orc, case):
+    nt, ns, npost, uni, rf, pres = case
+    w = synth.make_workload(nt, ns, npost, universe=uni, removed_frac=rf, presence=pres,
+                            seed=nt + ns, max_len=4096 if nt <= 200 else 64)
+    exp = orc.merge(w.segments, w.removed, decoded=True)
+    got = engine.merge(w.segments, w.removed, decoded=True)
+    assert_merge_equal(got, exp)
+    # independent numpy answer (no oracle code involved)
+    terms, vals, poff = w.expected_union(w.removed)
+    assert np.array_equal(got.post, vals) and np.array_equal(got.post_off, poff)
+
+
+def test_merge_all_segment_modes(engine, orc):
+    """DECODED, raw `_val` (file/reader.go:79-100) and direct mode (:73-77) inputs mixed."""
+    w = synth.make_workload(5000, 6, 60000, universe=1 << 14, seed=7)
+    segs = list(w.segments)
+    segs[1] = segs[1].to_val(orc.intcomp_encode_batch)
+    segs[4] = segs[4].to_val(orc.intcomp_encode_batch)
+    tb, off = synth.gather_terms(w.term_bytes, w.term_off, np.arange(0, 5000, 3))
+    segs.append(FlatSegment(tb, off, A.II2_SEG_DIRECT,
+                            val_off=np.full(len(off) - 1, (7 << 32) | 123, dtype=np.uint64)))
+    exp = orc.merge(segs, w.removed, decoded=True)
+    got = engine.merge(segs, w.removed, decoded=True)
+    assert_merge_equal(got, exp)
+
+
+def test_merged_segment_reads_back(engine, orc):
+    """The `_val` stream the GPU writes decodes (GPU and oracle decoder) to the merged lists."""
+    w = synth.make_workload(4000, 5, 200000, universe=1 << 18, seed=11, max_len=1000)
+    got = engine.merge(w.segments, w.removed, decoded=True)
+    seg = got.to_segment()
+    for backend in (engine, orc):
+        rr = backend.read_range([seg])
+        assert np.array_equal(rr.post, got.post) and np.array_equal(rr.post_off, got.post_off)
+        assert np.array_equal(rr.term_bytes, got.term_bytes)
+
+
+def test_single_source_passthrough_quirk(engine, orc):
+    """Survey Q4: a term seen in ONE segment is neither sorted nor deduped
+    (file/types.go:14-22 only runs on equal terms); shared terms are."""
+    a = FlatSegment.from_items([(b"only_a", [9, 3, 3, 7]), (b"shared", [5, 1, 5])])
+    b = FlatSegment.from_items([(b"only_b", [2, 2, 1]), (b"shared", [1, 9, 9])])
+    exp = orc.merge([a, b], None, decoded=True)
+    got = engine.merge([a, b], None, decoded=True)
+    assert_merge_equal(got, exp)
+    assert got.as_dict() == {b"only_a": [9, 3, 3, 7], b"only_b": [2, 2, 1], b"shared": [1, 5, 9]}
+    # one segment alone: everything passes through, removed values filtered in place
+    exp1 = orc.merge([a], np.array([3], dtype=np.uint32), decoded=True)
+    got1 = engine.merge([a], np.array([3], dtype=np.uint32), decoded=True)
+    assert_merge_equal(got1, exp1)
+    assert got1.as_dict() == {b"only_a": [9, 7], b"shared": [5, 1, 5]}
+
+
+def test_merge_edge_cases(engine, orc):
+    empty = FlatSegment.from_items([])
+    one = FlatSegment.from_items([(b"", [4]), (b"a", []), (b"b", [1, 2])])
+    two = FlatSegment.from_items([(b"", [4, 5]), (b"a", []), (b"c" * 300, [8])])
+    for segs, removed in [
+        ([], None),
+        ([empty], None),
+        ([empty, empty], None),
+        ([one], None),
+        ([one, two], None),
+        ([one, two, empty], np.array([4, 5, 8, 1, 2], dtype=np.uint32)),  # everything removed
+        ([one, two], np.array([4, 4, 4, 8], dtype=np.uint32)),            # duplicates in removed (Q6)
+    ]:
+        if removed is not None:
+            removed = np.sort(removed)
+        exp = orc.merge(segs, removed, decoded=True)
+        got = engine.merge(segs, removed, decoded=True)
+        assert_merge_equal(got, exp)
+    # all removed -> no segment is written (lazy writer, shard.go:197-205) but min/max are set (Q3)
+    got = engine.merge([one, two], np.array([1, 2, 4, 5, 8], dtype=np.uint32), decoded=True)
+    assert got.terms_count == 0 and got.val_size == 0
+    assert got.min_term == b"" and got.max_term == b"c" * 300
+
+
+def test_merge_long_and_similar_terms(engine, orc):
+    """Terms that only differ past the 16-byte key window, 1-byte terms (shard 0000, Q7),
+    prefixes of one another, and > 2048 instances sharing one long prefix."""
+    rng = np.random.default_rng(5)
+    base = b"commonprefix/" * 3
+    pool = sorted({base + bytes(rng.integers(97, 101, size=int(rng.integers(0, 12))).tolist())
+                   for _ in range(3000)} | {b"a", b"b", b"ab", b"abc", b"\x00", b"\x00\x00", b"\xff"})
+    segs = []
+    for s in range(5):
+        pick = [t for t in pool if rng.random() < 0.6]
+        segs.append(FlatSegment.from_items(
+            [(t, sorted(set(rng.integers(0, 500, size=int(rng.integers(1, 6))).tolist())))
+             for t in pick]))
+    removed = np.arange(0, 500, 7, dtype=np.uint32)
+    assert_merge_equal(engine.merge(segs, removed, decoded=True),
+                       orc.merge(segs, removed, decoded=True))
+    lo, hi = pool[len(pool) // 3], pool[2 * len(pool) // 3]
+    assert_read_equal(engine.read_range(segs, lo, hi), orc.read_range(segs, lo, hi))
+
+
+def test_heavy_terms_multi_cta_union(engine, orc):
+    """Lists far larger than one CTA's shared memory (survey §7 hard part 2): the global
+    bitonic path; also a heavy single-source list."""
+    rng = np.random.default_rng(9)
+    segs = []
+    for s in range(6):
+        items = [(b"heavy", np.unique(rng.integers(0, 1 << 20, size=60000)).tolist()),
+                 (b"medium", np.unique(rng.integers(0, 1 << 16, size=3000)).tolist()),
+                 (b"small%d" % s, [s, s + 1])]
+        if s == 0:
+            items.append((b"solo_heavy", rng.integers(0, 1 << 20, size=50000).tolist()))
+        segs.append(FlatSegment.from_items(sorted(items)))
+    removed = np.unique(rng.integers(0, 1 << 20, size=50000)).astype(np.uint32)
+    assert_merge_equal(engine.merge(segs, removed, decoded=True),
+                       orc.merge(segs, removed, decoded=True))
+
+
+# ---------------------------------------------------------------- range reads vs oracle
+def test_read_range_matches_oracle(engine, orc):
+    w = synth.make_workload(20000, 12, 300000, universe=1 << 16, seed=21)
+    n = 20000
+    t = lambda i: synth.term_at(w.term_bytes, w.term_off, i)
+    bounds = [(None, None), (t(0), t(n - 1)), (t(100), t(100)), (t(5000), t(5200)),
+              (None, t(3000)), (t(15000), None), (t(9000) + b"~", t(9100) + b"~"),
+              (b"zzzzzzzzzzzzzzzzzzzzzzzz", None), (None, b"A"), (t(300), t(200)), (b"", None)]
+    for lo, hi in bounds:
+        assert_read_equal(engine.read_range(w.segments, lo, hi), orc.read_range(w.segments, lo, hi))
+    # benchmark composition of config 3: read + Merge-style filter (survey Q2)
+    for lo, hi in bounds[:6]:
+        assert_read_equal(engine.read_range(w.segments, lo, hi, removed=w.removed),
+                          orc.read_range(w.segments, lo, hi, removed=w.removed))
+
+
+def test_read_keeps_empty_lists(engine, orc):
+    seg = FlatSegment.from_items([(b"t1", [10, 500, 300]), (b"t2", []), (b"t3", [66, 5513])])
+    got = engine.read_range([seg])
+    assert got.items() == [(b"t1", [10, 500, 300]), (b"t2", []), (b"t3", [66, 5513])]
+    assert_read_equal(got, orc.read_range([seg]))
+
+
+# ---------------------------------------------------------------- device-resident API
+def test_resident_pipeline_and_multipass(engine, orc):
+    """Resident segments; a result adopted as a segment and merged again equals the one-pass
+    merge (inputs are sorted-unique, so pass structure is invisible)."""
+    w = synth.make_workload(8000, 9, 150000, universe=1 << 15, seed=33)
+    dsegs = [engine.upload(s) for s in w.segments]
+    drem = engine.upload_removed(w.removed)
+    one = engine.merge_dev(dsegs, drem, encode=True).download_merge(decoded=True)
+    assert_merge_equal(one, orc.merge(w.segments, w.removed, decoded=True))
+    r1 = engine.merge_dev(dsegs[:4], drem, encode=False).to_segment()
+    r2 = engine.merge_dev(dsegs[4:], drem, encode=False).to_segment()
+    two = engine.merge_dev([r1, r2], drem, encode=True).download_merge(decoded=True)
+    assert np.array_equal(two.val_bytes, one.val_bytes) and np.array_equal(two.post, one.post)
+    assert np.array_equal(two.term_bytes, one.term_bytes)
+    rd = engine.read_range_dev(dsegs, None, None).download_read()
+    assert_read_equal(rd, orc.read_range(w.segments))
+    info = engine.read_range_dev(dsegs, None, None, drem).info()
+    assert info.postings_out == one.postings_out and info.terms_count == one.terms_count
+
+
+def test_concurrent_callers(engine, orc):
+    """The reference calls this path from many goroutines (inverted_index.go:83-103,
+    shard_test.go:236-247): concurrent C-ABI calls from host threads."""
+    ws = [synth.make_workload(2000, 4, 30000, universe=1 << 12, seed=100 + i) for i in range(8)]
+    exp = [orc.merge(w.segments, w.removed, decoded=True) for w in ws]
+    got = [None] * len(ws)
+    errs = []
+
+    def run(i):
+        try:
+            for _ in range(3):
+                got[i] = engine.merge(ws[i].segments, ws[i].removed, decoded=True)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(ws))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for g, e in zip(got, exp):
+        assert_merge_equal(g, e)
+
+
+# ---------------------------------------------------------------- codec vs oracle
+def _lists_to_flat(lists):
+    off = np.zeros(len(lists) + 1, dtype=np.uint64)
+    np.cumsum([len(x) for x in lists], out=off[1:])
+    post = np.concatenate([np.asarray(x, dtype=np.uint32) for x in lists]) if lists else \
+        np.zeros(0, dtype=np.uint32)
+    return post.astype(np.uint32), off
+
+
+def test_intcomp_matches_oracle(engine, orc):
+    rng = np.random.default_rng(3)
+    lists = [[], [0], [0xFFFFFFFF], [10, 500, 300], [5] * 200, list(range(128)), list(range(129)),
+             list(range(127)), [0xFFFFFFFF, 0, 0xFFFFFFFF, 1] * 64]
+    for n in (1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 1000, 4096, 70000):
+        for gap in (1, 16, 4096):
+            lists.append(np.cumsum(rng.integers(1, 2 * gap + 1, size=n)).astype(np.uint32).tolist())
+        lists.append(rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32).tolist())
+    post, off = _lists_to_flat(lists)
+    ew, eo = orc.intcomp_encode_batch(post, off)
+    gw, go = engine.intcomp_encode_batch(post, off)
+    assert np.array_equal(go, eo) and np.array_equal(gw, ew)
+    dv, do = engine.intcomp_decode_batch(ew, eo)
+    assert np.array_equal(do, off) and np.array_equal(dv, post)
+    ov, oo = orc.intcomp_decode_batch(gw, go)
+    assert np.array_equal(oo, off) and np.array_equal(ov, post)
+
+
+def test_intcomp_rejects_corrupt(engine):
+    from inverted_index_2_b200.engine import EngineError
+    words = np.array([256, 2, 0, 0], dtype=np.uint32)  # section length below its own header
+    with pytest.raises(EngineError) as e:
+        engine.intcomp_decode_batch(words, np.array([0, 4], dtype=np.uint64))
+    assert e.value.code == A.II2_ERR_CORRUPT
+
+
+# ---------------------------------------------------------------- bitmask vs oracle
+@pytest.mark.parametrize("L", [16, 64, 1024, 4096, 5000, 70000, 300000])
+def test_bitmask_matches_oracle(engine, orc, L):
+    """file/bitmask_test.go:15-21 shape: dictionary = universe of 2L ids, values = random half."""
+    rng = np.random.default_rng(L)
+    universe = np.sort(rng.choice(1 << 26, size=2 * L, replace=False)).astype(np.uint32)
+    vals = rng.permutation(universe)[:L]
+    g, o = engine.bitmask(universe), orc.Bitmask(universe)
+    eg, eo = g.put(vals), o.put(vals, fast=True)
+    assert eg == eo
+    assert np.array_equal(g.get(eo), o.get(eo))
+    assert np.array_equal(np.sort(g.get(eg)), np.sort(vals))
+    # grow-on-miss from an empty dictionary, duplicates inside and across puts
+    g2, o2 = engine.bitmask(), orc.Bitmask()
+    for k in range(3):
+        batch = np.concatenate([vals[k::3], vals[: L // 4], rng.integers(0, 50, size=20).astype(np.uint32)])
+        assert g2.put(batch) == o2.put(batch, fast=True)
+        assert np.array_equal(g2.all_values(), o2.all_values())
+    assert np.array_equal(g2.get(eg[:0] + g2.put(vals)), o2.get(o2.put(vals, fast=True)))
+
+
+def test_bitmask_slow_oracle_shape(engine, orc):
+    """Against the literal O(L*D) slices.Index restatement, incl. duplicate dictionary entries."""
+    init = [7, 3, 7, 9, 3]
+    g, o = engine.bitmask(init), orc.Bitmask(init)
+    for batch in ([3, 7, 11, 11, 9], [], [100, 3, 100, 200], [7]):
+        assert g.put(batch) == o.put(batch, fast=False)
+    assert g.all_values().tolist() == o.all_values().tolist() == [7, 3, 7, 9, 3, 11, 100, 200]
+    enc = o.put([9, 200, 7], fast=False)
+    assert g.get(enc).tolist() == o.get(enc).tolist()
+
+
+def test_bitmask_full_chunk_run_container(engine, orc):
+    """A full 65536-index chunk becomes the run container [0,65535] (run cookie, odd-sized
+    header); with >= 4 containers the offset header returns."""
+    for n in (65536, 65536 + 10, 5 * 65536 + 4097):
+        vals = np.arange(n, dtype=np.uint32) * 3
+        g, o = engine.bitmask(), orc.Bitmask()
+        eg, eo = g.put(vals), o.put(vals, fast=True)
+        assert eg == eo
+        assert np.array_equal(g.get(eg), vals) and np.array_equal(o.get(eg), vals)
+
+
+def test_bitmask_out_of_bound_and_trailing_bytes(engine, orc):
+    from inverted_index_2_b200.engine import EngineError
+    big = engine.bitmask([5, 6, 7])
+    enc = big.put([7])
+    assert big.get(enc + b"\x01\x02\x03garbage").tolist() == [7]  # bitmask_test.go:44-46
+    small = engine.bitmask([5])
+    with pytest.raises(EngineError) as e:
+        small.get(enc)
+    assert e.value.code == A.II2_ERR_BITMASK_OOB
+    with pytest.raises(EngineError) as e:
+        small.get(b"\x00\x01\x02\x03\x04")
+    assert e.value.code == A.II2_ERR_CORRUPT
