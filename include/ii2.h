@@ -87,6 +87,17 @@ const char* ii2_last_error(void);
 int ii2_set_stream(void* cuda_stream);
 /* Number of kernels this library launched since ii2_init (all threads). */
 uint64_t ii2_kernel_launches(void);
+/* Instrumentation for bench.py's roofline: while enabled, every kernel phase of the
+ * pipelines is bracketed by CUDA events on the launching stream.  ii2_prof_read
+ * aggregates by phase name (total ms, number of launches) since the last enable and
+ * returns the number of entries written (<= cap), or a negative error. */
+typedef struct ii2_prof_entry {
+  const char* name;
+  double ms;
+  uint64_t count;
+} ii2_prof_entry;
+int ii2_prof_enable(int on);
+int ii2_prof_read(ii2_prof_entry* out, int cap);
 /* Generic release for buffers documented as "free with ii2_free". */
 void ii2_free(void* p);
 

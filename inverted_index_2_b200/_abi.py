@@ -94,6 +94,10 @@ class ResultInfo(C.Structure):
     ]
 
 
+class ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_double), ("count", C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol include/ii2.h declares.
 PROTOTYPES = {
     "ii2_init": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
@@ -103,6 +107,8 @@ PROTOTYPES = {
     "ii2_last_error": (C.c_char_p, []),
     "ii2_set_stream": (C.c_int, [C.c_void_p]),
     "ii2_kernel_launches": (C.c_uint64, []),
+    "ii2_prof_enable": (C.c_int, [C.c_int]),
+    "ii2_prof_read": (C.c_int, [C.POINTER(ProfEntry), C.c_int]),
     "ii2_free": (None, [C.c_void_p]),
     "ii2_merge": (C.c_int, [C.POINTER(SegView), C.c_int, u32p, C.c_uint64, C.c_uint32,
                             C.POINTER(MergeOut)]),

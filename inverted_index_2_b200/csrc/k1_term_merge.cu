@@ -486,6 +486,7 @@ int k1_build_plan(MergePlan& plan, cudaStream_t s) {
   DevBuf<uint32_t> split;
   II2_TRY(split.alloc(S ? S : 1, s));
 
+  ProfScope split_scope("k1_split", s);
   if (S > 0) {
     size_t smem = (size_t)S * (8 + 4 + 2) + 16;
     static bool attr1 = false;
@@ -515,6 +516,8 @@ int k1_build_plan(MergePlan& plan, cudaStream_t s) {
     }
     II2_CUDA_TRY(cudaMemsetAsync(plan.bk_P() + B, 0, 8, s));
     II2_CUDA_TRY(cudaMemsetAsync(plan.bk_D() + B, 0, 8, s));
+    split_scope.end();
+    ProfScope scope("k1_merge_tiles", s);
     k1_merge_tiles<<<B, K1_THREADS, smem, s>>>(plan.segs, k, plan.part.p, plan.bk_pos.p,
                                                plan.bk_cpl.p, plan.ord_inst.p, plan.src_ptr.p,
                                                plan.src_len.p, plan.gsz.p, plan.bk_P(), plan.bk_D());

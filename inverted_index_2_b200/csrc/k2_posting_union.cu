@@ -498,8 +498,11 @@ int k2_union(const MergePlan& plan, const RemovedSet& rem, bool want_enc, bool k
   a.large_len = large_len.p;
   a.n_large = d_n_large;
 
-  k2_union_kernel<<<B, K2_THREADS, 0, s>>>(a);
-  II2_LAUNCHED();
+  {
+    ProfScope scope("k2_union", s);
+    k2_union_kernel<<<B, K2_THREADS, 0, s>>>(a);
+    II2_LAUNCHED();
+  }
   // optimistic: scan right away; redone only if large groups were deferred
   II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
   uint64_t h_tot[5];
@@ -507,6 +510,7 @@ int k2_union(const MergePlan& plan, const RemovedSet& rem, bool want_enc, bool k
   II2_CUDA_TRY(cudaStreamSynchronize(s));
   const uint32_t h_nl = (uint32_t)h_tot[4];
   if (h_nl > 0) {
+    ProfScope scope("k2_large", s);
     std::vector<uint64_t> lens(h_nl);
     II2_CUDA_TRY(cudaMemcpyAsync(lens.data(), large_len.p, (size_t)h_nl * 8,
                                  cudaMemcpyDeviceToHost, s));

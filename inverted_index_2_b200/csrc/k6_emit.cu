@@ -157,6 +157,7 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, bool want_decoded, bool wa
   a.o_post_off = out.post_off.p;
   a.o_val_words = out.val_words.p;
   a.o_val_off = out.val_off.p;
+  ProfScope scope("k6_emit", s);
   k6_emit_kernel<<<plan.n_buckets, K6_THREADS, 0, s>>>(a);
   II2_LAUNCHED();
   return II2_OK;

@@ -131,6 +131,52 @@ static void pinned_drain() {
   g_pinned.cached = 0;
 }
 
+// ------------------------------------------------------------------ instrumentation
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+struct Prof {
+  std::mutex m;
+  std::atomic<bool> on{false};
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> spare;
+};
+static Prof g_prof;
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : s(stream), slot(-1) {
+  if (!g_prof.on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof.m);
+  ProfRec r;
+  r.name = name;
+  for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+    if (!g_prof.spare.empty()) {
+      *e = g_prof.spare.back();
+      g_prof.spare.pop_back();
+    } else if (cudaEventCreate(e) != cudaSuccess) {
+      return;
+    }
+  }
+  cudaEventRecord(r.e0, s);
+  slot = (int)g_prof.recs.size();
+  g_prof.recs.push_back(r);
+}
+
+void ProfScope::end() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof.m);
+  if (slot < (int)g_prof.recs.size()) cudaEventRecord(g_prof.recs[slot].e1, s);
+  slot = -1;
+}
+
+static void prof_reset_locked() {
+  for (ProfRec& r : g_prof.recs) {
+    g_prof.spare.push_back(r.e0);
+    g_prof.spare.push_back(r.e1);
+  }
+  g_prof.recs.clear();
+}
+
 // ------------------------------------------------------------------ scan (3 phases)
 constexpr int kScanThreads = 512;
 constexpr int kScanItems = 8;
@@ -319,6 +365,38 @@ int ii2_set_stream(void* cuda_stream) {
 }
 
 uint64_t ii2_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int ii2_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.m);
+  prof_reset_locked();
+  g_prof.on.store(on != 0);
+  return II2_OK;
+}
+
+int ii2_prof_read(ii2_prof_entry* out, int cap) {
+  if (cap < 0 || (cap && !out)) return II2_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(g_prof.m);
+  int n = 0;
+  for (ProfRec& r : g_prof.recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int j = 0;
+    while (j < n && strcmp(out[j].name, r.name) != 0) j++;
+    if (j == n) {
+      if (n == cap) continue;
+      out[n].name = r.name;
+      out[n].ms = 0;
+      out[n].count = 0;
+      n++;
+    }
+    out[j].ms += ms;
+    out[j].count += 1;
+  }
+  return n;
+}
 
 void ii2_free(void* p) { pinned_free(p); }
 

@@ -50,6 +50,16 @@ struct DevBuf {
   T* take() { T* q = p; p = nullptr; n = 0; return q; }
 };
 
+// Instrumentation (ii2_prof_enable / ii2_prof_read): CUDA events around a kernel phase on the
+// launching stream.  No-ops unless enabled.
+struct ProfScope {
+  cudaStream_t s;
+  int slot;
+  ProfScope(const char* name, cudaStream_t stream);
+  void end();
+  ~ProfScope() { end(); }
+};
+
 // Pinned host memory with a size-class cache (cudaHostAlloc is far too slow per call).
 void* pinned_alloc(size_t bytes);
 void pinned_free(void* p);  // also accepts nullptr

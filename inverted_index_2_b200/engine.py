@@ -318,6 +318,17 @@ class Engine:
     def sync(self):
         self._check(self.lib.ii2_sync(), "sync")
 
+    def prof_enable(self, on: bool):
+        self._check(self.lib.ii2_prof_enable(int(on)), "prof_enable")
+
+    def prof_read(self) -> list[dict]:
+        arr = (A.ProfEntry * 32)()
+        n = self.lib.ii2_prof_read(arr, 32)
+        if n < 0:
+            self._check(n, "prof_read")
+        return [{"name": arr[i].name.decode(), "ms": float(arr[i].ms), "count": int(arr[i].count)}
+                for i in range(n)]
+
     def kernel_launches(self) -> int:
         return int(self.lib.ii2_kernel_launches())
 
