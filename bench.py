@@ -352,7 +352,7 @@ def run_ours(a):
 
     verified = None
     if a.verify and rank == 0:
-        res = eng.merge_dev(dsegs, drem, encode=True).download_merge(decoded=True)
+        res = eng.merge_dev(dsegs, drem, encode=True, decoded=True).download_merge(decoded=True)
         terms, vals, poff = w.expected_union(w.removed)
         etb, eoff = synth.gather_terms(w.term_bytes, w.term_off, terms)
         verified = bool(np.array_equal(res.post, vals) and np.array_equal(res.post_off, poff) and

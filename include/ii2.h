@@ -176,9 +176,13 @@ int ii2_removed_upload(const uint32_t* removed_sorted, uint64_t nrem, ii2_remove
 void ii2_removed_release(ii2_removed* rem);
 
 /* Same work as ii2_merge / ii2_read_range on resident inputs; the result stays
- * in HBM until downloaded.  `encode` != 0 runs the intcomp encoder (merge);
- * 0 leaves decoded postings only (read). */
-int ii2_merge_dev(ii2_seg* const* segs, int nseg, const ii2_removed* rem, int encode,
+ * in HBM until downloaded.  `flags` selects what a merge produces:
+ * II2_RESULT_ENCODED = the intcomp `_val` stream + FST outputs (what Writer.Append
+ * writes, file/writer.go:43-56), II2_RESULT_DECODED = decoded postings (needed by
+ * ii2_result_to_seg / ii2_result_download_read); 0 means decoded only. */
+#define II2_RESULT_ENCODED 1u
+#define II2_RESULT_DECODED 2u
+int ii2_merge_dev(ii2_seg* const* segs, int nseg, const ii2_removed* rem, uint32_t flags,
                   ii2_result** res);
 int ii2_read_range_dev(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen,
                        const uint8_t* max, size_t maxlen, const ii2_removed* rem,

@@ -24,6 +24,8 @@ II2_SEG_VAL = 1
 II2_SEG_DIRECT = 2
 
 II2_MERGE_WANT_DECODED = 1
+II2_RESULT_ENCODED = 1
+II2_RESULT_DECODED = 2
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -120,7 +122,7 @@ PROTOTYPES = {
     "ii2_seg_release": (None, [C.c_void_p]),
     "ii2_removed_upload": (C.c_int, [u32p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "ii2_removed_release": (None, [C.c_void_p]),
-    "ii2_merge_dev": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
+    "ii2_merge_dev": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32,
                                 C.POINTER(C.c_void_p)]),
     "ii2_read_range_dev": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, u8p, C.c_size_t, u8p,
                                      C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -102,23 +102,6 @@ k4_windows(SegDesc* __restrict__ segs, int k, const uint8_t* __restrict__ bounds
   if (s == 0) *n_total = tot;
 }
 
-// min / max term of the merged order (pre-filter, shard.go:176-179): first and last position.
-// out: [0]=len_min [1]=len_max, then the min bytes followed by the max bytes from +8
-__global__ void __launch_bounds__(256)
-k_minmax_terms(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ ord_inst,
-               uint32_t n_total, uint8_t* __restrict__ out) {
-  uint32_t at = 8;
-  for (int which = 0; which < 2; which++) {
-    int s;
-    uint32_t idx;
-    locate_instance(segs, k, ord_inst[which ? n_total - 1 : 0], s, idx);
-    uint32_t o = segs[s].toff[idx], n = segs[s].toff[idx + 1] - o;
-    if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(out)[which] = n;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[at + i] = segs[s].tb[o + i];
-    at += n;
-  }
-}
-
 // ------------------------------------------------------------------ the device pipeline
 // segs: resident segments; [min,max] optional; rem optional.
 int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen, bool has_min,
@@ -134,9 +117,20 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
     set_last_error("%d segments in one call (max %d per pass)", nseg, kMaxSegs);
     return II2_ERR_UNSUPPORTED;
   }
-  // segment table
-  std::vector<SegDesc> h(nseg ? nseg : 1);
-  uint64_t n_total64 = 0, n_in_full = 0;
+  // segment table, sample bases and range bounds travel through one pinned block so that no
+  // pageable copy stalls the stream
+  struct PinnedBlock {
+    void* p = nullptr;
+    ~PinnedBlock() { pinned_free(p); }
+  } stage;
+  const size_t nsegx = nseg ? nseg : 1;
+  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 4 * (nsegx + 1) + minlen + maxlen + 64;
+  stage.p = pinned_alloc(stage_bytes);
+  if (!stage.p) return II2_ERR_NOMEM;
+  SegDesc* h = static_cast<SegDesc*>(stage.p);
+  uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h + nsegx);
+  uint8_t* h_bounds = reinterpret_cast<uint8_t*>(h_sbase + nsegx + 1);
+  uint64_t n_total64 = 0, n_in = 0;
   for (int i = 0; i < nseg; i++) {
     const ii2_seg* g = segs[i];
     if (!g) return II2_ERR_INVALID;
@@ -149,16 +143,16 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
     h[i].hi = g->n_terms;
     h[i].base = (uint32_t)n_total64;
     n_total64 += g->n_terms;
-    n_in_full += g->n_post;
+    n_in += g->n_post;
   }
   if (n_total64 >= (1ull << 32)) {
     set_last_error("more than 2^32-1 term instances in one call");
     return II2_ERR_UNSUPPORTED;
   }
   DevBuf<SegDesc> d_segs;
-  II2_TRY(d_segs.alloc(nseg ? nseg : 1, s));
+  II2_TRY(d_segs.alloc(nsegx, s));
   if (nseg)
-    II2_CUDA_TRY(cudaMemcpyAsync(d_segs.p, h.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, s));
+    II2_CUDA_TRY(cudaMemcpyAsync(d_segs.p, h, sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, s));
   uint32_t n_total = (uint32_t)n_total64;
   const bool ranged = has_min || has_max;
   if (ranged && nseg) {
@@ -166,15 +160,19 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
     DevBuf<uint32_t> d_nt;
     II2_TRY(d_bounds.alloc(minlen + maxlen + 8, s));
     II2_TRY(d_nt.alloc(1, s));
-    if (has_min && minlen)
-      II2_CUDA_TRY(cudaMemcpyAsync(d_bounds.p, min, minlen, cudaMemcpyHostToDevice, s));
-    if (has_max && maxlen)
-      II2_CUDA_TRY(cudaMemcpyAsync(d_bounds.p + minlen, max, maxlen, cudaMemcpyHostToDevice, s));
+    if (has_min && minlen) memcpy(h_bounds, min, minlen);
+    if (has_max && maxlen) memcpy(h_bounds + minlen, max, maxlen);
+    if (minlen + maxlen)
+      II2_CUDA_TRY(cudaMemcpyAsync(d_bounds.p, h_bounds, minlen + maxlen, cudaMemcpyHostToDevice, s));
     k4_windows<<<1, 1024, 0, s>>>(d_segs.p, nseg, d_bounds.p, (uint32_t)minlen, has_min ? 1 : 0,
                                   (uint32_t)maxlen, has_max ? 1 : 0, d_nt.p);
     II2_LAUNCHED();
-    II2_CUDA_TRY(cudaMemcpyAsync(&n_total, d_nt.p, 4, cudaMemcpyDeviceToHost, s));
+    // the windows come back: the planner spreads its samples over them
+    II2_CUDA_TRY(cudaMemcpyAsync(h, d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
+    n_total64 = 0;
+    for (int i = 0; i < nseg; i++) n_total64 += h[i].hi - h[i].lo;
+    n_total = (uint32_t)n_total64;
   }
 
   EmitOut& out = res->out;
@@ -200,13 +198,12 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
   plan.k = nseg;
   plan.n_total = n_total;
   plan.segs = d_segs.p;
-  II2_TRY(k1_build_plan(plan, s));
-
-  DevBuf<uint8_t> d_mm;
-  if (want_minmax) {
-    II2_TRY(d_mm.alloc(8 + 2 * 65536, s));
-    k_minmax_terms<<<1, 256, 0, s>>>(d_segs.p, nseg, plan.ord_inst.p, n_total, d_mm.p);
-    II2_LAUNCHED();
+  II2_TRY(k1_build_plan(plan, h, h_sbase, s));
+  if (ranged) {  // Σ input postings inside the windows sizes the union buffers
+    uint64_t h_plan_tot[2] = {0, 0};
+    II2_CUDA_TRY(cudaMemcpyAsync(h_plan_tot, plan.totals.p, 16, cudaMemcpyDeviceToHost, s));
+    II2_CUDA_TRY(cudaStreamSynchronize(s));
+    n_in = h_plan_tot[1];
   }
 
   RemovedSet rs;
@@ -219,35 +216,45 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
     rs.bitmap_bits = 0;
   }
   UnionOut u;
-  II2_TRY(k2_union(plan, rs, want_enc, keep_empty, ranged ? 0 : n_in_full, u, s));
+  II2_TRY(k12_union(plan, rs, want_dec, want_enc, keep_empty, n_in, u, s));
   res->T = u.h_totals[0];
   res->TB = u.h_totals[1];
   res->P = u.h_totals[2];
   res->E = u.h_totals[3];
-  II2_TRY(k6_emit(plan, u, want_dec, want_enc, out, s));
-
-  uint64_t h_plan_tot[2] = {0, 0};
-  II2_CUDA_TRY(cudaMemcpyAsync(h_plan_tot, plan.totals.p, 16, cudaMemcpyDeviceToHost, s));
-  std::vector<uint8_t> mm;
+  res->postings_in = n_in;
+  res->terms_merged = u.terms_merged;
+  DevBuf<uint8_t> d_mm;
   if (want_minmax) {
-    mm.resize(4096);
-    II2_CUDA_TRY(cudaMemcpyAsync(mm.data(), d_mm.p, 4096, cudaMemcpyDeviceToHost, s));
+    II2_TRY(d_mm.alloc(8 + 2 * 65536, s));
+    II2_TRY(k6_minmax(plan, u, d_mm.p, s));
   }
-  II2_CUDA_TRY(cudaStreamSynchronize(s));
-  res->postings_in = h_plan_tot[0];
-  res->terms_merged = h_plan_tot[1];
+  II2_TRY(k6_emit(plan, u, out, s));
+
+  uint8_t* mm = nullptr;
   if (want_minmax) {
-    uint32_t ln[2];
-    memcpy(ln, mm.data(), 8);
-    const size_t need = 8 + (size_t)ln[0] + ln[1];
-    if (need > mm.size()) {  // long terms: fetch the rest
-      mm.resize(need);
-      II2_CUDA_TRY(cudaMemcpyAsync(mm.data(), d_mm.p, need, cudaMemcpyDeviceToHost, s));
-      II2_CUDA_TRY(cudaStreamSynchronize(s));
+    mm = static_cast<uint8_t*>(pinned_alloc(8 + 2 * 65536));
+    if (!mm) return II2_ERR_NOMEM;
+    cudaError_t e = cudaMemcpyAsync(mm, d_mm.p, 4096, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    uint32_t ln[2] = {0, 0};
+    if (e == cudaSuccess) {
+      memcpy(ln, mm, 8);
+      if (8 + (size_t)ln[0] + ln[1] > 4096) {  // long terms: fetch the rest
+        e = cudaMemcpyAsync(mm, d_mm.p, 8 + (size_t)ln[0] + ln[1], cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      }
     }
-    res->min_term.assign(reinterpret_cast<const char*>(mm.data()) + 8, ln[0]);
-    res->max_term.assign(reinterpret_cast<const char*>(mm.data()) + 8 + ln[0], ln[1]);
-    res->has_minmax = true;
+    if (e != cudaSuccess) {
+      pinned_free(mm);
+      set_last_error("min/max copy: %s", cudaGetErrorString(e));
+      return II2_ERR_CUDA;
+    }
+    res->min_term.assign(reinterpret_cast<const char*>(mm) + 8, ln[0]);
+    res->max_term.assign(reinterpret_cast<const char*>(mm) + 8 + ln[0], ln[1]);
+    res->has_minmax = u.terms_merged > 0;
+    pinned_free(mm);
+  } else {
+    II2_CUDA_TRY(cudaStreamSynchronize(s));
   }
   *res_out = res.release();
   return II2_OK;
@@ -405,15 +412,16 @@ int ii2_removed_upload(const uint32_t* removed_sorted, uint64_t nrem, ii2_remove
 
 void ii2_removed_release(ii2_removed* rem) { delete rem; }
 
-int ii2_merge_dev(ii2_seg* const* segs, int nseg, const ii2_removed* rem, int encode,
+int ii2_merge_dev(ii2_seg* const* segs, int nseg, const ii2_removed* rem, uint32_t flags,
                   ii2_result** res) {
   if (!res) return II2_ERR_INVALID;
   *res = nullptr;
   II2_TRY(ctx_require());
-  // merge: full windows; decoded postings are always kept so the result can be re-used as a
-  // resident segment, the `_val` stream is produced when `encode` is set.
-  return run_pipeline(segs, nseg, nullptr, 0, false, nullptr, 0, false, rem, true, encode != 0,
-                      true, false, res);
+  if (flags == 0) flags = II2_RESULT_DECODED;
+  // merge: full windows, min/max recorded, emptied terms dropped
+  return run_pipeline(segs, nseg, nullptr, 0, false, nullptr, 0, false, rem,
+                      (flags & II2_RESULT_DECODED) != 0, (flags & II2_RESULT_ENCODED) != 0, true,
+                      false, res);
 }
 
 int ii2_read_range_dev(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen,
@@ -558,7 +566,9 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
   if (nrem) II2_TRY(ii2_removed_upload(removed_sorted, nrem, &rem));
   std::unique_ptr<ii2_removed> rem_guard(rem);
   ii2_result* res = nullptr;
-  II2_TRY(ii2_merge_dev(list.v.data(), nseg, rem, 1, &res));
+  II2_TRY(ii2_merge_dev(list.v.data(), nseg, rem,
+                        II2_RESULT_ENCODED | ((flags & II2_MERGE_WANT_DECODED) ? II2_RESULT_DECODED : 0u),
+                        &res));
   std::unique_ptr<ii2_result> res_guard(res);
   return ii2_result_download_merge(res, flags, out);
 }

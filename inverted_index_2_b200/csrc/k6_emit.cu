@@ -1,32 +1,30 @@
-// k6_emit.cu — emit the merged segment / read result from the union results.
+// k6_emit.cu — emit the merged segment / read result from K12's per-term records.
 //
-// Replaces the writer half of the merge loop: empty-term drop (shard.go:192-194),
-// Writer.Append (file/writer.go:32-59: FST output = running valuesOffset, `_val` = one
-// intcomp stream per term, little-endian words, no framing) and, for reads, the TermValues
-// the iterator would yield.  One CTA per K1 bucket; positions are walked in chunks of 256,
-// a block scan over the surviving heads gives every term its output slots (bucket bases come
-// from the bucket-level scan in k2_union), then warps copy term bytes, postings and encode.
-#include "intcomp.cuh"
+// Replaces the writer half of the merge loop: empty-term drop (shard.go:192-194) and
+// Writer.Append (file/writer.go:32-59: FST output = running valuesOffset, `_val` = one intcomp
+// stream per term, little-endian words, no framing); for reads, the TermValues the iterator
+// would yield.  Everything was computed by K12 — this kernel only places it: one CTA per
+// bucket walks the bucket's records in chunks of 256, a block scan over the surviving terms
+// gives every term its output slots (bucket bases come from the bucket-level scan), then warps
+// copy term bytes, encoded words and/or decoded postings.  Pure HBM copy work.
 #include "union.cuh"
 
 namespace ii2 {
 
 constexpr int K6_THREADS = 256;
 constexpr int K6_WARPS = K6_THREADS / 32;
+constexpr uint32_t K6_PENDING = 0xFFFFFFFFu;
 
 struct K6Args {
   const SegDesc* segs;
   int k;
-  const uint32_t* bk_pos;
-  const uint32_t* ord_inst;
-  const uint16_t* gsz;
-  const uint32_t* tmp_post;
-  const uint32_t* g_cnt;
-  const uint32_t* g_enc;
-  const uint64_t* g_off;
+  const uint64_t* bk_pos;
+  const uint32_t* bk_D;
+  const GroupRec* recs;
+  const uint32_t* tmp_enc;
   const uint64_t* bk_out;  // [4][nb1] exclusive prefixes
   uint32_t nb1;
-  int want_decoded, want_enc, keep_empty;
+  int want_dec, want_enc, keep_empty;
   uint8_t* o_term_bytes;
   uint32_t* o_term_off;
   uint32_t* o_post;
@@ -37,63 +35,65 @@ struct K6Args {
 
 struct K6Work {
   const uint8_t* tsrc;
-  uint32_t tlen;
-  uint32_t tdst;
-  uint32_t cnt;
-  uint64_t src_off;
+  const uint32_t* dsrc;
+  const uint32_t* esrc;
   uint64_t post_dst;
   uint64_t enc_dst;
+  uint32_t tdst;
+  uint32_t tlen;
+  uint32_t cnt;
+  uint32_t enc;
 };
 
 __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
   __shared__ K6Work s_work[K6_THREADS];
   __shared__ uint64_t s_ws64[K6_WARPS + 2];
-  __shared__ uint32_t s_ws32[K6_WARPS + 2];
-  __shared__ uint32_t s_stage[K6_WARPS][intcomp::kStageWords];
   const uint32_t tid = threadIdx.x, b = blockIdx.x;
-  const uint32_t p0 = a.bk_pos[b], p1 = a.bk_pos[b + 1];
+  const uint32_t nrec = a.bk_D[b];
+  const GroupRec* recs = a.recs + a.bk_pos[b];
   uint64_t run_t = a.bk_out[0ull * a.nb1 + b];
   uint64_t run_tb = a.bk_out[1ull * a.nb1 + b];
   uint64_t run_p = a.bk_out[2ull * a.nb1 + b];
   uint64_t run_e = a.bk_out[3ull * a.nb1 + b];
-  for (uint32_t q = p0; q < p1; q += K6_THREADS) {
-    const uint32_t p = q + tid;
-    uint32_t cnt = 0, enc = 0, tl = 0;
-    const uint8_t* tsrc = nullptr;
+  for (uint32_t q = 0; q < nrec; q += K6_THREADS) {
+    const uint32_t r = q + tid;
+    GroupRec g;
+    g.cnt = 0;
+    g.enc = 0;
+    g.tlen = 0;
     uint32_t surv = 0;
-    if (p < p1 && a.gsz[p] != 0) {
-      cnt = a.g_cnt[p];
-      if (cnt || a.keep_empty) {
-        surv = 1;
-        enc = a.g_enc[p];
-        int s;
-        uint32_t idx;
-        locate_instance(a.segs, a.k, a.ord_inst[p], s, idx);
-        const uint32_t o = a.segs[s].toff[idx];
-        tl = a.segs[s].toff[idx + 1] - o;
-        tsrc = a.segs[s].tb + o;
-      }
+    if (r < nrec) {
+      g = recs[r];
+      surv = (g.cnt != K6_PENDING && (g.cnt || a.keep_empty)) ? 1u : 0u;
     }
-    uint32_t n_surv;
-    const uint32_t ex_t = block_exclusive_scan(surv, s_ws32, n_surv);
-    uint32_t tot_tb;
-    const uint32_t ex_tb = block_exclusive_scan(tl, s_ws32, tot_tb);
-    uint64_t tot_p, tot_e;
-    const uint64_t ex_p = block_exclusive_scan((uint64_t)cnt, s_ws64, tot_p);
-    const uint64_t ex_e = block_exclusive_scan((uint64_t)enc, s_ws64, tot_e);
+    const uint32_t tl = surv ? g.tlen : 0u;
+    const uint32_t cnt = surv ? g.cnt : 0u;
+    const uint32_t enc = surv ? g.enc : 0u;
+    // (terms, term bytes) share one scan; postings and words can be large, one each
+    uint64_t tot_a, tot_p, tot_e;
+    const uint64_t ex_a = block_exclusive_scan<uint64_t>((uint64_t)surv | ((uint64_t)tl << 32),
+                                                         s_ws64, tot_a);
+    const uint64_t ex_p = block_exclusive_scan<uint64_t>(cnt, s_ws64, tot_p);
+    const uint64_t ex_e = block_exclusive_scan<uint64_t>(enc, s_ws64, tot_e);
+    const uint32_t n_surv = (uint32_t)tot_a;
     if (surv) {
-      const uint64_t t = run_t + ex_t;
+      const uint64_t t = run_t + (uint32_t)ex_a;
       K6Work w;
-      w.tsrc = tsrc;
+      int s;
+      uint32_t idx;
+      locate_instance(a.segs, a.k, g.inst, s, idx);
+      w.tsrc = a.segs[s].tb + a.segs[s].toff[idx];
       w.tlen = tl;
-      w.tdst = (uint32_t)(run_tb + ex_tb);
+      w.tdst = (uint32_t)(run_tb + (ex_a >> 32));
       w.cnt = cnt;
-      w.src_off = a.g_off[p];
+      w.enc = enc;
+      w.dsrc = reinterpret_cast<const uint32_t*>(g.dec);
+      w.esrc = a.tmp_enc + g.eoff;
       w.post_dst = run_p + ex_p;
       w.enc_dst = run_e + ex_e;
-      s_work[ex_t] = w;
+      s_work[(uint32_t)ex_a] = w;
       a.o_term_off[t] = w.tdst;
-      if (a.want_decoded) a.o_post_off[t] = w.post_dst;
+      if (a.want_dec) a.o_post_off[t] = w.post_dst;
       if (a.want_enc) a.o_val_off[t] = 4ull * w.enc_dst;
     }
     __syncthreads();
@@ -101,13 +101,13 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
       const K6Work w = s_work[h];
       const unsigned lane = lane_id();
       for (uint32_t i = lane; i < w.tlen; i += 32) a.o_term_bytes[w.tdst + i] = w.tsrc[i];
-      const uint32_t* src = a.tmp_post + w.src_off;
-      if (a.want_decoded)
-        for (uint32_t i = lane; i < w.cnt; i += 32) a.o_post[w.post_dst + i] = src[i];
-      if (a.want_enc) intcomp::enc_emit_warp(src, w.cnt, a.o_val_words + w.enc_dst, s_stage[warp_id()]);
+      if (a.want_dec)
+        for (uint32_t i = lane; i < w.cnt; i += 32) a.o_post[w.post_dst + i] = w.dsrc[i];
+      if (a.want_enc)
+        for (uint32_t i = lane; i < w.enc; i += 32) a.o_val_words[w.enc_dst + i] = w.esrc[i];
     }
     run_t += n_surv;
-    run_tb += tot_tb;
+    run_tb += tot_a >> 32;
     run_p += tot_p;
     run_e += tot_e;
     __syncthreads();
@@ -115,12 +115,11 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
   // terminal offsets, written once by the last bucket
   if (b == gridDim.x - 1 && tid == 0) {
     a.o_term_off[run_t] = (uint32_t)run_tb;
-    if (a.want_decoded) a.o_post_off[run_t] = run_p;
+    if (a.want_dec) a.o_post_off[run_t] = run_p;
   }
 }
 
-int k6_emit(const MergePlan& plan, const UnionOut& u, bool want_decoded, bool want_enc,
-            EmitOut& out, cudaStream_t s) {
+int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t s) {
   const uint64_t T = u.h_totals[0], TB = u.h_totals[1], P = u.h_totals[2], E = u.h_totals[3];
   if (TB >= (1ull << 32)) {
     set_last_error("merged term dictionary exceeds 4 GiB of term bytes");
@@ -128,28 +127,25 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, bool want_decoded, bool wa
   }
   II2_TRY(out.term_bytes.alloc(TB, s, 32));
   II2_TRY(out.term_off.alloc(T + 1, s));
-  if (want_decoded) {
-    II2_TRY(out.post.alloc(P, s));
+  if (u.want_dec) {
+    II2_TRY(out.post.alloc(P, s, 16));
     II2_TRY(out.post_off.alloc(T + 1, s));
   }
-  if (want_enc) {
+  if (u.want_enc) {
     II2_TRY(out.val_words.alloc(E, s));
     II2_TRY(out.val_off.alloc(T, s));
   }
   K6Args a;
   a.segs = plan.segs;
   a.k = plan.k;
-  a.bk_pos = plan.bk_pos.p;
-  a.ord_inst = plan.ord_inst.p;
-  a.gsz = plan.gsz.p;
-  a.tmp_post = u.tmp_post.p;
-  a.g_cnt = u.g_cnt.p;
-  a.g_enc = u.g_enc.p;
-  a.g_off = u.g_off.p;
+  a.bk_pos = plan.bk_pos();
+  a.bk_D = u.bk_D.p;
+  a.recs = u.recs.p;
+  a.tmp_enc = u.tmp_enc.p;
   a.bk_out = u.bk_out.p;
   a.nb1 = plan.n_buckets + 1;
-  a.want_decoded = want_decoded;
-  a.want_enc = want_enc;
+  a.want_dec = u.want_dec ? 1 : 0;
+  a.want_enc = u.want_enc ? 1 : 0;
   a.keep_empty = u.keep_empty ? 1 : 0;
   a.o_term_bytes = out.term_bytes.p;
   a.o_term_off = out.term_off.p;
@@ -159,6 +155,50 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, bool want_decoded, bool wa
   a.o_val_off = out.val_off.p;
   ProfScope scope("k6_emit", s);
   k6_emit_kernel<<<plan.n_buckets, K6_THREADS, 0, s>>>(a);
+  II2_LAUNCHED();
+  return II2_OK;
+}
+
+// min / max term of the merged order (pre-filter, shard.go:176-179): the first record of the
+// first non-empty bucket and the last record of the last one.
+__global__ void __launch_bounds__(256)
+k6_minmax_kernel(const SegDesc* __restrict__ segs, int k, const uint64_t* __restrict__ bk_pos,
+                 const uint32_t* __restrict__ bk_D, uint32_t B, const GroupRec* __restrict__ recs,
+                 uint8_t* __restrict__ out) {
+  __shared__ uint32_t s_first, s_last;
+  if (threadIdx.x == 0) {
+    s_first = 0xFFFFFFFFu;
+    s_last = 0;
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+    if (bk_D[b]) {
+      atomicMin(&s_first, b);
+      atomicMax(&s_last, b);
+    }
+  }
+  __syncthreads();
+  if (s_first == 0xFFFFFFFFu) {
+    if (threadIdx.x < 2) reinterpret_cast<uint32_t*>(out)[threadIdx.x] = 0;
+    return;
+  }
+  uint32_t at = 8;
+  for (int which = 0; which < 2; which++) {
+    const uint32_t b = which ? s_last : s_first;
+    const GroupRec g = recs[bk_pos[b] + (which ? bk_D[b] - 1 : 0)];
+    int s;
+    uint32_t idx;
+    locate_instance(segs, k, g.inst, s, idx);
+    const uint32_t o = segs[s].toff[idx], n = g.tlen;
+    if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(out)[which] = n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[at + i] = segs[s].tb[o + i];
+    at += n;
+  }
+}
+
+int k6_minmax(const MergePlan& plan, const UnionOut& u, uint8_t* d_out, cudaStream_t s) {
+  k6_minmax_kernel<<<1, 256, 0, s>>>(plan.segs, plan.k, plan.bk_pos(), u.bk_D.p, plan.n_buckets,
+                                     u.recs.p, d_out);
   II2_LAUNCHED();
   return II2_OK;
 }

@@ -234,29 +234,30 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(uint64_t* __restric
   }
 }
 
-// single CTA: m arrays of length n laid out back to back, each scanned independently
+// m arrays of length n laid out back to back, each scanned independently by its own CTA:
+// every thread owns a contiguous chunk (sum, block scan of the sums, second pass writes).
 __global__ void __launch_bounds__(1024) k_scan_multi(const uint64_t* a, uint64_t* out, uint64_t n,
-                                                     int m, uint64_t* __restrict__ totals) {
+                                                     uint64_t* __restrict__ totals) {
   __shared__ uint64_t ws[1024 / 32 + 2];
-  for (int j = 0; j < m; j++) {
-    const uint64_t* arr = a + (uint64_t)j * n;
-    uint64_t* dst = out + (uint64_t)j * n;
-    uint64_t carry = 0;
-    for (uint64_t base = 0; base < n; base += 1024) {
-      uint64_t idx = base + threadIdx.x;
-      uint64_t v = idx < n ? arr[idx] : 0;
-      uint64_t total;
-      uint64_t ex = block_exclusive_scan(v, ws, total);
-      if (idx < n) dst[idx] = carry + ex;
-      carry += total;
-    }
-    if (threadIdx.x == 0 && totals) totals[j] = carry;
+  const uint64_t* arr = a + (uint64_t)blockIdx.x * n;
+  uint64_t* dst = out + (uint64_t)blockIdx.x * n;
+  const uint64_t chunk = (n + 1023) / 1024;
+  const uint64_t lo = threadIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  uint64_t sum = 0;
+  for (uint64_t i = lo; i < hi; i++) sum += arr[i];
+  uint64_t total;
+  uint64_t ex = block_exclusive_scan(sum, ws, total);
+  for (uint64_t i = lo; i < hi; i++) {
+    const uint64_t v = arr[i];
+    dst[i] = ex;
+    ex += v;
   }
+  if (threadIdx.x == 0 && totals) totals[blockIdx.x] = total;
 }
 
 int exclusive_scan_multi_u64(const uint64_t* in, uint64_t* out, uint64_t n, int m,
                              uint64_t* d_totals, cudaStream_t s) {
-  k_scan_multi<<<1, 1024, 0, s>>>(in, out, n, m, d_totals);
+  k_scan_multi<<<m, 1024, 0, s>>>(in, out, n, d_totals);
   II2_LAUNCHED();
   return II2_OK;
 }

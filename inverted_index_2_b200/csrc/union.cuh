@@ -1,45 +1,62 @@
-// union.cuh — outputs of K2 (posting union) and inputs of the emit kernel.
+// union.cuh — outputs of K12 (fused term merge + posting union) and inputs of the emit kernel.
 #pragma once
 #include "plan.cuh"
 
 namespace ii2 {
 
-struct UnionOut {
-  DevBuf<uint32_t> tmp_post;  // [N_in] union results; group at head p starts at g_off[p]
-  DevBuf<uint32_t> g_cnt;     // [N_T] at heads: values left after union + removed filter
-  DevBuf<uint32_t> g_enc;     // [N_T] at heads: intcomp words of that list (if encoding)
-  DevBuf<uint64_t> g_off;     // [N_T] at heads: offset into tmp_post
-  // [4][B+1] per bucket {surviving terms, their term bytes, postings out, encoded words}
-  DevBuf<uint64_t> bk_raw;
-  DevBuf<uint64_t> bk_out;    // exclusive prefixes of bk_raw
-  DevBuf<uint64_t> totals;    // [4] device
-  uint64_t h_totals[4] = {0, 0, 0, 0};
-  bool keep_empty = false;    // reads without a filter keep terms whose list is empty
+// One record per DISTINCT term, in merged (ascending term) order inside its bucket: the
+// records of bucket b start at index bk_pos[b] (an upper bound of the groups before it).
+struct GroupRec {
+  uint64_t dec;   // device address of the unioned + filtered postings (if kept decoded)
+  uint64_t eoff;  // word offset of the term's intcomp stream in tmp_enc (if encoded)
+  uint32_t inst;  // global instance id of one source (names the term bytes)
+  uint32_t tlen;  // term length
+  uint32_t cnt;   // values left after union + removed filter
+  uint32_t enc;   // intcomp words of that list
 };
 
-// K2: per-term union + dedup of uint32 posting lists with the removed filter in the same pass
+struct UnionOut {
+  DevBuf<GroupRec> recs;       // [N_T]
+  DevBuf<uint32_t> tmp_post;   // [N_in] decoded union results (only if decoded output is wanted)
+  DevBuf<uint32_t> tmp_enc;    // encoded streams, allocated by sub-tile with one atomicAdd
+  DevBuf<uint32_t> large_tmp;  // sort space of the multi-CTA path for heavy terms
+  DevBuf<uint32_t> bk_D;       // [B] distinct terms per bucket
+  // [4][B+1] per bucket {surviving terms, their term bytes, postings out, encoded words}
+  DevBuf<uint64_t> bk_raw;
+  DevBuf<uint64_t> bk_out;     // exclusive prefixes of bk_raw
+  DevBuf<uint64_t> totals;     // [4] device (+ scratch counters behind)
+  uint64_t h_totals[4] = {0, 0, 0, 0};
+  uint64_t terms_merged = 0;   // Σ bk_D
+  bool keep_empty = false;     // reads without a filter keep terms whose list is empty
+  bool want_dec = false, want_enc = false;
+};
+
+// K12: per bucket, finish the k-way term merge (group equal terms, order the distinct ones) and
+// union + dedup the posting lists of every term with the removed filter in the same pass
 // (file.MergeTermValues file/types.go:14-22 for terms with >= 2 sources, pass-through for
-// single-source terms; filter shard.go:181-190).  Synchronises the stream once to learn
-// the output sizes.
-// n_in_hint: Σ input postings if the host already knows it (full-window merges), else 0.
+// single-source terms; filter shard.go:181-190); encode (intcomp) while the list is still in
+// shared memory.  Synchronises the stream once to learn the output sizes.
 // keep_empty: terms left with no values are kept (plain reads) instead of dropped (merge,
 // shard.go:192-194).
-int k2_union(const MergePlan& plan, const RemovedSet& rem, bool want_enc, bool keep_empty,
-             uint64_t n_in_hint, UnionOut& u, cudaStream_t s);
+int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool want_enc,
+              bool keep_empty, uint64_t n_in, UnionOut& u, cudaStream_t s);
 
 struct EmitOut {
   DevBuf<uint8_t> term_bytes;
   DevBuf<uint32_t> term_off;  // [T+1]
-  DevBuf<uint32_t> post;      // [P]    (if want_decoded)
-  DevBuf<uint64_t> post_off;  // [T+1]  (if want_decoded)
+  DevBuf<uint32_t> post;      // [P]    (if want_dec)
+  DevBuf<uint64_t> post_off;  // [T+1]  (if want_dec)
   DevBuf<uint32_t> val_words; // [E]    (if want_enc)
   DevBuf<uint64_t> val_off;   // [T]    byte offsets (if want_enc)
 };
 
 // Emit: surviving terms (non-empty after the filter, shard.go:192-194) with compact term
-// bytes/offsets, decoded postings and/or the intcomp-encoded `_val` stream with running byte
-// offsets (Writer.Append, file/writer.go:43-56).
-int k6_emit(const MergePlan& plan, const UnionOut& u, bool want_decoded, bool want_enc,
-            EmitOut& out, cudaStream_t s);
+// bytes/offsets, decoded postings and/or the `_val` stream with running byte offsets
+// (Writer.Append, file/writer.go:43-56).  Pure gather/copy: everything was computed by K12.
+int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t s);
+
+// First and last term of the merged order (pre-filter min/max, shard.go:176-179).
+// d_out: [0]=len_min [1]=len_max (u32), bytes from +8 (min then max); needs 8 + 2*65536 bytes.
+int k6_minmax(const MergePlan& plan, const UnionOut& u, uint8_t* d_out, cudaStream_t s);
 
 }  // namespace ii2

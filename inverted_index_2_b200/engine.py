@@ -261,11 +261,12 @@ class Engine:
         return arr
 
     def merge_dev(self, segs: list[DeviceSegment], removed: DeviceRemoved | None = None,
-                  encode: bool = True) -> DeviceResult:
+                  encode: bool = True, decoded: bool = False) -> DeviceResult:
+        flags = (A.II2_RESULT_ENCODED if encode else 0) | (A.II2_RESULT_DECODED if decoded else 0)
         h = C.c_void_p()
         self._check(self.lib.ii2_merge_dev(self._handles(segs), len(segs),
-                                           removed.h if removed else None, int(encode),
-                                           C.byref(h)), "merge_dev")
+                                           removed.h if removed else None, flags, C.byref(h)),
+                    "merge_dev")
         return DeviceResult(self, h.value)
 
     def read_range_dev(self, segs: list[DeviceSegment], min_term: bytes | None = None,

@@ -232,11 +232,11 @@ def test_resident_pipeline_and_multipass(engine, orc):
     w = synth.make_workload(8000, 9, 150000, universe=1 << 15, seed=33)
     dsegs = [engine.upload(s) for s in w.segments]
     drem = engine.upload_removed(w.removed)
-    one = engine.merge_dev(dsegs, drem, encode=True).download_merge(decoded=True)
+    one = engine.merge_dev(dsegs, drem, encode=True, decoded=True).download_merge(decoded=True)
     assert_merge_equal(one, orc.merge(w.segments, w.removed, decoded=True))
     r1 = engine.merge_dev(dsegs[:4], drem, encode=False).to_segment()
     r2 = engine.merge_dev(dsegs[4:], drem, encode=False).to_segment()
-    two = engine.merge_dev([r1, r2], drem, encode=True).download_merge(decoded=True)
+    two = engine.merge_dev([r1, r2], drem, encode=True, decoded=True).download_merge(decoded=True)
     assert np.array_equal(two.val_bytes, one.val_bytes) and np.array_equal(two.post, one.post)
     assert np.array_equal(two.term_bytes, one.term_bytes)
     rd = engine.read_range_dev(dsegs, None, None).download_read()
