@@ -93,7 +93,8 @@ uint64_t ii2_kernel_launches(void);
  * returns the number of entries written (<= cap), or a negative error. */
 typedef struct ii2_prof_entry {
   const char* name;
-  double ms;
+  double ms;      /* device time between the phase's events */
+  double host_ms; /* host wall time spent inside the phase (launch + allocation + waits) */
   uint64_t count;
 } ii2_prof_entry;
 int ii2_prof_enable(int on);

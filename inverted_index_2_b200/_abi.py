@@ -97,7 +97,8 @@ class ResultInfo(C.Structure):
 
 
 class ProfEntry(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("ms", C.c_double), ("count", C.c_uint64)]
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_double), ("host_ms", C.c_double),
+                ("count", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/ii2.h declares.

@@ -104,11 +104,11 @@ k4_windows(SegDesc* __restrict__ segs, int k, const uint8_t* __restrict__ bounds
 
 // ------------------------------------------------------------------ the device pipeline
 // segs: resident segments; [min,max] optional; rem optional.
-int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen, bool has_min,
-                 const uint8_t* max, size_t maxlen, bool has_max, const ii2_removed* rem,
-                 bool want_dec, bool want_enc, bool want_minmax, bool keep_empty,
-                 ii2_result** res_out) {
-  cudaStream_t s = cur_stream();
+int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen,
+                      bool has_min, const uint8_t* max, size_t maxlen, bool has_max,
+                      const ii2_removed* rem, bool want_dec, bool want_enc, bool want_minmax,
+                      bool keep_empty, ii2_result** res_out, cudaStream_t s) {
+  ProfScope pipe_scope("pipeline_total", s);
   std::unique_ptr<ii2_result> res(new ii2_result());
   res->has_dec = want_dec;
   res->has_enc = want_enc;
@@ -150,7 +150,7 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
     return II2_ERR_UNSUPPORTED;
   }
   DevBuf<SegDesc> d_segs;
-  II2_TRY(d_segs.alloc(nsegx, s));
+  II2_TRY(d_segs.alloc_scratch(nsegx, s));
   if (nseg)
     II2_CUDA_TRY(cudaMemcpyAsync(d_segs.p, h, sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, s));
   uint32_t n_total = (uint32_t)n_total64;
@@ -158,8 +158,8 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
   if (ranged && nseg) {
     DevBuf<uint8_t> d_bounds;
     DevBuf<uint32_t> d_nt;
-    II2_TRY(d_bounds.alloc(minlen + maxlen + 8, s));
-    II2_TRY(d_nt.alloc(1, s));
+    II2_TRY(d_bounds.alloc_scratch(minlen + maxlen + 8, s));
+    II2_TRY(d_nt.alloc_scratch(1, s));
     if (has_min && minlen) memcpy(h_bounds, min, minlen);
     if (has_max && maxlen) memcpy(h_bounds + minlen, max, maxlen);
     if (minlen + maxlen)
@@ -225,7 +225,7 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
   res->terms_merged = u.terms_merged;
   DevBuf<uint8_t> d_mm;
   if (want_minmax) {
-    II2_TRY(d_mm.alloc(8 + 2 * 65536, s));
+    II2_TRY(d_mm.alloc_scratch(8 + 2 * 65536, s));
     II2_TRY(k6_minmax(plan, u, d_mm.p, s));
   }
   II2_TRY(k6_emit(plan, u, out, s));
@@ -258,6 +258,19 @@ int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minl
   }
   *res_out = res.release();
   return II2_OK;
+}
+
+// Intermediates live in the calling thread's scratch arena for the duration of the call.
+int run_pipeline(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen, bool has_min,
+                 const uint8_t* max, size_t maxlen, bool has_max, const ii2_removed* rem,
+                 bool want_dec, bool want_enc, bool want_minmax, bool keep_empty,
+                 ii2_result** res_out) {
+  cudaStream_t s = cur_stream();
+  const int rc = run_pipeline_impl(segs, nseg, min, minlen, has_min, max, maxlen, has_max, rem,
+                                   want_dec, want_enc, want_minmax, keep_empty, res_out, s);
+  if (rc != II2_OK) cudaStreamSynchronize(s);
+  arena_reset(s);
+  return rc;
 }
 
 template <typename T>

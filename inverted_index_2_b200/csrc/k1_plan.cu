@@ -175,16 +175,16 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   plan.n_samples = S;
   plan.n_buckets = B;
   ProfScope scope("k1_plan", s);
-  II2_TRY(plan.part.alloc((size_t)(S + 2) * k, s));
-  II2_TRY(plan.row_of.alloc(B + 1, s));
-  II2_TRY(plan.bk_cpl.alloc(B, s));
-  II2_TRY(plan.bk_WP.alloc(2 * (size_t)(B + 1), s));
-  II2_TRY(plan.totals.alloc(2, s));
+  II2_TRY(plan.part.alloc_scratch((size_t)(S + 2) * k, s));
+  II2_TRY(plan.row_of.alloc_scratch(B + 1, s));
+  II2_TRY(plan.bk_cpl.alloc_scratch(B, s));
+  II2_TRY(plan.bk_WP.alloc_scratch(2 * (size_t)(B + 1), s));
+  II2_TRY(plan.totals.alloc_scratch(2, s));
   DevBuf<uint32_t> d_sbase, d_u32;
   DevBuf<uint64_t> d_u64;
-  II2_TRY(d_sbase.alloc(k + 1, s));
-  II2_TRY(d_u64.alloc(3 * (size_t)(S ? S : 1), s));
-  II2_TRY(d_u32.alloc(3 * (size_t)(S ? S : 1), s));
+  II2_TRY(d_sbase.alloc_scratch(k + 1, s));
+  II2_TRY(d_u64.alloc_scratch(3 * (size_t)(S ? S : 1), s));
+  II2_TRY(d_u32.alloc_scratch(3 * (size_t)(S ? S : 1), s));
   II2_CUDA_TRY(cudaMemcpyAsync(d_sbase.p, sbase, (k + 1) * 4, cudaMemcpyHostToDevice, s));
   const size_t Sx = S ? S : 1;
   SampleArrays sa{d_u64.p, d_u64.p + Sx, d_u64.p + 2 * Sx, d_u32.p, d_u32.p + Sx, d_u32.p + 2 * Sx};

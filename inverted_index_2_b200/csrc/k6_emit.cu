@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
       w.cnt = cnt;
       w.enc = enc;
       w.dsrc = reinterpret_cast<const uint32_t*>(g.dec);
-      w.esrc = a.tmp_enc + g.eoff;
+      w.esrc = reinterpret_cast<const uint32_t*>(g.eoff);
       w.post_dst = run_p + ex_p;
       w.enc_dst = run_e + ex_e;
       s_work[(uint32_t)ex_a] = w;

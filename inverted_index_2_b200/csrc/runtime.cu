@@ -1,4 +1,6 @@
 // runtime.cu — context / streams / memory pools / scan utility for libii2.
+#include <time.h>
+
 #include <cstdarg>
 #include <map>
 #include <mutex>
@@ -131,11 +133,87 @@ static void pinned_drain() {
   g_pinned.cached = 0;
 }
 
+// ------------------------------------------------------------------ scratch arena
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0, want = 0;
+  std::vector<void*> spill;  // stream-ordered allocations made when the block was too small
+};
+static std::mutex g_arena_m;
+static std::vector<Arena*> g_arenas;
+static thread_local Arena* t_arena = nullptr;
+
+static Arena* my_arena() {
+  if (!t_arena) {
+    t_arena = new Arena();
+    std::lock_guard<std::mutex> lk(g_arena_m);
+    g_arenas.push_back(t_arena);
+  }
+  return t_arena;
+}
+
+void* arena_alloc(size_t bytes, cudaStream_t stream) {
+  Arena* a = my_arena();
+  bytes = (bytes + 255) & ~size_t(255);
+  a->want += bytes;
+  if (a->used + bytes <= a->cap) {
+    void* p = a->base + a->used;
+    a->used += bytes;
+    return p;
+  }
+  void* q = nullptr;
+  cudaError_t e = cudaMallocAsync(&q, bytes, stream);
+  if (e != cudaSuccess) {
+    set_last_error("scratch allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  a->spill.push_back(q);
+  return q;
+}
+
+void arena_reset(cudaStream_t stream) {
+  Arena* a = my_arena();
+  for (void* q : a->spill) cudaFreeAsync(q, stream);
+  const bool grow = !a->spill.empty() || a->want > a->cap;
+  a->spill.clear();
+  if (grow) {  // the caller has synchronised: nothing in flight uses the old block
+    cudaStreamSynchronize(stream);
+    if (a->base) cudaFree(a->base);
+    a->base = nullptr;
+    a->cap = 0;
+    const size_t cap = a->want + a->want / 8 + (size_t(1) << 20);
+    void* q = nullptr;
+    if (cudaMalloc(&q, cap) == cudaSuccess) {
+      a->base = static_cast<uint8_t*>(q);
+      a->cap = cap;
+    } else {
+      cudaGetLastError();  // stay on the spill path
+    }
+  }
+  a->used = 0;
+  a->want = 0;
+}
+
+void arena_release_all() {
+  std::lock_guard<std::mutex> lk(g_arena_m);
+  for (Arena* a : g_arenas) {
+    if (a->base) cudaFree(a->base);
+    a->base = nullptr;
+    a->cap = a->used = a->want = 0;
+  }
+}
+
 // ------------------------------------------------------------------ instrumentation
 struct ProfRec {
   const char* name;
   cudaEvent_t e0, e1;
+  double host_t0, host_ms;
 };
+static double host_now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 struct Prof {
   std::mutex m;
   std::atomic<bool> on{false};
@@ -158,6 +236,8 @@ ProfScope::ProfScope(const char* name, cudaStream_t stream) : s(stream), slot(-1
     }
   }
   cudaEventRecord(r.e0, s);
+  r.host_t0 = host_now_ms();
+  r.host_ms = 0;
   slot = (int)g_prof.recs.size();
   g_prof.recs.push_back(r);
 }
@@ -165,7 +245,10 @@ ProfScope::ProfScope(const char* name, cudaStream_t stream) : s(stream), slot(-1
 void ProfScope::end() {
   if (slot < 0) return;
   std::lock_guard<std::mutex> lk(g_prof.m);
-  if (slot < (int)g_prof.recs.size()) cudaEventRecord(g_prof.recs[slot].e1, s);
+  if (slot < (int)g_prof.recs.size()) {
+    cudaEventRecord(g_prof.recs[slot].e1, s);
+    g_prof.recs[slot].host_ms = host_now_ms() - g_prof.recs[slot].host_t0;
+  }
   slot = -1;
 }
 
@@ -354,6 +437,7 @@ int ii2_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_ctx.m);
   if (!g_ctx.ready) return II2_OK;
   cudaDeviceSynchronize();
+  arena_release_all();
   pinned_drain();
   g_ctx.ready = false;
   return II2_OK;
@@ -390,10 +474,12 @@ int ii2_prof_read(ii2_prof_entry* out, int cap) {
       if (n == cap) continue;
       out[n].name = r.name;
       out[n].ms = 0;
+      out[n].host_ms = 0;
       out[n].count = 0;
       n++;
     }
     out[j].ms += ms;
+    out[j].host_ms += r.host_ms;
     out[j].count += 1;
   }
   return n;

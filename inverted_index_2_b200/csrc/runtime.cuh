@@ -11,20 +11,32 @@ bool ctx_ready();
 int ctx_require();            // II2_OK or II2_ERR_NO_DEVICE (sets last error)
 cudaStream_t cur_stream();    // this thread's stream (caller-provided or library-owned)
 
-// Stream-ordered device buffer (cudaMallocAsync on the device's default pool).
+// Per-thread scratch arena: one grow-only device block, bump-allocated during a pipeline call
+// and reset when the call is over.  GB-sized cudaMallocAsync requests were measured at tens of
+// milliseconds per call on B200 (the pool re-maps physical memory); the arena makes every
+// intermediate buffer free of charge after the first call.
+void* arena_alloc(size_t bytes, cudaStream_t stream);  // nullptr + last error on failure
+// Call once per pipeline, after the stream has been synchronised: frees spill-over
+// allocations and grows the block to the high-water mark of the call.
+void arena_reset(cudaStream_t stream);
+void arena_release_all();  // ii2_shutdown
+
+// Device buffer: stream-ordered allocation (cudaMallocAsync) for data that outlives the call,
+// or arena scratch for intermediates.
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaStream_t s = nullptr;
+  bool scratch = false;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s), scratch(o.scratch) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
     if (this != &o) {
       release();
-      p = o.p; n = o.n; s = o.s;
+      p = o.p; n = o.n; s = o.s; scratch = o.scratch;
       o.p = nullptr; o.n = 0;
     }
     return *this;
@@ -35,6 +47,7 @@ struct DevBuf {
     release();
     s = stream;
     n = count;
+    scratch = false;
     size_t bytes = count * sizeof(T) + pad_bytes;
     if (bytes == 0) bytes = 16;
     void* q = nullptr;
@@ -42,8 +55,19 @@ struct DevBuf {
     p = static_cast<T*>(q);
     return II2_OK;
   }
+  // intermediate of the current pipeline call: lives until arena_reset
+  int alloc_scratch(size_t count, cudaStream_t stream, size_t pad_bytes = 0) {
+    release();
+    s = stream;
+    n = count;
+    scratch = true;
+    size_t bytes = count * sizeof(T) + pad_bytes;
+    if (bytes == 0) bytes = 16;
+    p = static_cast<T*>(arena_alloc(bytes, stream));
+    return p ? II2_OK : II2_ERR_NOMEM;
+  }
   void release() {
-    if (p) cudaFreeAsync(p, s);
+    if (p && !scratch) cudaFreeAsync(p, s);
     p = nullptr;
     n = 0;
   }

@@ -8,7 +8,7 @@ namespace ii2 {
 // records of bucket b start at index bk_pos[b] (an upper bound of the groups before it).
 struct GroupRec {
   uint64_t dec;   // device address of the unioned + filtered postings (if kept decoded)
-  uint64_t eoff;  // word offset of the term's intcomp stream in tmp_enc (if encoded)
+  uint64_t eoff;  // device address of the term's intcomp stream (if encoded)
   uint32_t inst;  // global instance id of one source (names the term bytes)
   uint32_t tlen;  // term length
   uint32_t cnt;   // values left after union + removed filter
@@ -18,7 +18,8 @@ struct GroupRec {
 struct UnionOut {
   DevBuf<GroupRec> recs;       // [N_T]
   DevBuf<uint32_t> tmp_post;   // [N_in] decoded union results (only if decoded output is wanted)
-  DevBuf<uint32_t> tmp_enc;    // encoded streams, allocated by sub-tile with one atomicAdd
+  DevBuf<uint32_t> tmp_enc;    // encoded streams, one upper-bound slot per light term
+  DevBuf<uint32_t> large_enc;  // the same for heavy terms
   DevBuf<uint32_t> large_tmp;  // sort space of the multi-CTA path for heavy terms
   DevBuf<uint32_t> bk_D;       // [B] distinct terms per bucket
   // [4][B+1] per bucket {surviving terms, their term bytes, postings out, encoded words}

@@ -327,7 +327,8 @@ class Engine:
         n = self.lib.ii2_prof_read(arr, 32)
         if n < 0:
             self._check(n, "prof_read")
-        return [{"name": arr[i].name.decode(), "ms": float(arr[i].ms), "count": int(arr[i].count)}
+        return [{"name": arr[i].name.decode(), "ms": float(arr[i].ms),
+                 "host_ms": float(arr[i].host_ms), "count": int(arr[i].count)}
                 for i in range(n)]
 
     def kernel_launches(self) -> int:
