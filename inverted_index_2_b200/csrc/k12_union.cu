@@ -429,53 +429,56 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
 // ---- warp-level union of one group held in shared memory --------------------------------
 // Sorting network over 32*R values striped over the warp (element e = r*32 + lane): for each
 // block size a mirrored "flip" step, then half-cleaners.  The lower element of every pair
-// takes the minimum, so a compare-exchange is one shuffle + one predicated min/max.
+// takes the minimum, so a compare-exchange is one shuffle + one predicated min/max.  The
+// shuffle stages run as LOOPS over the distance (only the few register-to-register stages are
+// unrolled): the kernel stays small enough for the instruction cache.
+template <int R>
+__device__ __forceinline__ void shuffle_stage(uint32_t (&v)[R], uint32_t mask, bool lower) {
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], mask);
+    v[r] = lower ? min(v[r], o) : max(v[r], o);
+  }
+}
+
 template <int R>
 __device__ __forceinline__ void sort_regs(uint32_t (&v)[R]) {
   const unsigned lane = lane_id();
+  // block sizes 2..32: everything stays inside one register row
+#pragma unroll 1
+  for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+    shuffle_stage<R>(v, kk - 1, (lane & (kk >> 1)) == 0);
+#pragma unroll 1
+    for (uint32_t j = kk >> 2; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+  }
+  // block sizes 64..32R: flip and the first half-cleaners pair register rows
 #pragma unroll
-  for (uint32_t kk = 2; kk <= 32u * R; kk <<= 1) {
-    if (kk <= 32) {
-      const bool lower = (lane & (kk >> 1)) == 0;
+  for (uint32_t kk = 64; kk <= 32u * R; kk <<= 1) {
+    const int rm = (int)(kk >> 5) - 1, hb = (int)(kk >> 6);
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], kk - 1);
-        v[r] = lower ? min(v[r], o) : max(v[r], o);
+    for (int r = 0; r < R; r++) {
+      if ((r & hb) == 0) {
+        const int r2 = r ^ rm;
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, v[r2], 31);
+        const uint32_t o2 = __shfl_xor_sync(0xffffffffu, v[r], 31);
+        v[r] = min(v[r], o1);
+        v[r2] = max(v[r2], o2);
       }
-    } else {
-      const int rm = (int)(kk >> 5) - 1, hb = (int)(kk >> 6);
+    }
+#pragma unroll
+    for (uint32_t j = kk >> 2; j >= 32; j >>= 1) {
+      const int dr = (int)(j >> 5);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        if ((r & hb) == 0) {
-          const int r2 = r ^ rm;
-          const uint32_t o1 = __shfl_xor_sync(0xffffffffu, v[r2], 31);
-          const uint32_t o2 = __shfl_xor_sync(0xffffffffu, v[r], 31);
-          v[r] = min(v[r], o1);
-          v[r2] = max(v[r2], o2);
+        if ((r & dr) == 0) {
+          const uint32_t x = v[r], y = v[r | dr];
+          v[r] = min(x, y);
+          v[r | dr] = max(x, y);
         }
       }
     }
-#pragma unroll
-    for (uint32_t j = kk >> 2; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const int dr = (int)(j >> 5);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          if ((r & dr) == 0) {
-            const uint32_t x = v[r], y = v[r | dr];
-            v[r] = min(x, y);
-            v[r | dr] = max(x, y);
-          }
-        }
-      } else {
-        const bool lower = (lane & j) == 0;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
-          v[r] = lower ? min(v[r], o) : max(v[r], o);
-        }
-      }
-    }
+#pragma unroll 1
+    for (uint32_t j = 16; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
   }
 }
 
@@ -520,7 +523,7 @@ __device__ __forceinline__ uint32_t union_regs(uint32_t* base, uint32_t L, const
 
 // single-source pass-through: order and duplicates kept, only the filter (in place)
 __device__ __forceinline__ uint32_t filter_inplace_warp(uint32_t* base, uint32_t L,
-                                                        const RemovedSet& rem) {
+                                                     const RemovedSet& rem) {
   if (rem.n == 0) return L;
   const unsigned lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
@@ -539,110 +542,85 @@ __device__ __forceinline__ uint32_t filter_inplace_warp(uint32_t* base, uint32_t
   return outn;
 }
 
-// intcomp.CompressUint32 of base[0..n) (n <= 32*R) from registers, written IN PLACE over
-// base when the stream fits the `room` words of the group's slot (all values are in registers
-// before the first store).  Returns the stream length in words, or 0xFFFFFFFF when it does not
-// fit (the caller then keeps the decoded list and encodes straight to global memory).
-template <int R>
-__device__ __forceinline__ uint32_t encode_regs_inplace(uint32_t* base, uint32_t n, uint32_t room) {
+// intcomp.CompressUint32 of v[0..n) (shared memory) into out (shared memory, a different
+// buffer, at least enc_bound(n) words), one pass with rolled loops.  Returns the stream
+// length in words (uniform).
+__device__ __forceinline__ uint32_t encode_shared_warp(const uint32_t* v, uint32_t n, uint32_t* out) {
+  if (n == 0) return 0;
   const unsigned lane = lane_id();
-  uint32_t w[R], coded[R], wd[R];
-  uint32_t v0 = 0;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    const uint32_t e = r * 32 + lane;
-    w[r] = e < n ? base[e] : 0u;
-  }
-  v0 = __shfl_sync(0xffffffffu, w[0], 0);
   const uint32_t nb = n >> 7, tail = n & 127u;
-  uint32_t words = nb ? 3u : 0u, tail_bytes = 0;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    const uint32_t e = r * 32 + lane;
-    uint32_t prev = prev_striped<R>(w, r);
-    if ((uint32_t)r < nb * 4) {  // bit-packed group r of block r/4
-      if (e == 0) prev = w[r];
-      const uint32_t z = intcomp::zigzag(w[r], prev);
-      const uint32_t m = __reduce_or_sync(0xffffffffu, z);
-      const uint32_t sgn = m & 1u;
-      wd[r] = sgn ? intcomp::bitlen(m) : intcomp::bitlen(m >> 1);
-      coded[r] = sgn ? z : (w[r] - prev);
-      wd[r] |= sgn << 7;
-      words += (wd[r] & 0x7Fu) + ((r & 3) == 0 ? 1u : 0u);
-    } else {  // var-byte tail: delta vs the previous value, 0 before the first
-      if (e == nb * 128) prev = 0;
-      coded[r] = intcomp::zigzag(w[r], prev);
-      wd[r] = e < n ? intcomp::vbyte_len(coded[r]) : 0u;
-      tail_bytes += wd[r];
-    }
-  }
-  tail_bytes = warp_sum(tail_bytes);
-  if (tail) words += 1 + (tail_bytes + 3) / 4;
-  if (words > room) return 0xFFFFFFFFu;
-  __syncwarp();
-  // every store below lands in base[0..words)
-  for (uint32_t i = lane; i < words; i += 32) base[i] = 0;
-  __syncwarp();
   uint32_t pos = 0;
   if (nb) {
     pos = 3;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      if ((uint32_t)r < nb * 4) {
-        if ((r & 3) == 0) {
-          if (lane == 0)
-            base[pos] = (wd[r] << 24) | (wd[r + 1 < R ? r + 1 : r] << 16) |
-                        (wd[r + 2 < R ? r + 2 : r] << 8) | wd[r + 3 < R ? r + 3 : r];
-          pos += 1;
-        }
-        const uint32_t bw = wd[r] & 0x7Fu;
+#pragma unroll 1
+    for (uint32_t blk = 0; blk < nb; blk++) {
+      const uint32_t hpos = pos++;
+      uint32_t hdr = 0;
+#pragma unroll 1
+      for (uint32_t g = 0; g < 4; g++) {
+        const uint32_t idx = blk * 128 + g * 32 + lane;
+        const uint32_t cur = v[idx];
+        const uint32_t prev = idx ? v[idx - 1] : cur;
+        const uint32_t z = intcomp::zigzag(cur, prev);
+        const uint32_t m = __reduce_or_sync(0xffffffffu, z);
+        const uint32_t sgn = m & 1u;
+        const uint32_t bw = sgn ? intcomp::bitlen(m) : intcomp::bitlen(m >> 1);
+        const uint32_t coded = sgn ? z : (cur - prev);
+        hdr |= ((sgn << 7) | bw) << (24 - 8 * g);
         if (bw == 32) {
-          base[pos + lane] = coded[r];
+          out[pos + lane] = coded;
         } else if (bw > 0) {
+          if (lane < bw) out[pos + lane] = 0;
+          __syncwarp();
           const uint32_t bit = lane * bw, sh = bit & 31u;
-          atomicOr(&base[pos + (bit >> 5)], coded[r] << sh);
-          if (sh + bw > 32u) atomicOr(&base[pos + (bit >> 5) + 1], coded[r] >> (32u - sh));
+          atomicOr(&out[pos + (bit >> 5)], coded << sh);
+          if (sh + bw > 32u) atomicOr(&out[pos + (bit >> 5) + 1], coded >> (32u - sh));
         }
         pos += bw;
       }
+      if (lane == 0) out[hpos] = hdr;
     }
     if (lane == 0) {
-      base[0] = nb * 128;
-      base[1] = pos;
-      base[2] = v0;
+      out[0] = nb * 128;
+      out[1] = pos;
+      out[2] = v[0];
     }
   }
   if (tail) {
-    if (lane == 0) base[pos] = tail;
+    if (lane == 0) out[pos] = tail;
     pos += 1;
-    uint8_t* sb = reinterpret_cast<uint8_t*>(base + pos);
+    uint8_t* sb = reinterpret_cast<uint8_t*>(out + pos);
     uint32_t bo = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      if ((uint32_t)r >= nb * 4) {
-        const uint32_t len = wd[r];
-        const uint32_t inc = warp_inclusive_scan(len);
-        const uint32_t off = bo + inc - len;
-        uint32_t z = coded[r];
-        for (uint32_t t = 0; t < len; t++) {
-          uint32_t byte = z & 0x7Fu;
-          z >>= 7;
-          if (t + 1 == len) byte |= 0x80u;
-          sb[off + t] = (uint8_t)byte;
-        }
-        bo += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll 1
+    for (uint32_t t0 = 0; t0 < tail; t0 += 32) {
+      const uint32_t i = t0 + lane;
+      uint32_t z = 0, len = 0;
+      if (i < tail) {
+        const uint32_t idx = nb * 128 + i;
+        z = intcomp::zigzag(v[idx], i ? v[idx - 1] : 0u);
+        len = intcomp::vbyte_len(z);
       }
+      const uint32_t inc = warp_inclusive_scan(len);
+      const uint32_t off = bo + inc - len;
+      // 7 bits per byte, low group first, the last byte carries 0x80
+      if (len > 0) sb[off] = (uint8_t)((z & 0x7Fu) | (len == 1 ? 0x80u : 0u));
+      if (len > 1) sb[off + 1] = (uint8_t)(((z >> 7) & 0x7Fu) | (len == 2 ? 0x80u : 0u));
+      if (len > 2) sb[off + 2] = (uint8_t)(((z >> 14) & 0x7Fu) | (len == 3 ? 0x80u : 0u));
+      if (len > 3) sb[off + 3] = (uint8_t)(((z >> 21) & 0x7Fu) | (len == 4 ? 0x80u : 0u));
+      if (len > 4) sb[off + 4] = (uint8_t)(((z >> 28) & 0x7Fu) | 0x80u);
+      bo += __shfl_sync(0xffffffffu, inc, 31);
     }
+    if (lane < ((4u - (bo & 3u)) & 3u)) sb[bo + lane] = 0;  // zero padding of the last word
     pos += (bo + 3) / 4;
   }
   __syncwarp();
   return pos;
 }
 
-
 // ---------------------------------------------------------------- K2b: one warp per term
 constexpr int K2B_THREADS = 256;
 constexpr int K2B_WARPS = K2B_THREADS / 32;
+constexpr uint32_t K2B_ENC_WORDS = 3 + 2 * 129 + 1 + (5 * 127 + 3) / 4 + 1;  // enc_bound(255)
 
 struct K2bArgs {
   const uint64_t* bk_pos;
@@ -666,16 +644,17 @@ struct K2bArgs {
 
 __global__ void __launch_bounds__(K2B_THREADS, 4) k2b_union_kernel(const K2bArgs a) {
   __shared__ uint32_t s_buf[K2B_WARPS][REG_CAP];
-  __shared__ uint32_t s_stage[K2B_WARPS][intcomp::kStageWords];
+  __shared__ uint32_t s_enc[K2B_WARPS][K2B_ENC_WORDS + 3];
   const unsigned lane = lane_id(), warp = warp_id();
   const uint32_t b = blockIdx.x;
   const uint32_t D = a.bk_D[b];
   if (D == 0) return;
   const uint64_t rec_base = a.bk_pos[b];
   uint32_t* buf = s_buf[warp];
-  const bool inplace_enc = a.want_enc && !a.want_dec;
+  uint32_t* ebuf = s_enc[warp];
   uint32_t acc_t = 0, acc_tb = 0, acc_e = 0;
   uint64_t acc_p = 0;
+#pragma unroll 1
   for (uint32_t r = warp; r < D; r += K2B_WARPS) {
     const GroupIn g = a.gin[rec_base + r];
     GroupRec rec;
@@ -695,8 +674,9 @@ __global__ void __launch_bounds__(K2B_THREADS, 4) k2b_union_kernel(const K2bArgs
       continue;
     }
     const uint32_t L = g.L;
-    // gather the sources into the warp's slot
+    // gather the sources into the warp's slot: lane j copies source j
     uint32_t filled = 0;
+#pragma unroll 1
     for (uint32_t j0 = 0; j0 < g.c; j0 += 32) {
       const uint32_t j = j0 + lane;
       uint32_t n = 0;
@@ -707,7 +687,18 @@ __global__ void __launch_bounds__(K2B_THREADS, 4) k2b_union_kernel(const K2bArgs
       }
       const uint32_t inc = warp_inclusive_scan(n);
       uint32_t* dst = buf + filled + (inc - n);
-      for (uint32_t t = 0; t < n; t++) dst[t] = __ldg(src + t);
+      uint32_t t = 0;
+#pragma unroll 1
+      for (; t + 4 <= n; t += 4) {
+        const uint32_t x0 = __ldg(src + t), x1 = __ldg(src + t + 1), x2 = __ldg(src + t + 2),
+                       x3 = __ldg(src + t + 3);
+        dst[t] = x0;
+        dst[t + 1] = x1;
+        dst[t + 2] = x2;
+        dst[t + 3] = x3;
+      }
+#pragma unroll 1
+      for (; t < n; t++) dst[t] = __ldg(src + t);
       filled += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncwarp();
@@ -727,17 +718,8 @@ __global__ void __launch_bounds__(K2B_THREADS, 4) k2b_union_kernel(const K2bArgs
     if (a.want_dec)
       for (uint32_t e = lane; e < outn; e += 32) dec[e] = buf[e];
     if (a.want_enc && outn) {
-      uint32_t w = 0xFFFFFFFFu;
-      if (inplace_enc) {  // the slot holds REG_CAP words and the list is dead after encoding
-        if (outn <= 128) w = encode_regs_inplace<4>(buf, outn, REG_CAP);
-        else w = encode_regs_inplace<8>(buf, outn, REG_CAP);
-      }
-      if (w != 0xFFFFFFFFu) {
-        enc = w;
-        for (uint32_t e = lane; e < enc; e += 32) enc_dst[e] = buf[e];
-      } else {
-        enc = intcomp::enc_emit_warp(buf, outn, enc_dst, s_stage[warp]);
-      }
+      enc = encode_shared_warp(buf, outn, ebuf);
+      for (uint32_t e = lane; e < enc; e += 32) enc_dst[e] = ebuf[e];
     }
     __syncwarp();
     if (lane == 0) {
