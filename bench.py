@@ -279,18 +279,22 @@ def run_ours(a):
     # ---- roofline of the dominant kernel (per launch, live CUDA events) ----
     t_in = w.term_instances
     t_in_bytes = int(sum(int(s.term_off[-1]) for s in w.segments))
+    n_groups = int(prof_terms) if (prof_terms := stats[2]) else 0  # distinct terms ~ terms out
     alg = {
-        # K1: term bytes + term offsets + posting offsets in, 18 B of plan per instance out
-        "k1_merge_tiles": t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 18 * t_in,
-        # K2: plan + postings in, unioned postings + 16 B per group out
-        "k2_union": 14 * t_in + 4 * n_in + 4 * n_out + 16 * t_in + 4 * len(w.removed),
-        # K6: unioned postings in; term bytes/offsets, decoded postings and `_val` out
-        "k6_emit": 4 * n_out + 16 * t_in + t_out_bytes + 12 * t_out + 4 * n_out + val_size + 8 * t_out,
+        # K1b: term bytes + term offsets + posting offsets in; a 12 B source entry per instance
+        # and a 32 B record per distinct term out
+        "k1b_group": t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 12 * t_in
+        + 32 * n_groups,
+        # K2b: records + source entries + postings in; records + the `_val` stream out
+        "k2b_union": 32 * n_groups + 12 * t_in + 4 * n_in + 4 * len(w.removed) + 32 * n_groups
+        + val_size,
+        # K6: records + staged `_val` words + surviving term bytes in; the new segment out
+        "k6_emit": 32 * n_groups + val_size + t_out_bytes + val_size + t_out_bytes + 12 * t_out,
     }
     peak, peak_src = peaks()
     roof = None
     if prof:
-        top = max(prof, key=lambda e: e["ms"])
+        top = max((e for e in prof if e["name"] in alg), key=lambda e: e["ms"])
         per_launch_ms = top["ms"] / max(1, top["count"])
         b = alg.get(top["name"])
         if b is not None and per_launch_ms > 0:

@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
   uint16_t* grp = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
   uint16_t* reps = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
   uint16_t* table = reinterpret_cast<uint16_t*>(sp);
-  // alias, valid once the distinct terms are ordered (keys dead)
-  uint32_t* sbase = reinterpret_cast<uint32_t*>(key_hi);  // by representative: first source slot
+  // alias, valid once the hash table is done (K1B_HT u16 slots = CAP_I u32 words)
+  uint32_t* sbase = reinterpret_cast<uint32_t*>(table);  // by representative: first source slot
 
   const uint32_t tid = threadIdx.x;
   const unsigned lane = lane_id(), warp = warp_id();
@@ -174,24 +174,22 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     __syncthreads();
 
     // ---------------- (1) run starts; reset of the tile state ----------------
-    if (k <= 128) {  // one warp scans four segments per lane
-      if (warp == 0) {
-        uint32_t v[4], sum = 0;
+    if (k <= 128) {  // every warp scans for itself (identical values): no warp waits for another
+      uint32_t v[4], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int s = lane * 4 + j;
-          v[j] = s < k ? mm[s] - cur[s] : 0u;
-          sum += v[j];
-        }
-        uint32_t ex = warp_inclusive_scan(sum) - sum;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int s = lane * 4 + j;
-          if (s < k) rstart[s] = ex;
-          ex += v[j];
-        }
-        if (lane == 0) rstart[k] = size;
+      for (int j = 0; j < 4; j++) {
+        const int s = lane * 4 + j;
+        v[j] = s < k ? mm[s] - cur[s] : 0u;
+        sum += v[j];
       }
+      uint32_t ex = warp_inclusive_scan(sum) - sum;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int s = lane * 4 + j;
+        if (s < k) rstart[s] = ex;
+        ex += v[j];
+      }
+      if (lane == 0) rstart[k] = size;
     } else {
       uint32_t run = 0;
       for (int base = 0; base < k; base += K1B_THREADS) {
@@ -211,6 +209,27 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     }
     if (tid == 0) s_nreps = 0;
     __syncthreads();
+
+    // bytes past the 16-byte window, only needed for terms longer than cpl+16
+    auto tail_compare = [&](uint32_t x, uint32_t y) -> int {
+      const uint32_t skip = cpl + 16;
+      const uint32_t nx = tlen[x], ny = tlen[y];
+      if (nx > skip && ny > skip) {
+        const SegDesc& sx = a.segs[seg_a[x]];
+        const SegDesc& sy = a.segs[seg_a[y]];
+        const uint8_t* px = sx.tb + __ldg(sx.toff + idx_a[x]) + skip;
+        const uint8_t* py = sy.tb + __ldg(sy.toff + idx_a[y]) + skip;
+        return term_compare(px, nx - skip, py, ny - skip);
+      }
+      return nx < ny ? -1 : (nx > ny ? 1 : 0);
+    };
+    auto less = [&](uint16_t x, uint16_t y) -> bool {
+      const uint64_t hx = key_hi[x], hy = key_hi[y];
+      if (hx != hy) return hx < hy;
+      const uint64_t lx = key_lo[x], ly = key_lo[y];
+      if (lx != ly) return lx < ly;
+      return tail_compare(x, y) < 0;
+    };
 
     // ---------------- (2) key windows + posting lengths ----------------
     constexpr int PER = CAP_I / K1B_THREADS;
@@ -263,30 +282,12 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         }
       }
     }
-    __syncthreads();
-
-    // bytes past the 16-byte window, only needed for terms longer than cpl+16
-    auto tail_compare = [&](uint32_t x, uint32_t y) -> int {
-      const uint32_t skip = cpl + 16;
-      const uint32_t nx = tlen[x], ny = tlen[y];
-      if (nx > skip && ny > skip) {
-        const SegDesc& sx = a.segs[seg_a[x]];
-        const SegDesc& sy = a.segs[seg_a[y]];
-        const uint8_t* px = sx.tb + __ldg(sx.toff + idx_a[x]) + skip;
-        const uint8_t* py = sy.tb + __ldg(sy.toff + idx_a[y]) + skip;
-        return term_compare(px, nx - skip, py, ny - skip);
-      }
-      return nx < ny ? -1 : (nx > ny ? 1 : 0);
-    };
-    auto less = [&](uint16_t x, uint16_t y) -> bool {
-      const uint64_t hx = key_hi[x], hy = key_hi[y];
-      if (hx != hy) return hx < hy;
-      const uint64_t lx = key_lo[x], ly = key_lo[y];
-      if (lx != ly) return lx < ly;
-      return tail_compare(x, y) < 0;
-    };
+    // a thread's keys are visible to the block before it enters the hash table: whoever finds
+    // its slot taken reads the owner's keys after the CAS
+    __threadfence_block();
 
     // ---------------- (3) group equal terms (hash table of representatives) ----------------
+#pragma unroll 1
     for (uint32_t i = tid; i < size; i += K1B_THREADS) {
       const uint64_t kh = key_hi[i], kl = key_lo[i];
       uint64_t h = kh * 0x9E3779B97F4A7C15ull;
@@ -305,8 +306,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
           reps[atomicAdd(&s_nreps, 1u)] = (uint16_t)i;
           break;
         }
-        if (key_hi[prev] == kh && key_lo[prev] == kl && tlen[prev] == tlen[i] &&
-            tail_compare(i, prev) == 0) {
+        if (*(volatile uint64_t*)&key_hi[prev] == kh && *(volatile uint64_t*)&key_lo[prev] == kl &&
+            *(volatile uint16_t*)&tlen[prev] == tlen[i] && tail_compare(i, prev) == 0) {
           rep = prev;
           break;
         }
@@ -321,44 +322,54 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     const uint32_t D = s_nreps;
 
     // ---------------- (4) order the distinct terms; one record per term ----------------
-    if (D <= K1B_SMALL_D) {  // rank by counting: one thread per term, D comparisons each
-      uint32_t rank = 0, ib = 0, pst = 0, est = 0, me = 0;
-      if (tid < D) {
-        me = reps[tid];
-        for (uint32_t j = 0; j < D; j++) {
-          const uint32_t o = reps[j];
-          if (o != me && less((uint16_t)o, (uint16_t)me)) {
-            rank++;
-            ib += cnt[o];
-            if (gl[o] <= REG_CAP) {
-              pst += gl[o];
-              est += enc_slot_words(gl[o]);
+    if (D <= K1B_SMALL_D) {  // rank by counting: one warp per term, lanes over the others
+#pragma unroll 1
+      for (uint32_t t = warp; t < D; t += K1B_WARPS) {
+        const uint32_t me = reps[t];
+        uint32_t rank = 0;
+        uint64_t acc = 0;  // instances | postings << 16 | staging words << 36 of the smaller terms
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < D; j0 += 32) {
+          const uint32_t j = j0 + lane;
+          uint64_t mine = 0;
+          bool lt = false;
+          if (j < D) {
+            const uint32_t o = reps[j];
+            lt = o != me && less((uint16_t)o, (uint16_t)me);
+            if (lt) {
+              mine = cnt[o];
+              if (gl[o] <= REG_CAP)
+                mine |= ((uint64_t)gl[o] << 16) | ((uint64_t)enc_slot_words(gl[o]) << 36);
             }
           }
+          rank += __popc(__ballot_sync(0xffffffffu, lt));
+          acc += warp_sum(mine);
         }
-      }
-      __syncthreads();  // the keys are dead from here on
-      if (tid < D) {
-        const SegDesc& sd = a.segs[seg_a[me]];
-        GroupIn g;
-        g.inst = sd.base + (idx_a[me] - sd.lo);
-        g.tlen = tlen[me];
-        g.src = (uint32_t)rec_base + icount + ib;
-        g.c = cnt[me];
-        g.L = gl[me];
-        g.pst = pcount + pst;
-        g.eslot = ecount + est;
-        g.pad = 0;
-        a.gin[rec_base + dcount + rank] = g;
-        sbase[me] = g.src;
-        if (rank == D - 1) {
-          s_tot[0] = pst + (gl[me] <= REG_CAP ? gl[me] : 0u);
-          s_tot[1] = est + (gl[me] <= REG_CAP ? enc_slot_words(gl[me]) : 0u);
+        if (lane == 0) {
+          const uint32_t ib = (uint32_t)(acc & 0xFFFFu), pst = (uint32_t)((acc >> 16) & 0xFFFFFu),
+                         est = (uint32_t)(acc >> 36);
+          const bool light = gl[me] <= REG_CAP;
+          const SegDesc& sd = a.segs[seg_a[me]];
+          GroupIn g;
+          g.inst = sd.base + (idx_a[me] - sd.lo);
+          g.tlen = tlen[me];
+          g.src = (uint32_t)rec_base + icount + ib;
+          g.c = cnt[me];
+          g.L = gl[me];
+          g.pst = pcount + pst;
+          g.eslot = ecount + est;
+          g.pad = 0;
+          a.gin[rec_base + dcount + rank] = g;
+          sbase[me] = g.src;
+          if (rank == D - 1) {
+            s_tot[0] = pst + (light ? gl[me] : 0u);
+            s_tot[1] = est + (light ? enc_slot_words(gl[me]) : 0u);
+          }
         }
       }
     } else {
       bitonic_sort_any(reps, D, tid, (uint32_t)K1B_THREADS, less, [] { __syncthreads(); });
-      __syncthreads();  // the keys are dead from here on
+      __syncthreads();
       uint32_t run_i = 0, run_p = 0, run_e = 0;
       for (uint32_t base = 0; base < D; base += K1B_THREADS) {
         const uint32_t r = base + tid;
@@ -416,6 +427,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     pcount += s_tot[0];
     ecount += s_tot[1];
     W -= size;
+    if (W == 0) break;
     __syncthreads();
     for (int s = tid; s < k; s += K1B_THREADS) cur[s] = mm[s];
     __syncthreads();
@@ -444,12 +456,22 @@ __device__ __forceinline__ void shuffle_stage(uint32_t (&v)[R], uint32_t mask, b
 template <int R>
 __device__ __forceinline__ void sort_regs(uint32_t (&v)[R]) {
   const unsigned lane = lane_id();
-  // block sizes 2..32: everything stays inside one register row
+  // block sizes 2..32: everything stays inside one register row.  Up to four rows the network
+  // is small enough to unroll completely (5 KB of SASS); eight rows keep the distance loops.
+  if (R <= 4) {
+#pragma unroll
+    for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+      shuffle_stage<R>(v, kk - 1, (lane & (kk >> 1)) == 0);
+#pragma unroll
+      for (uint32_t j = kk >> 2; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+    }
+  } else {
 #pragma unroll 1
-  for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
-    shuffle_stage<R>(v, kk - 1, (lane & (kk >> 1)) == 0);
+    for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+      shuffle_stage<R>(v, kk - 1, (lane & (kk >> 1)) == 0);
 #pragma unroll 1
-    for (uint32_t j = kk >> 2; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+      for (uint32_t j = kk >> 2; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+    }
   }
   // block sizes 64..32R: flip and the first half-cleaners pair register rows
 #pragma unroll
@@ -477,8 +499,13 @@ __device__ __forceinline__ void sort_regs(uint32_t (&v)[R]) {
         }
       }
     }
+    if (R <= 4) {
+#pragma unroll
+      for (uint32_t j = 16; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+    } else {
 #pragma unroll 1
-    for (uint32_t j = 16; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+      for (uint32_t j = 16; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+    }
   }
 }
 

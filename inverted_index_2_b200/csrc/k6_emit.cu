@@ -7,6 +7,7 @@
 // bucket walks the bucket's records in chunks of 256, a block scan over the surviving terms
 // gives every term its output slots (bucket bases come from the bucket-level scan), then warps
 // copy term bytes, encoded words and/or decoded postings.  Pure HBM copy work.
+#include "keys.cuh"
 #include "union.cuh"
 
 namespace ii2 {
@@ -159,46 +160,53 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   return II2_OK;
 }
 
-// min / max term of the merged order (pre-filter, shard.go:176-179): the first record of the
-// first non-empty bucket and the last record of the last one.
-__global__ void __launch_bounds__(256)
-k6_minmax_kernel(const SegDesc* __restrict__ segs, int k, const uint64_t* __restrict__ bk_pos,
-                 const uint32_t* __restrict__ bk_D, uint32_t B, const GroupRec* __restrict__ recs,
-                 uint8_t* __restrict__ out) {
-  __shared__ uint32_t s_first, s_last;
-  if (threadIdx.x == 0) {
-    s_first = 0xFFFFFFFFu;
-    s_last = 0;
-  }
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
-    if (bk_D[b]) {
-      atomicMin(&s_first, b);
-      atomicMax(&s_last, b);
-    }
-  }
-  __syncthreads();
-  if (s_first == 0xFFFFFFFFu) {
-    if (threadIdx.x < 2) reinterpret_cast<uint32_t*>(out)[threadIdx.x] = 0;
-    return;
+// min / max term of the merged order (pre-filter, shard.go:176-179) = the smallest first term
+// and the largest last term over the segments' windows.  One warp.
+__global__ void __launch_bounds__(32)
+k6_minmax_kernel(const SegDesc* __restrict__ segs, int k, uint8_t* __restrict__ out) {
+  const unsigned lane = lane_id();
+  int best[2] = {-1, -1};
+  for (int s = lane; s < k; s += 32) {
+    const SegDesc sd = segs[s];
+    if (sd.hi <= sd.lo) continue;
+    if (best[0] < 0 ||
+        keyed_compare(keyed_term(sd, sd.lo), keyed_term(segs[best[0]], segs[best[0]].lo)) < 0)
+      best[0] = s;
+    if (best[1] < 0 ||
+        keyed_compare(keyed_term(sd, sd.hi - 1), keyed_term(segs[best[1]], segs[best[1]].hi - 1)) > 0)
+      best[1] = s;
   }
   uint32_t at = 8;
   for (int which = 0; which < 2; which++) {
-    const uint32_t b = which ? s_last : s_first;
-    const GroupRec g = recs[bk_pos[b] + (which ? bk_D[b] - 1 : 0)];
-    int s;
-    uint32_t idx;
-    locate_instance(segs, k, g.inst, s, idx);
-    const uint32_t o = segs[s].toff[idx], n = g.tlen;
-    if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(out)[which] = n;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[at + i] = segs[s].tb[o + i];
+    int b = best[which];
+    for (int d = 16; d > 0; d >>= 1) {
+      const int o = __shfl_xor_sync(0xffffffffu, b, d);
+      if (o >= 0) {
+        if (b < 0) {
+          b = o;
+        } else if (o != b) {
+          const uint32_t ib = which ? segs[b].hi - 1 : segs[b].lo, io = which ? segs[o].hi - 1 : segs[o].lo;
+          const int c = keyed_compare(keyed_term(segs[o], io), keyed_term(segs[b], ib));
+          // ties: the smaller segment index, so every lane converges on the same winner
+          if (which ? (c > 0 || (c == 0 && o < b)) : (c < 0 || (c == 0 && o < b))) b = o;
+        }
+      }
+    }
+    uint32_t n = 0;
+    if (b >= 0) {
+      const uint32_t idx = which ? segs[b].hi - 1 : segs[b].lo;
+      const uint32_t o = segs[b].toff[idx];
+      n = segs[b].toff[idx + 1] - o;
+      for (uint32_t i = lane; i < n; i += 32) out[at + i] = segs[b].tb[o + i];
+    }
+    if (lane == 0) reinterpret_cast<uint32_t*>(out)[which] = n;
     at += n;
   }
 }
 
 int k6_minmax(const MergePlan& plan, const UnionOut& u, uint8_t* d_out, cudaStream_t s) {
-  k6_minmax_kernel<<<1, 256, 0, s>>>(plan.segs, plan.k, plan.bk_pos(), u.bk_D.p, plan.n_buckets,
-                                     u.recs.p, d_out);
+  (void)u;
+  k6_minmax_kernel<<<1, 32, 0, s>>>(plan.segs, plan.k, d_out);
   II2_LAUNCHED();
   return II2_OK;
 }
