@@ -124,12 +124,12 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     ~PinnedBlock() { pinned_free(p); }
   } stage;
   const size_t nsegx = nseg ? nseg : 1;
-  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 4 * (nsegx + 1) + minlen + maxlen + 64;
+  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 8 * (nsegx + 1) + minlen + maxlen + 64;
   stage.p = pinned_alloc(stage_bytes);
   if (!stage.p) return II2_ERR_NOMEM;
   SegDesc* h = static_cast<SegDesc*>(stage.p);
   uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h + nsegx);
-  uint8_t* h_bounds = reinterpret_cast<uint8_t*>(h_sbase + nsegx + 1);
+  uint8_t* h_bounds = reinterpret_cast<uint8_t*>(h_sbase + 2 * (nsegx + 1));
   uint64_t n_total64 = 0, n_in = 0;
   for (int i = 0; i < nseg; i++) {
     const ii2_seg* g = segs[i];

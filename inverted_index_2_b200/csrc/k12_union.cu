@@ -58,7 +58,6 @@ struct K1bArgs {
   const SegDesc* segs;
   int k;
   const uint32_t* part;
-  const uint32_t* row_of;
   const uint64_t* bk_pos;
   const uint32_t* bk_cpl;
   GroupIn* gin;
@@ -115,7 +114,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     return;
   }
   {
-    const uint32_t r0 = a.row_of[b], r1 = a.row_of[b + 1];
+    const uint32_t r0 = b, r1 = b + 1;
     for (int s = tid; s < k; s += K1B_THREADS) {
       cur[s] = a.part[(uint64_t)r0 * k + s];
       endr[s] = a.part[(uint64_t)r1 * k + s];
@@ -1001,7 +1000,6 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     a.segs = plan.segs;
     a.k = k;
     a.part = plan.part.p;
-    a.row_of = plan.row_of.p;
     a.bk_pos = plan.bk_pos();
     a.bk_cpl = plan.bk_cpl.p;
     a.gin = gin.p;

@@ -6,17 +6,21 @@
 //
 //   k1_sample_keys     every segment contributes evenly spaced sample terms in proportion to
 //                      its size (about one per 640 instances overall); 16-byte key windows.
-//   k1_rank_partition  one warp per sample x, lanes over segments: (a) binary search among the
-//                      segment's own samples -> how many are smaller -> the rank of x in the
-//                      merged sample order is the sum over segments (a k-way merge by ranking,
-//                      no sort); (b) the two neighbouring samples bound the lower_bound of x in
-//                      the full segment to ~n/m terms, finished by a short binary search.
-//                      Row x of `part` = lower_bound of x in every segment.
+//   k1_rank_samples    one warp per sample x, lanes over segments: binary search among every
+//                      segment's samples -> how many are smaller -> the rank of x in the merged
+//                      sample order is the sum over segments (a k-way merge by ranking, no
+//                      sort).  Sorted splitter arrays by scatter.
+//   k1_partition_chunks merge-path partition: one CTA per 2048-term chunk of one segment stages
+//                      the chunk's key windows in shared memory (coalesced, every term byte
+//                      read once) and locates the splitters that fall inside it.  Row r+1 of
+//                      `part` = lower_bound of splitter r in every segment.
 //   k1_bucket_stats    per bucket: instances, input postings (from the posting offsets),
 //                      common prefix length; then one scan -> bucket bases.
 //
 // Integer/byte work; every probe is an L2 hit after the first touch (samples and offsets of
 // 64 segments are a few MB).
+#include <algorithm>
+
 #include "keys.cuh"
 #include "plan.cuh"
 
@@ -69,27 +73,22 @@ __device__ __forceinline__ KeyedTerm sample_term(const SampleArrays& sa, uint32_
   return t;
 }
 
+// One warp per sample x, lanes over segments: how many samples of every segment sort before x
+// (ties between equal terms broken by segment) = the rank of x among all samples.  The sorted
+// splitter arrays are filled by scattering x to its rank.
 __global__ void __launch_bounds__(256)
-k1_rank_partition(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ sbase,
-                  uint32_t S, SampleArrays sa, uint32_t* __restrict__ part,
-                  uint32_t* __restrict__ row_of) {
+k1_rank_samples(int k, const uint32_t* __restrict__ sbase, uint32_t S, SampleArrays sa,
+                SampleArrays sorted) {
   const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = lane_id();
-  if (x >= S + 2) return;
-  if (x >= S) {  // row S = window starts, row S+1 = window ends
-    for (int s = lane; s < k; s += 32) part[(uint64_t)x * k + s] = x == S ? segs[s].lo : segs[s].hi;
-    if (lane == 0) row_of[x == S ? 0 : S + 1] = x;
-    return;
-  }
+  if (x >= S) return;
   const KeyedTerm tx = sample_term(sa, x);
   const uint32_t sx = sa.seg[x];
   uint32_t racc = 0;
   for (int s = lane; s < k; s += 32) {
     const uint32_t b0 = sbase[s], m = sbase[s + 1] - b0;
-    uint32_t lb;
     if ((uint32_t)s == sx) {
       racc += x - b0;
-      lb = sa.idx[x];
     } else {
       uint32_t lo = 0, hi = m;  // samples of s strictly below x
       while (lo < hi) {
@@ -99,30 +98,112 @@ k1_rank_partition(const SegDesc* __restrict__ segs, int k, const uint32_t* __res
         else
           hi = mid;
       }
-      const uint32_t q = lo;
-      const SegDesc sd = segs[s];
-      const uint32_t wlo = q > 0 ? sa.idx[b0 + q - 1] + 1 : sd.lo;
-      uint32_t whi = sd.hi;
-      bool equal = false;
-      if (q < m) {
-        whi = sa.idx[b0 + q];
-        equal = keyed_compare(sample_term(sa, b0 + q), tx) == 0;
-      }
       // ties between equal sample terms are ordered by segment
-      racc += q + ((equal && (uint32_t)s < sx) ? 1u : 0u);
-      lb = equal ? whi : keyed_lower_bound(sd, wlo, whi, tx);
+      const bool equal = lo < m && (uint32_t)s < sx && keyed_compare(sample_term(sa, b0 + lo), tx) == 0;
+      racc += lo + (equal ? 1u : 0u);
     }
-    part[(uint64_t)x * k + s] = lb;
   }
   racc = warp_sum(racc);
-  if (lane == 0) row_of[racc + 1] = x;
+  if (lane == 0) {
+    sorted.hi[racc] = tx.hi;
+    sorted.lo[racc] = tx.lo;
+    sorted.ptr[racc] = reinterpret_cast<uint64_t>(tx.p);
+    sorted.len[racc] = tx.len;
+  }
+}
+
+// Merge-path partition: one CTA per chunk of K1_CHUNK consecutive terms of one segment.  The
+// chunk's 16-byte key windows are staged in shared memory (coalesced: every term byte of the
+// dictionary is read exactly once), the splitters that fall inside the chunk are found with two
+// searches over the sorted splitter array, and each of them is located in the staged keys.
+// part row r+1 = lower_bound of splitter r in every segment; row 0 / S+1 = window starts / ends.
+constexpr uint32_t K1_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256)
+k1_partition_chunks(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ cbase,
+                    uint32_t S, SampleArrays sp, uint32_t* __restrict__ part) {
+  __shared__ uint64_t s_hi[K1_CHUNK], s_lo[K1_CHUNK];
+  __shared__ uint32_t s_len[K1_CHUNK];
+  __shared__ uint32_t s_range[2];
+  const uint32_t c = blockIdx.x;
+  int lo = 0, hi = k;  // segment of chunk c: last s with cbase[s] <= c
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cbase[mid + 1] <= c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const int s = lo;
+  const SegDesc sd = segs[s];
+  const uint32_t nchunks = cbase[s + 1] - cbase[s], ci = c - cbase[s];
+  const uint32_t i0 = sd.lo + ci * K1_CHUNK;
+  const uint32_t i1 = (ci + 1 == nchunks) ? sd.hi : i0 + K1_CHUNK;
+  const uint32_t n = i1 - i0;
+  for (uint32_t t = threadIdx.x; t < n; t += 256) {
+    const KeyedTerm kt = keyed_term(sd, i0 + t);
+    s_hi[t] = kt.hi;
+    s_lo[t] = kt.lo;
+    s_len[t] = kt.len;
+  }
+  if (threadIdx.x < 2) {
+    // splitters <= the term before the chunk (0 for the first chunk) and <= its last term
+    // (all of them for the last chunk, whose tail maps to the window end)
+    uint32_t r;
+    const bool first = threadIdx.x == 0;
+    if (first ? ci == 0 : ci + 1 == nchunks) {
+      r = first ? 0u : S;
+    } else {
+      const KeyedTerm t = keyed_term(sd, first ? i0 - 1 : i1 - 1);
+      uint32_t a = 0, b = S;  // first splitter > t
+      while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (keyed_compare(sample_term(sp, mid), t) <= 0)
+          a = mid + 1;
+        else
+          b = mid;
+      }
+      r = a;
+    }
+    s_range[threadIdx.x] = r;
+    if (ci == 0) part[(uint64_t)(first ? 0 : S + 1) * k + s] = first ? sd.lo : sd.hi;
+  }
+  __syncthreads();
+  const uint32_t ra = s_range[0], rb = s_range[1];
+  for (uint32_t r = ra + threadIdx.x; r < rb; r += 256) {
+    const KeyedTerm x = sample_term(sp, r);
+    uint32_t a = 0, b = n;  // first staged term >= x
+    while (a < b) {
+      const uint32_t mid = (a + b) >> 1;
+      KeyedTerm t;
+      t.hi = s_hi[mid];
+      t.lo = s_lo[mid];
+      t.len = s_len[mid];
+      int cmp;
+      if (t.hi != x.hi) {
+        cmp = t.hi < x.hi ? -1 : 1;
+      } else if (t.lo != x.lo) {
+        cmp = t.lo < x.lo ? -1 : 1;
+      } else if (t.len > 16 && x.len > 16) {
+        t.p = sd.tb + __ldg(sd.toff + i0 + mid);
+        cmp = term_compare(t.p + 16, t.len - 16, x.p + 16, x.len - 16);
+      } else {
+        cmp = t.len < x.len ? -1 : (t.len > x.len ? 1 : 0);
+      }
+      if (cmp < 0)
+        a = mid + 1;
+      else
+        b = mid;
+    }
+    part[(uint64_t)(r + 1) * k + s] = i0 + a;
+  }
 }
 
 // One warp per bucket.  raw[0][b] = instances, raw[1][b] = input postings.
 __global__ void __launch_bounds__(256)
-k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArrays sa,
-                const uint32_t* __restrict__ part, const uint32_t* __restrict__ row_of,
-                uint64_t* __restrict__ raw, uint32_t* __restrict__ bk_cpl) {
+k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArrays sp,
+                const uint32_t* __restrict__ part, uint64_t* __restrict__ raw,
+                uint32_t* __restrict__ bk_cpl) {
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t B = S + 1;
   if (b > B) return;
@@ -131,10 +212,9 @@ k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArray
     if (lane == 0) raw[B] = raw[(uint64_t)(B + 1) + B] = 0;
     return;
   }
-  const uint32_t r0 = row_of[b], r1 = row_of[b + 1];
   uint64_t w = 0, p = 0;
   for (int s = lane; s < k; s += 32) {
-    const uint32_t a = part[(uint64_t)r0 * k + s], e = part[(uint64_t)r1 * k + s];
+    const uint32_t a = part[(uint64_t)b * k + s], e = part[(uint64_t)(b + 1) * k + s];
     w += e - a;
     if (e > a) p += __ldg(segs[s].poff + e) - __ldg(segs[s].poff + a);
   }
@@ -144,10 +224,10 @@ k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArray
     raw[b] = w;
     raw[(uint64_t)(B + 1) + b] = p;
     uint32_t c = 0;
-    if (r0 < S && r1 < S) {  // both delimiting splitters exist
-      const uint8_t* x = reinterpret_cast<const uint8_t*>(sa.ptr[r0]);
-      const uint8_t* y = reinterpret_cast<const uint8_t*>(sa.ptr[r1]);
-      const uint32_t m = sa.len[r0] < sa.len[r1] ? sa.len[r0] : sa.len[r1];
+    if (b >= 1 && b < S) {  // both delimiting splitters exist: b-1 and b
+      const uint8_t* x = reinterpret_cast<const uint8_t*>(sp.ptr[b - 1]);
+      const uint8_t* y = reinterpret_cast<const uint8_t*>(sp.ptr[b]);
+      const uint32_t m = sp.len[b - 1] < sp.len[b] ? sp.len[b - 1] : sp.len[b];
       while (c < m && x[c] == y[c]) c++;
     }
     bk_cpl[b] = c;
@@ -161,43 +241,48 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     set_last_error("k1: %d segments in one pass (max %d)", k, kMaxSegs);
     return II2_ERR_UNSUPPORTED;
   }
-  // samples per segment, proportional to its window
+  // samples per segment, proportional to its window; chunks of the merge-path partition
   uint64_t want = N / kInstancesPerBucket;
   if (want > kMaxBuckets - 1) want = kMaxBuckets - 1;
+  uint32_t* cbase = sbase + (k + 1);
   sbase[0] = 0;
+  cbase[0] = 0;
   for (int i = 0; i < k; i++) {
     const uint64_t n = h_segs[i].hi - h_segs[i].lo;
     uint64_t m = N ? want * n / N : 0;
     if (m + 1 > n) m = n ? n - 1 : 0;
     sbase[i + 1] = sbase[i] + (uint32_t)m;
+    cbase[i + 1] = cbase[i] + (uint32_t)std::max<uint64_t>(1, (n + K1_CHUNK - 1) / K1_CHUNK);
   }
-  const uint32_t S = sbase[k], B = S + 1;
+  const uint32_t S = sbase[k], B = S + 1, n_chunks = cbase[k];
   plan.n_samples = S;
   plan.n_buckets = B;
   ProfScope scope("k1_plan", s);
   II2_TRY(plan.part.alloc_scratch((size_t)(S + 2) * k, s));
-  II2_TRY(plan.row_of.alloc_scratch(B + 1, s));
   II2_TRY(plan.bk_cpl.alloc_scratch(B, s));
   II2_TRY(plan.bk_WP.alloc_scratch(2 * (size_t)(B + 1), s));
   II2_TRY(plan.totals.alloc_scratch(2, s));
-  DevBuf<uint32_t> d_sbase, d_u32;
+  DevBuf<uint32_t> d_base, d_u32;
   DevBuf<uint64_t> d_u64;
-  II2_TRY(d_sbase.alloc_scratch(k + 1, s));
-  II2_TRY(d_u64.alloc_scratch(3 * (size_t)(S ? S : 1), s));
-  II2_TRY(d_u32.alloc_scratch(3 * (size_t)(S ? S : 1), s));
-  II2_CUDA_TRY(cudaMemcpyAsync(d_sbase.p, sbase, (k + 1) * 4, cudaMemcpyHostToDevice, s));
   const size_t Sx = S ? S : 1;
+  II2_TRY(d_base.alloc_scratch(2 * (size_t)(k + 1), s));
+  II2_TRY(d_u64.alloc_scratch(6 * Sx, s));
+  II2_TRY(d_u32.alloc_scratch(4 * Sx, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(d_base.p, sbase, 2 * (size_t)(k + 1) * 4, cudaMemcpyHostToDevice, s));
+  const uint32_t* d_sbase = d_base.p;
+  const uint32_t* d_cbase = d_base.p + (k + 1);
   SampleArrays sa{d_u64.p, d_u64.p + Sx, d_u64.p + 2 * Sx, d_u32.p, d_u32.p + Sx, d_u32.p + 2 * Sx};
+  SampleArrays sp{d_u64.p + 3 * Sx, d_u64.p + 4 * Sx, d_u64.p + 5 * Sx, d_u32.p + 3 * Sx, nullptr, nullptr};
   if (S) {
-    k1_sample_keys<<<div_up(S, 256), 256, 0, s>>>(plan.segs, k, d_sbase.p, S, sa);
+    k1_sample_keys<<<div_up(S, 256), 256, 0, s>>>(plan.segs, k, d_sbase, S, sa);
+    II2_LAUNCHED();
+    k1_rank_samples<<<div_up((uint64_t)S * 32, 256), 256, 0, s>>>(k, d_sbase, S, sa, sp);
     II2_LAUNCHED();
   }
-  k1_rank_partition<<<div_up((uint64_t)(S + 2) * 32, 256), 256, 0, s>>>(plan.segs, k, d_sbase.p, S,
-                                                                       sa, plan.part.p,
-                                                                       plan.row_of.p);
+  k1_partition_chunks<<<n_chunks, 256, 0, s>>>(plan.segs, k, d_cbase, S, sp, plan.part.p);
   II2_LAUNCHED();
   k1_bucket_stats<<<div_up((uint64_t)(B + 1) * 32, 256), 256, 0, s>>>(
-      plan.segs, k, S, sa, plan.part.p, plan.row_of.p, plan.bk_WP.p, plan.bk_cpl.p);
+      plan.segs, k, S, sp, plan.part.p, plan.bk_WP.p, plan.bk_cpl.p);
   II2_LAUNCHED();
   II2_TRY(exclusive_scan_multi_u64(plan.bk_WP.p, plan.bk_WP.p, B + 1, 2, plan.totals.p, s));
   return II2_OK;

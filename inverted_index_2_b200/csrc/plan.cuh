@@ -20,10 +20,9 @@ struct MergePlan {
   uint32_t n_samples = 0;         // S
   uint32_t n_buckets = 0;         // B = S + 1
   const SegDesc* segs = nullptr;  // [k] device, windows filled in
-  // rows of k lower bounds: row x < S = lower_bound of sample x in every segment (sample order,
-  // NOT sorted); row S = window starts; row S+1 = window ends
+  // rows of k lower bounds: row 0 = window starts, row r+1 = lower_bound of splitter r (sorted)
+  // in every segment, row S+1 = window ends; bucket b spans rows b .. b+1
   DevBuf<uint32_t> part;          // [(S+2) * k]
-  DevBuf<uint32_t> row_of;        // [B+1] bucket b spans rows row_of[b] .. row_of[b+1]
   DevBuf<uint32_t> bk_cpl;        // [B]   common prefix length of all terms in the bucket
   DevBuf<uint64_t> bk_WP;         // [2][B+1] exclusive prefixes: instances / input postings
   const uint64_t* bk_pos() const { return bk_WP.p; }
@@ -34,7 +33,7 @@ struct MergePlan {
 // K1: choose splitters and partition every segment (the k-way merge of the term dictionaries,
 // go-iterators MergingIterator built at shard.go:267 with file.CompareTermValues, is finished
 // per bucket inside K12).  plan.k / n_total / segs must be set; h_segs = host copy of segs
-// (windows), used to spread the samples; sbase = k+1 words of PINNED host scratch that stay
+// (windows), used to spread the samples; sbase = 2(k+1) words of PINNED host scratch that stay
 // valid until the stream has drained (the call does not synchronise).
 int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaStream_t s);
 
