@@ -69,7 +69,7 @@ struct K1bArgs {
 
 __host__ __device__ inline size_t k1b_smem_bytes(int k) {
   return (size_t)CAP_I * 16                      // key_hi, key_lo
-         + (size_t)CAP_I * 4 * 4                 // idx, plen, gl, cnt
+         + (size_t)CAP_I * 4 * 3                 // inst, cnt, gl
          + (size_t)(5 * k + 1) * 4               // cur, mm, hi, endr, rstart
          + (size_t)CAP_I * 2 * 4                 // seg, tlen, grp, reps
          + (size_t)K1B_HT * 2 + 64;
@@ -85,20 +85,20 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
   uint8_t* sp = smem_raw;
   uint64_t* key_hi = reinterpret_cast<uint64_t*>(sp); sp += CAP_I * 8;
   uint64_t* key_lo = reinterpret_cast<uint64_t*>(sp); sp += CAP_I * 8;
-  uint32_t* idx_a = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
-  uint32_t* plen = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
-  uint32_t* gl = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;   // by representative
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;  // by representative
+  // by representative: sources / Σ source lengths (each saturated at REG_CAP + 1)
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
+  uint32_t* gl = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
+  uint32_t* inst_a = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;  // global instance id
+  uint16_t* seg_a = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
+  uint16_t* tlen = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
+  uint16_t* grp = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
+  uint16_t* reps = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
+  uint16_t* table = reinterpret_cast<uint16_t*>(sp); sp += K1B_HT * 2;  // 16-byte aligned
   uint32_t* cur = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* mm = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* hib = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* endr = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* rstart = reinterpret_cast<uint32_t*>(sp); sp += (k + 1) * 4;
-  uint16_t* seg_a = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
-  uint16_t* tlen = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
-  uint16_t* grp = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
-  uint16_t* reps = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
-  uint16_t* table = reinterpret_cast<uint16_t*>(sp);
   // alias, valid once the hash table is done (K1B_HT u16 slots = CAP_I u32 words)
   uint32_t* sbase = reinterpret_cast<uint32_t*>(table);  // by representative: first source slot
 
@@ -201,11 +201,11 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       }
       if (tid == 0) rstart[k] = size;
     }
-    for (uint32_t t = tid; t < K1B_HT; t += K1B_THREADS) table[t] = K1B_EMPTY;
-    for (uint32_t i = tid; i < size; i += K1B_THREADS) {
-      cnt[i] = 0;
-      gl[i] = 0;
-    }
+    static_assert(K1B_HT * 2 == K1B_THREADS * 16, "one 16-byte store per thread resets the table");
+    reinterpret_cast<uint4*>(table)[tid] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    // cnt and gl are adjacent: 2 * CAP_I words, zeroed four at a time
+    for (uint32_t i = 4 * tid; i < 2 * CAP_I; i += 4 * K1B_THREADS)
+      *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_nreps = 0;
     __syncthreads();
 
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       if (nx > skip && ny > skip) {
         const SegDesc& sx = a.segs[seg_a[x]];
         const SegDesc& sy = a.segs[seg_a[y]];
-        const uint8_t* px = sx.tb + __ldg(sx.toff + idx_a[x]) + skip;
-        const uint8_t* py = sy.tb + __ldg(sy.toff + idx_a[y]) + skip;
+        const uint8_t* px = sx.tb + __ldg(sx.toff + (sx.lo + (inst_a[x] - sx.base))) + skip;
+        const uint8_t* py = sy.tb + __ldg(sy.toff + (sy.lo + (inst_a[y] - sy.base))) + skip;
         return term_compare(px, nx - skip, py, ny - skip);
       }
       return nx < ny ? -1 : (nx > ny ? 1 : 0);
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     // ---------------- (2) key windows + posting lengths ----------------
     constexpr int PER = CAP_I / K1B_THREADS;
     uint64_t pp[PER];  // first posting of the thread's instances (kept for the source list)
+    uint32_t pl[PER];  // their lengths
     {
       int sg[PER];
       uint32_t ix[PER], to[PER], tn[PER];
@@ -274,10 +275,11 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
           key_hi[i] = kh;
           key_lo[i] = kl;
           tlen[i] = (uint16_t)n;
-          idx_a[i] = ix[j];
+          const SegDesc& sd = a.segs[sg[j]];
+          inst_a[i] = sd.base + (ix[j] - sd.lo);
           seg_a[i] = (uint16_t)sg[j];
-          plen[i] = (p1[j] - pp[j]) > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)(p1[j] - pp[j]);
-          pp[j] = reinterpret_cast<uint64_t>(a.segs[sg[j]].post + pp[j]);
+          pl[j] = (p1[j] - pp[j]) > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)(p1[j] - pp[j]);
+          pp[j] = reinterpret_cast<uint64_t>(sd.post + pp[j]);
         }
       }
     }
@@ -286,8 +288,10 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     __threadfence_block();
 
     // ---------------- (3) group equal terms (hash table of representatives) ----------------
-#pragma unroll 1
-    for (uint32_t i = tid; i < size; i += K1B_THREADS) {
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const uint32_t i = tid + j * K1B_THREADS;
+      if (i >= size) break;
       const uint64_t kh = key_hi[i], kl = key_lo[i];
       uint64_t h = kh * 0x9E3779B97F4A7C15ull;
       h ^= (kl + 0xD6E8FEB86659FD93ull + (h << 6) + (h >> 2));
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       grp[i] = (uint16_t)rep;
       atomicAdd(&cnt[rep], 1u);
       // term length, saturating per source so the sum cannot wrap: heavy iff sum > REG_CAP
-      atomicAdd(&gl[rep], plen[i] > REG_CAP ? REG_CAP + 1 : plen[i]);
+      atomicAdd(&gl[rep], pl[j] > REG_CAP ? REG_CAP + 1 : pl[j]);
     }
     __syncthreads();
     const uint32_t D = s_nreps;
@@ -336,9 +340,9 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
             const uint32_t o = reps[j];
             lt = o != me && less((uint16_t)o, (uint16_t)me);
             if (lt) {
+              const uint32_t len = gl[o];
               mine = cnt[o];
-              if (gl[o] <= REG_CAP)
-                mine |= ((uint64_t)gl[o] << 16) | ((uint64_t)enc_slot_words(gl[o]) << 36);
+              if (len <= REG_CAP) mine |= ((uint64_t)len << 16) | ((uint64_t)enc_slot_words(len) << 36);
             }
           }
           rank += __popc(__ballot_sync(0xffffffffu, lt));
@@ -347,22 +351,22 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         if (lane == 0) {
           const uint32_t ib = (uint32_t)(acc & 0xFFFFu), pst = (uint32_t)((acc >> 16) & 0xFFFFFu),
                          est = (uint32_t)(acc >> 36);
-          const bool light = gl[me] <= REG_CAP;
-          const SegDesc& sd = a.segs[seg_a[me]];
+          const uint32_t len = gl[me];
+          const bool light = len <= REG_CAP;
           GroupIn g;
-          g.inst = sd.base + (idx_a[me] - sd.lo);
+          g.inst = inst_a[me];
           g.tlen = tlen[me];
           g.src = (uint32_t)rec_base + icount + ib;
           g.c = cnt[me];
-          g.L = gl[me];
+          g.L = len;
           g.pst = pcount + pst;
           g.eslot = ecount + est;
           g.pad = 0;
           a.gin[rec_base + dcount + rank] = g;
           sbase[me] = g.src;
           if (rank == D - 1) {
-            s_tot[0] = pst + (light ? gl[me] : 0u);
-            s_tot[1] = est + (light ? enc_slot_words(gl[me]) : 0u);
+            s_tot[0] = pst + (light ? len : 0u);
+            s_tot[1] = est + (light ? enc_slot_words(len) : 0u);
           }
         }
       }
@@ -373,11 +377,13 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       for (uint32_t base = 0; base < D; base += K1B_THREADS) {
         const uint32_t r = base + tid;
         uint32_t me = 0, ci = 0, li = 0, ei = 0;
+        uint32_t len = 0;
         if (r < D) {
           me = reps[r];
           ci = cnt[me];
-          if (gl[me] <= REG_CAP) {
-            li = gl[me];
+          len = gl[me];
+          if (len <= REG_CAP) {
+            li = len;
             ei = enc_slot_words(li);
           }
         }
@@ -386,13 +392,12 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         const uint32_t xp = block_exclusive_scan(li, s_ws32, tp);
         const uint32_t xe = block_exclusive_scan(ei, s_ws32, te);
         if (r < D) {
-          const SegDesc& sd = a.segs[seg_a[me]];
           GroupIn g;
-          g.inst = sd.base + (idx_a[me] - sd.lo);
+          g.inst = inst_a[me];
           g.tlen = tlen[me];
           g.src = (uint32_t)rec_base + icount + run_i + xi;
           g.c = ci;
-          g.L = gl[me];
+          g.L = len;
           g.pst = pcount + run_p + xp;
           g.eslot = ecount + run_e + xe;
           g.pad = 0;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         const uint32_t g = grp[i];
         const uint32_t at = sbase[g] + (atomicSub(&cnt[g], 1u) - 1u);
         a.src_ptr[at] = pp[j];
-        a.src_len[at] = plen[i];
+        a.src_len[at] = pl[j];
       }
     }
     dcount += D;

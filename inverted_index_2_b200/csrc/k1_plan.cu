@@ -54,7 +54,15 @@ k1_sample_keys(const SegDesc* __restrict__ segs, int k, const uint32_t* __restri
   const int s = lo;
   const SegDesc sd = segs[s];
   const uint32_t m = sbase[s + 1] - sbase[s], j = x - sbase[s], n = sd.hi - sd.lo;
-  const uint32_t idx = sd.lo + (uint32_t)(((uint64_t)(j + 1) * n) / (m + 1));
+  // Segments of one shard are samples of the same term distribution: equal relative positions
+  // would pile all k samples of a quantile onto the same few terms and leave k-times oversized
+  // buckets between the piles.  Every segment gets its own phase (golden-ratio sequence), so
+  // the merged samples interleave evenly.
+  const double phase = (double)s * 0.6180339887498949;
+  const double phi = phase - floor(phase);
+  uint32_t off = (uint32_t)(((double)j + phi) * (double)n / (double)m);
+  if (off >= n) off = n - 1;
+  const uint32_t idx = sd.lo + off;
   const KeyedTerm t = keyed_term(sd, idx);
   sa.hi[x] = t.hi;
   sa.lo[x] = t.lo;
