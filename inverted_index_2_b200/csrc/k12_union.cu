@@ -673,7 +673,7 @@ struct K2bArgs {
   uint32_t* large_bucket;
 };
 
-__global__ void __launch_bounds__(K2B_THREADS, 4) k2b_union_kernel(const K2bArgs a) {
+__global__ void __launch_bounds__(K2B_THREADS, 6) k2b_union_kernel(const K2bArgs a) {
   __shared__ uint32_t s_buf[K2B_WARPS][REG_CAP];
   __shared__ uint32_t s_enc[K2B_WARPS][K2B_ENC_WORDS + 3];
   const unsigned lane = lane_id(), warp = warp_id();

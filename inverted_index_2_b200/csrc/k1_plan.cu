@@ -20,13 +20,14 @@
 // Integer/byte work; every probe is an L2 hit after the first touch (samples and offsets of
 // 64 segments are a few MB).
 #include <algorithm>
+#include <cstdlib>
 
 #include "keys.cuh"
 #include "plan.cuh"
 
 namespace ii2 {
 
-constexpr uint32_t kInstancesPerBucket = 640;  // target; K12 tiles hold 1024
+constexpr uint32_t kInstancesPerBucket = 768;  // target; K1b tiles hold 1024
 constexpr uint32_t kMaxBuckets = 1u << 20;
 
 struct SampleArrays {
@@ -250,7 +251,12 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     return II2_ERR_UNSUPPORTED;
   }
   // samples per segment, proportional to its window; chunks of the merge-path partition
-  uint64_t want = N / kInstancesPerBucket;
+  static const uint32_t per_bucket = [] {  // tuning knob: II2_BUCKET=<instances per bucket>
+    const char* e = getenv("II2_BUCKET");
+    const long v = e ? atol(e) : 0;
+    return (v >= 32 && v <= 1024) ? (uint32_t)v : kInstancesPerBucket;
+  }();
+  uint64_t want = N / per_bucket;
   if (want > kMaxBuckets - 1) want = kMaxBuckets - 1;
   uint32_t* cbase = sbase + (k + 1);
   sbase[0] = 0;
