@@ -1,0 +1,131 @@
+#!/usr/bin/env python3
+"""bench_extra.py — the other BASELINE.json configurations, one JSON line each:
+  C3  term-range read union across 256 segments with 5 % removed_list filtering (µs per call)
+  C4  file/bitmask + intcomp encode/decode sweep, posting-list lengths 16 .. 16M
+bench.py stays the headline (C2 compaction); these lines are evidence for SURVEY §8 rows."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from inverted_index_2_b200 import synth  # noqa: E402
+
+
+def timed(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), float(np.percentile(ts, 99))
+
+
+def c3(eng, a):
+    w = synth.make_workload(a.terms, 256, a.postings, seed=0xC3, presence=0.125)
+    dsegs = [eng.upload(s) for s in w.segments]
+    drem = eng.upload_removed(w.removed)
+    n = len(w.term_off) - 1
+    rng = np.random.default_rng(3)
+    out = []
+    for frac in (0.001, 0.01, 0.1, 1.0):
+        span = max(1, int(n * frac))
+        lat, info = [], None
+        for _ in range(16 if frac < 1 else 4):
+            lo = int(rng.integers(0, n - span + 1))
+            tlo = synth.term_at(w.term_bytes, w.term_off, lo)
+            thi = synth.term_at(w.term_bytes, w.term_off, lo + span - 1)
+
+            def call():
+                nonlocal info
+                r = eng.read_range_dev(dsegs, tlo, thi, drem)
+                info = r.info()
+                r.release()
+            med, _ = timed(call, 3)
+            lat.append(med)
+        out.append({"range_frac": frac, "terms": int(info.terms_count),
+                    "postings_in": int(info.postings_in), "postings_out": int(info.postings_out),
+                    "median_us": 1e6 * float(np.median(lat)), "p99_us": 1e6 * float(np.max(lat)),
+                    "postings_in_per_s": int(info.postings_in) / float(np.median(lat))})
+    print(json.dumps({"config": "C3 range read, 256 segments, 5% removed (read + merge-style filter)",
+                      "terms": a.terms, "postings": w.postings_in, "results": out}))
+
+
+def c4(eng, a):
+    from oracle import orc  # checker only
+    rows = []
+    rng = np.random.default_rng(4)
+    for lg in range(4, 25, 4):
+        L = 1 << lg
+        nlists = max(1, (1 << 24) // L)  # >= 16M values per timing
+        for gap in (1, 16, 4096):
+            gaps = rng.integers(1, 2 * gap + 1, size=L * nlists, dtype=np.int64)
+            starts = np.arange(nlists, dtype=np.int64) * L
+            c = np.cumsum(gaps)
+            vals = (c - np.repeat(c[starts] - gaps[starts], L)).astype(np.uint32)
+            off = (np.arange(nlists + 1, dtype=np.uint64) * np.uint64(L))
+            words = woff = None
+
+            def enc():
+                nonlocal words, woff
+                words, woff = eng.intcomp_encode_batch(vals, off)
+            te, _ = timed(enc, 3)
+
+            def dec():
+                eng.intcomp_decode_batch(words, woff)
+            td, _ = timed(dec, 3)
+            if lg <= 12:  # parity spot check on the small cases
+                ew, eo = orc.intcomp_encode_batch(vals[:L * min(nlists, 64)], off[:min(nlists, 64) + 1])
+                assert np.array_equal(ew, words[:len(ew)]) and np.array_equal(eo, woff[:len(eo)])
+            rows.append({"codec": "intcomp", "L": L, "lists": nlists, "gap": gap,
+                         "ratio": 4.0 * len(vals) / (4.0 * len(words)),
+                         "encode_values_per_s": len(vals) / te, "decode_values_per_s": len(vals) / td,
+                         "api": "host buffers (H2D + kernels + D2H)"})
+    for lg in range(4, 25, 4):
+        L = 1 << lg
+        universe = np.sort(rng.choice(max(4 * L, 1 << 10), size=2 * L, replace=False)).astype(np.uint32)
+        vals = rng.permutation(universe)[:L]
+        bm = eng.bitmask(universe)
+        enc = None
+
+        def put():
+            nonlocal enc
+            enc = bm.put(vals)
+        tp, _ = timed(put, 3)
+
+        def get():
+            bm.get(enc)
+        tg, _ = timed(get, 3)
+        rows.append({"codec": "bitmask", "L": L, "dictionary": 2 * L, "bytes": len(enc),
+                     "put_values_per_s": L / tp, "get_values_per_s": L / tg,
+                     "api": "host buffers (H2D + kernels + D2H)"})
+    print(json.dumps({"config": "C4 codec sweep, list lengths 16..16M", "results": rows}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="c3,c4")
+    ap.add_argument("--terms", type=int, default=1_000_000)
+    ap.add_argument("--postings", type=int, default=100_000_000)
+    a = ap.parse_args()
+    from inverted_index_2_b200.engine import Engine
+    eng = Engine(0)
+    if "c3" in a.which:
+        c3(eng, a)
+    if "c4" in a.which:
+        c4(eng, a)
+
+
+if __name__ == "__main__":
+    main()

@@ -261,10 +261,14 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   uint32_t* cbase = sbase + (k + 1);
   sbase[0] = 0;
   cbase[0] = 0;
+  uint64_t cum = 0, given = 0;
   for (int i = 0; i < k; i++) {
     const uint64_t n = h_segs[i].hi - h_segs[i].lo;
-    uint64_t m = N ? want * n / N : 0;
+    cum += n;
+    // cumulative rounding: the samples add up to `want` even when every segment's share is < 1
+    uint64_t m = N ? want * cum / N - given : 0;
     if (m + 1 > n) m = n ? n - 1 : 0;
+    given += m;
     sbase[i + 1] = sbase[i] + (uint32_t)m;
     cbase[i + 1] = cbase[i] + (uint32_t)std::max<uint64_t>(1, (n + K1_CHUNK - 1) / K1_CHUNK);
   }
