@@ -354,6 +354,37 @@ def run_ours(a):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / e_steps,
                "steps": e_steps, "api": "ii2_merge (host buffers, pinned)"}
 
+    # ---- cross-shard read (BASELINE configs[4]): every rank reads its shard range, the
+    # results are gathered in rank order with NCCL (sizes, then a padded all-gather) ----
+    xread = None
+    if world > 1:
+        from inverted_index_2_b200.sharded import _gather_var
+        nt = len(w.term_off) - 1
+        lo_t = synth.term_at(w.term_bytes, w.term_off, nt // 2)
+        hi_t = synth.term_at(w.term_bytes, w.term_off, nt // 2 + nt // 100)
+
+        def xstep():
+            with torch.cuda.stream(stream):
+                r = eng.read_range_dev(dsegs, lo_t, hi_t, None)
+                tens = r.as_tensors(local)
+                parts = {k2: _gather_var(dist, v) for k2, v in tens.items()}
+                n_post = sum(int(p.numel()) for p in parts["post"])
+                stream.synchronize()
+                r.release()
+            return n_post
+        for _ in range(2):
+            n_post = xstep()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            xstep()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 5
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        xread = {"range": "1% of every rank's terms", "gathered_postings": int(n_post),
+                 "us_per_read": 1e6 * float(t.item()), "collective": "NCCL all_gather (sizes + padded arrays)"}
+
     verified = None
     if a.verify and rank == 0:
         res = eng.merge_dev(dsegs, drem, encode=True, decoded=True).download_merge(decoded=True)
@@ -382,6 +413,8 @@ def run_ours(a):
         }
         if verified is not None:
             line["verified_full_size"] = verified
+        if xread is not None:
+            line["cross_shard_read"] = xread
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

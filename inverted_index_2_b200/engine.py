@@ -110,6 +110,30 @@ class DeviceResult:
         finally:
             self.eng.lib.ii2_read_out_free(C.byref(out))
 
+    def as_tensors(self, device_index: int = 0) -> dict:
+        """Zero-copy torch views of the result's device arrays (valid until release()); the
+        NCCL gather of cross-shard reads works on these.  Unsigned data is viewed as the signed
+        type of the same width (NCCL has no unsigned 32/64-bit types)."""
+        import torch
+        info = self.info()
+
+        class _Arr:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr,
+                                                 "data": (int(ptr), False), "version": 2}
+
+        def view(ptr, n, typestr, dt):
+            if not ptr or int(n) == 0:
+                return torch.zeros(0, dtype=dt, device=f"cuda:{device_index}")
+            return torch.as_tensor(_Arr(ptr, n, typestr), device=f"cuda:{device_index}")
+        t = int(info.terms_count)
+        return {
+            "term_bytes": view(info.d_term_bytes, info.term_bytes, "|u1", torch.uint8),
+            "term_off": view(info.d_term_off, t + 1, "<i4", torch.int32),
+            "post": view(info.d_post, info.postings_out, "<i4", torch.int32),
+            "post_off": view(info.d_post_off, t + 1 if info.d_post_off else 0, "<i8", torch.int64),
+        }
+
     def to_segment(self) -> DeviceSegment:
         h = C.c_void_p()
         n = int(self.info().terms_count)
