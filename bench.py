@@ -280,14 +280,16 @@ def run_ours(a):
     t_in = w.term_instances
     t_in_bytes = int(sum(int(s.term_off[-1]) for s in w.segments))
     n_groups = int(prof_terms) if (prof_terms := stats[2]) else 0  # distinct terms ~ terms out
+    k1b_bytes = (t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 12 * t_in
+                 + 32 * n_groups)
+    k2b_bytes = 32 * n_groups + 12 * t_in + 4 * n_in + 4 * len(w.removed) + 32 * n_groups + val_size
     alg = {
-        # K1b: term bytes + term offsets + posting offsets in; a 12 B source entry per instance
-        # and a 32 B record per distinct term out
-        "k1b_group": t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 12 * t_in
-        + 32 * n_groups,
-        # K2b: records + source entries + postings in; records + the `_val` stream out
-        "k2b_union": 32 * n_groups + 12 * t_in + 4 * n_in + 4 * len(w.removed) + 32 * n_groups
-        + val_size,
+        # K1b (grouping: term bytes + term/posting offsets in; a 12 B source entry per instance
+        # and a 32 B record per distinct term out) and K2b (records + source entries + postings
+        # in; records + the `_val` stream out) run as one two-stream pipeline over bucket chunks
+        "k12_group_union": k1b_bytes + k2b_bytes,
+        "k1b_group": k1b_bytes,
+        "k2b_union": k2b_bytes,
         # K6: records + staged `_val` words + surviving term bytes in; the new segment out
         "k6_emit": 32 * n_groups + val_size + t_out_bytes + val_size + t_out_bytes + 12 * t_out,
     }

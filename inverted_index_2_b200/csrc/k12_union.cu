@@ -51,8 +51,8 @@ struct GroupIn {
 };
 
 // staging words that certainly hold the intcomp stream of n values (oracle/intcomp_ref.c
-// orc_intcomp_bound: 3 + 129 per block + 1 + ceil(5 * tail / 4) + 1)
-__host__ __device__ __forceinline__ uint32_t enc_slot_words(uint32_t n) { return n + (n >> 2) + 8; }
+// orc_intcomp_bound: 3 + 129 per block + 1 + ceil(5 * tail / 4) + 1; at most two blocks here)
+__host__ __device__ __forceinline__ uint32_t enc_slot_words(uint32_t n) { return n + (n >> 2) + 6; }
 
 struct K1bArgs {
   const SegDesc* segs;
@@ -64,7 +64,7 @@ struct K1bArgs {
   uint64_t* src_ptr;
   uint32_t* src_len;
   uint32_t* bk_D;   // [B] distinct terms per bucket
-  uint64_t* bk_E;   // [B+1] staging words per bucket (scanned afterwards)
+  uint32_t bucket0; // first bucket of this launch (the grid covers a chunk of buckets)
 };
 
 __host__ __device__ inline size_t k1b_smem_bytes(int k) {
@@ -104,13 +104,10 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
 
   const uint32_t tid = threadIdx.x;
   const unsigned lane = lane_id(), warp = warp_id();
-  const uint32_t b = blockIdx.x;
+  const uint32_t b = a.bucket0 + blockIdx.x;
   uint32_t W = (uint32_t)(a.bk_pos[b + 1] - a.bk_pos[b]);
   if (W == 0) {
-    if (tid == 0) {
-      a.bk_D[b] = 0;
-      a.bk_E[b] = 0;
-    }
+    if (tid == 0) a.bk_D[b] = 0;
     return;
   }
   {
@@ -436,10 +433,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     for (int s = tid; s < k; s += K1B_THREADS) cur[s] = mm[s];
     __syncthreads();
   }
-  if (tid == 0) {
-    a.bk_D[b] = dcount;
-    a.bk_E[b] = ecount;
-  }
+  if (tid == 0) a.bk_D[b] = dcount;
 }
 
 // ---- warp-level union of one group held in shared memory --------------------------------
@@ -671,13 +665,14 @@ struct K2bArgs {
   uint32_t* n_large;
   uint32_t* large_rec;
   uint32_t* large_bucket;
+  uint32_t bucket0;  // first bucket of this launch
 };
 
 __global__ void __launch_bounds__(K2B_THREADS, 6) k2b_union_kernel(const K2bArgs a) {
   __shared__ uint32_t s_buf[K2B_WARPS][REG_CAP];
   __shared__ uint32_t s_enc[K2B_WARPS][K2B_ENC_WORDS + 3];
   const unsigned lane = lane_id(), warp = warp_id();
-  const uint32_t b = blockIdx.x;
+  const uint32_t b = a.bucket0 + blockIdx.x;
   const uint32_t D = a.bk_D[b];
   if (D == 0) return;
   const uint64_t rec_base = a.bk_pos[b];
@@ -982,91 +977,93 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   const uint32_t B = plan.n_buckets, N = plan.n_total;
   const int k = plan.k;
   DevBuf<GroupIn> gin;
-  DevBuf<uint64_t> src_ptr, bk_E;
+  DevBuf<uint64_t> src_ptr;
   DevBuf<uint32_t> src_len;
-  ProfScope alloc_scope("k12_alloc", s);
   II2_TRY(gin.alloc_scratch(N, s));
   II2_TRY(src_ptr.alloc_scratch(N, s));
   II2_TRY(src_len.alloc_scratch(N, s));
-  II2_TRY(bk_E.alloc_scratch(B + 1, s));
   II2_TRY(u.recs.alloc_scratch(N, s));
   II2_TRY(u.bk_D.alloc_scratch(B, s));
   II2_TRY(u.bk_raw.alloc_scratch(4 * (size_t)(B + 1), s));
   II2_TRY(u.bk_out.alloc_scratch(4 * (size_t)(B + 1), s));
-  // totals[0..3] scan totals, [4] terms merged, [5] staging words, [6] n_large (u32)
+  // totals[0..3] scan totals, [4] terms merged, [6] n_large (u32)
   II2_TRY(u.totals.alloc_scratch(8, s));
-  II2_CUDA_TRY(cudaMemsetAsync(u.totals.p, 0, 64, s));
-  II2_CUDA_TRY(cudaMemsetAsync(u.bk_raw.p, 0, 4 * (size_t)(B + 1) * 8, s));
-  II2_CUDA_TRY(cudaMemsetAsync(bk_E.p + B, 0, 8, s));
-  alloc_scope.end();
-
-  {
-    K1bArgs a;
-    a.segs = plan.segs;
-    a.k = k;
-    a.part = plan.part.p;
-    a.bk_pos = plan.bk_pos();
-    a.bk_cpl = plan.bk_cpl.p;
-    a.gin = gin.p;
-    a.src_ptr = src_ptr.p;
-    a.src_len = src_len.p;
-    a.bk_D = u.bk_D.p;
-    a.bk_E = bk_E.p;
-    const size_t smem = k1b_smem_bytes(k);
-    static size_t attr = 0;
-    if (smem > attr) {
-      II2_CUDA_TRY(cudaFuncSetAttribute(k1b_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)k1b_smem_bytes(kMaxSegs)));
-      attr = k1b_smem_bytes(kMaxSegs);
-    }
-    ProfScope scope("k1b_group", s);
-    k1b_group_kernel<<<B, K1B_THREADS, smem, s>>>(a);
-    II2_LAUNCHED();
-  }
-  k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
-  II2_LAUNCHED();
-  II2_TRY(exclusive_scan_multi_u64(bk_E.p, bk_E.p, B + 1, 1, u.totals.p + 5, s));
-  // the `_val` staging buffer is sized from an upper bound known without a round trip:
-  // every light term of L values reserved L + L/4 + 8 words
-  const uint64_t enc_cap = n_in + n_in / 4 + 8ull * N + 64;
-  (void)enc_cap;
-  uint64_t h_tot[8];
-  ProfScope sync_scope("k12_sync_alloc", s);
-  if (want_enc) {  // exact reservation: one small read back
-    II2_CUDA_TRY(cudaMemcpyAsync(h_tot, u.totals.p, 64, cudaMemcpyDeviceToHost, s));
-    II2_CUDA_TRY(cudaStreamSynchronize(s));
-    II2_TRY(u.tmp_enc.alloc_scratch(h_tot[5] + 64, s));
-  }
+  // `_val` staging: every light term of L values owns a slot of L + L/4 + 6 words; the bucket
+  // bases are the plan's upper-bound prefix, so nothing has to be read back before K2b
+  const uint64_t enc_cap = n_in + n_in / 4 + 6ull * N + 64;
+  if (want_enc) II2_TRY(u.tmp_enc.alloc_scratch(enc_cap, s));
   if (want_dec) II2_TRY(u.tmp_post.alloc_scratch(n_in, s));
   const uint32_t large_cap = (uint32_t)std::min<uint64_t>(N, n_in / REG_CAP + 1);
   DevBuf<uint32_t> large_u32;
   II2_TRY(large_u32.alloc_scratch(2 * (size_t)large_cap, s));
-  sync_scope.end();
-  {
-    K2bArgs a;
-    a.bk_pos = plan.bk_pos();
-    a.bk_P = plan.bk_P();
-    a.bk_E = bk_E.p;
-    a.bk_D = u.bk_D.p;
-    a.gin = gin.p;
-    a.src_ptr = src_ptr.p;
-    a.src_len = src_len.p;
-    a.rem = rem;
-    a.want_enc = want_enc ? 1 : 0;
-    a.want_dec = want_dec ? 1 : 0;
-    a.keep_empty = keep_empty ? 1 : 0;
-    a.recs = u.recs.p;
-    a.tmp_post = u.tmp_post.p;
-    a.tmp_enc = u.tmp_enc.p;
-    a.bk_raw = u.bk_raw.p;
-    a.nb1 = B + 1;
-    a.n_large = reinterpret_cast<uint32_t*>(u.totals.p + 6);
-    a.large_rec = large_u32.p;
-    a.large_bucket = large_u32.p + large_cap;
-    ProfScope scope("k2b_union", s);
-    k2b_union_kernel<<<B, K2B_THREADS, 0, s>>>(a);
-    II2_LAUNCHED();
+  II2_CUDA_TRY(cudaMemsetAsync(u.totals.p, 0, 64, s));
+  II2_CUDA_TRY(cudaMemsetAsync(u.bk_raw.p, 0, 4 * (size_t)(B + 1) * 8, s));
+
+  K1bArgs a1;
+  a1.segs = plan.segs;
+  a1.k = k;
+  a1.part = plan.part.p;
+  a1.bk_pos = plan.bk_pos();
+  a1.bk_cpl = plan.bk_cpl.p;
+  a1.gin = gin.p;
+  a1.src_ptr = src_ptr.p;
+  a1.src_len = src_len.p;
+  a1.bk_D = u.bk_D.p;
+  K2bArgs a2;
+  a2.bk_pos = plan.bk_pos();
+  a2.bk_P = plan.bk_P();
+  a2.bk_E = plan.bk_E();
+  a2.bk_D = u.bk_D.p;
+  a2.gin = gin.p;
+  a2.src_ptr = src_ptr.p;
+  a2.src_len = src_len.p;
+  a2.rem = rem;
+  a2.want_enc = want_enc ? 1 : 0;
+  a2.want_dec = want_dec ? 1 : 0;
+  a2.keep_empty = keep_empty ? 1 : 0;
+  a2.recs = u.recs.p;
+  a2.tmp_post = u.tmp_post.p;
+  a2.tmp_enc = u.tmp_enc.p;
+  a2.bk_raw = u.bk_raw.p;
+  a2.nb1 = B + 1;
+  a2.n_large = reinterpret_cast<uint32_t*>(u.totals.p + 6);
+  a2.large_rec = large_u32.p;
+  a2.large_bucket = large_u32.p + large_cap;
+  const size_t smem = k1b_smem_bytes(k);
+  static size_t attr = 0;
+  if (smem > attr) {
+    II2_CUDA_TRY(cudaFuncSetAttribute(k1b_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)k1b_smem_bytes(kMaxSegs)));
+    attr = k1b_smem_bytes(kMaxSegs);
   }
+  {
+    // K1b is barrier/latency bound, K2b issue bound: chunks of buckets flow through the two
+    // kernels on two streams so the grouping of chunk c+1 overlaps the union of chunk c
+    ProfScope scope("k12_group_union", s);
+    const uint32_t n_chunks = 1;  // measured on B200: overlapping the two kernels over 8 chunks is slower (3.27 vs 2.94 ms)
+    cudaStream_t s2 = n_chunks > 1 ? aux_stream() : s;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+      const uint32_t b0 = (uint32_t)((uint64_t)B * c / n_chunks);
+      const uint32_t b1 = (uint32_t)((uint64_t)B * (c + 1) / n_chunks);
+      if (b1 == b0) continue;
+      a1.bucket0 = a2.bucket0 = b0;
+      k1b_group_kernel<<<b1 - b0, K1B_THREADS, smem, s>>>(a1);
+      II2_LAUNCHED();
+      if (n_chunks > 1) {
+        II2_CUDA_TRY(cudaEventRecord(aux_event((int)c), s));
+        II2_CUDA_TRY(cudaStreamWaitEvent(s2, aux_event((int)c), 0));
+      }
+      k2b_union_kernel<<<b1 - b0, K2B_THREADS, 0, s2>>>(a2);
+      II2_LAUNCHED();
+    }
+    if (n_chunks > 1) {
+      II2_CUDA_TRY(cudaEventRecord(aux_event(15), s2));
+      II2_CUDA_TRY(cudaStreamWaitEvent(s, aux_event(15), 0));
+    }
+  }
+  k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
+  II2_LAUNCHED();
+  uint64_t h_tot[8];
   // optimistic: scan right away; redone only if heavy terms were deferred
   {
     ProfScope scope("k12_scan_sync", s);

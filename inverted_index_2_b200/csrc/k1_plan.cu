@@ -208,7 +208,8 @@ k1_partition_chunks(const SegDesc* __restrict__ segs, int k, const uint32_t* __r
   }
 }
 
-// One warp per bucket.  raw[0][b] = instances, raw[1][b] = input postings.
+// One warp per bucket.  raw[0][b] = instances, raw[1][b] = input postings, raw[2][b] = staging
+// words (upper bound).
 __global__ void __launch_bounds__(256)
 k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArrays sp,
                 const uint32_t* __restrict__ part, uint64_t* __restrict__ raw,
@@ -218,7 +219,7 @@ k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArray
   if (b > B) return;
   const unsigned lane = lane_id();
   if (b == B) {
-    if (lane == 0) raw[B] = raw[(uint64_t)(B + 1) + B] = 0;
+    if (lane == 0) raw[B] = raw[(uint64_t)(B + 1) + B] = raw[2ull * (B + 1) + B] = 0;
     return;
   }
   uint64_t w = 0, p = 0;
@@ -232,6 +233,9 @@ k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArray
   if (lane == 0) {
     raw[b] = w;
     raw[(uint64_t)(B + 1) + b] = p;
+    // `_val` staging words the bucket can need: every term of L values reserves
+    // L + L/4 + 6 words (k12_union.cu enc_slot_words) and there are at most w terms
+    raw[2ull * (B + 1) + b] = p + (p >> 2) + 6 * w;
     uint32_t c = 0;
     if (b >= 1 && b < S) {  // both delimiting splitters exist: b-1 and b
       const uint8_t* x = reinterpret_cast<const uint8_t*>(sp.ptr[b - 1]);
@@ -278,8 +282,8 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   ProfScope scope("k1_plan", s);
   II2_TRY(plan.part.alloc_scratch((size_t)(S + 2) * k, s));
   II2_TRY(plan.bk_cpl.alloc_scratch(B, s));
-  II2_TRY(plan.bk_WP.alloc_scratch(2 * (size_t)(B + 1), s));
-  II2_TRY(plan.totals.alloc_scratch(2, s));
+  II2_TRY(plan.bk_WP.alloc_scratch(3 * (size_t)(B + 1), s));
+  II2_TRY(plan.totals.alloc_scratch(3, s));
   DevBuf<uint32_t> d_base, d_u32;
   DevBuf<uint64_t> d_u64;
   const size_t Sx = S ? S : 1;
@@ -302,7 +306,7 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   k1_bucket_stats<<<div_up((uint64_t)(B + 1) * 32, 256), 256, 0, s>>>(
       plan.segs, k, S, sp, plan.part.p, plan.bk_WP.p, plan.bk_cpl.p);
   II2_LAUNCHED();
-  II2_TRY(exclusive_scan_multi_u64(plan.bk_WP.p, plan.bk_WP.p, B + 1, 2, plan.totals.p, s));
+  II2_TRY(exclusive_scan_multi_u64(plan.bk_WP.p, plan.bk_WP.p, B + 1, 3, plan.totals.p, s));
   return II2_OK;
 }
 

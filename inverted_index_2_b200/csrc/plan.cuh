@@ -24,10 +24,12 @@ struct MergePlan {
   // in every segment, row S+1 = window ends; bucket b spans rows b .. b+1
   DevBuf<uint32_t> part;          // [(S+2) * k]
   DevBuf<uint32_t> bk_cpl;        // [B]   common prefix length of all terms in the bucket
-  DevBuf<uint64_t> bk_WP;         // [2][B+1] exclusive prefixes: instances / input postings
+  // [3][B+1] exclusive prefixes: instances / input postings / `_val` staging words (upper bound)
+  DevBuf<uint64_t> bk_WP;
   const uint64_t* bk_pos() const { return bk_WP.p; }
   const uint64_t* bk_P() const { return bk_WP.p + (n_buckets + 1); }
-  DevBuf<uint64_t> totals;        // [2] {Σ instances, Σ postings in}
+  const uint64_t* bk_E() const { return bk_WP.p + 2 * (size_t)(n_buckets + 1); }
+  DevBuf<uint64_t> totals;        // [3] {Σ instances, Σ postings in, Σ staging words}
 };
 
 // K1: choose splitters and partition every segment (the k-way merge of the term dictionaries,

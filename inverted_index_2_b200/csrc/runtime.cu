@@ -46,6 +46,8 @@ int ctx_require() {
 
 struct ThreadStream {
   cudaStream_t own = nullptr;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev[16] = {};
   cudaStream_t user = nullptr;
   bool use_user = false;
   ~ThreadStream() {
@@ -59,6 +61,16 @@ cudaStream_t cur_stream() {
   if (t_stream.use_user) return t_stream.user;
   if (!t_stream.own) cudaStreamCreateWithFlags(&t_stream.own, cudaStreamNonBlocking);
   return t_stream.own;
+}
+
+cudaStream_t aux_stream() {
+  if (!t_stream.aux) cudaStreamCreateWithFlags(&t_stream.aux, cudaStreamNonBlocking);
+  return t_stream.aux;
+}
+
+cudaEvent_t aux_event(int i) {
+  if (!t_stream.ev[i]) cudaEventCreateWithFlags(&t_stream.ev[i], cudaEventDisableTiming);
+  return t_stream.ev[i];
 }
 
 // ------------------------------------------------------------------ pinned pool

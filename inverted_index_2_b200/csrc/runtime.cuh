@@ -10,6 +10,8 @@ namespace ii2 {
 bool ctx_ready();
 int ctx_require();            // II2_OK or II2_ERR_NO_DEVICE (sets last error)
 cudaStream_t cur_stream();    // this thread's stream (caller-provided or library-owned)
+cudaStream_t aux_stream();    // a second library-owned stream of this thread (kernel overlap)
+cudaEvent_t aux_event(int i);  // this thread's reusable timing-free events, i < 16
 
 // Per-thread scratch arena: one grow-only device block, bump-allocated during a pipeline call
 // and reset when the call is over.  GB-sized cudaMallocAsync requests were measured at tens of
