@@ -149,11 +149,28 @@ k1_partition_chunks(const SegDesc* __restrict__ segs, int k, const uint32_t* __r
   const uint32_t i0 = sd.lo + ci * K1_CHUNK;
   const uint32_t i1 = (ci + 1 == nchunks) ? sd.hi : i0 + K1_CHUNK;
   const uint32_t n = i1 - i0;
-  for (uint32_t t = threadIdx.x; t < n; t += 256) {
-    const KeyedTerm kt = keyed_term(sd, i0 + t);
-    s_hi[t] = kt.hi;
-    s_lo[t] = kt.lo;
-    s_len[t] = kt.len;
+  {  // all offset loads first, then all key loads: 8 independent chains per thread in flight
+    constexpr int PER = K1_CHUNK / 256;
+    uint32_t o[PER], e[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const uint32_t t = threadIdx.x + j * 256;
+      if (t < n) {
+        o[j] = __ldg(sd.toff + i0 + t);
+        e[j] = __ldg(sd.toff + i0 + t + 1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const uint32_t t = threadIdx.x + j * 256;
+      if (t < n) {
+        uint64_t kh, kl;
+        load_key16(sd.tb, o[j], e[j] - o[j], 0, kh, kl);
+        s_hi[t] = kh;
+        s_lo[t] = kl;
+        s_len[t] = e[j] - o[j];
+      }
+    }
   }
   if (threadIdx.x < 2) {
     // splitters <= the term before the chunk (0 for the first chunk) and <= its last term
