@@ -362,12 +362,12 @@ int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
     DevBuf<uint64_t> d_vo, d_woff;
     DevBuf<uint32_t> d_words;
     II2_TRY(h2d(d_vo, v->val_off, (size_t)n, s));
-    II2_TRY(d_words.alloc(v->val_size / 4, s, 16));
+    II2_TRY(d_words.alloc_scratch(v->val_size / 4, s, 16));
     if (v->val_size)
       II2_CUDA_TRY(cudaMemcpyAsync(d_words.p, v->val_bytes, v->val_size, cudaMemcpyHostToDevice, s));
     II2_TRY(val_offsets_to_word_offsets(d_vo.p, n, v->val_size, d_woff, s));
     uint64_t total = 0;
-    II2_TRY(intcomp_decode_dev(d_words.p, d_woff.p, n, g->post, g->poff, &total, s));
+    II2_TRY(intcomp_decode_dev(d_words.p, d_woff.p, n, g->post, g->poff, &total, s, false));
     g->n_post = total;
   } else {
     set_last_error("unknown segment mode %d", v->mode);
@@ -375,7 +375,7 @@ int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
   }
   // sanity: term lengths must fit the tile kernel's 16-bit length field
   DevBuf<uint32_t> stats;
-  II2_TRY(stats.alloc(2, s));
+  II2_TRY(stats.alloc_scratch(2, s));
   II2_CUDA_TRY(cudaMemsetAsync(stats.p, 0, 8, s));
   if (n) {
     k_seg_check<<<div_up(n, 256), 256, 0, s>>>(g->toff.p, (uint32_t)n, g->poff.p, stats.p);
@@ -392,6 +392,7 @@ int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
     set_last_error("term of %u bytes (max 65535)", hs[0]);
     return II2_ERR_UNSUPPORTED;
   }
+  arena_reset(s);
   *seg_out = g.release();
   return II2_OK;
 }

@@ -147,6 +147,135 @@ __device__ __forceinline__ uint32_t enc_emit_warp(const uint32_t* v, uint32_t n,
   return pos;
 }
 
+// ---- CTA-cooperative encoder for long lists ------------------------------------------
+// words of 128-block `blk` of v (header word + four packed groups); uniform over the warp
+__device__ __forceinline__ uint32_t enc_block_size_warp(const uint32_t* v, uint32_t blk) {
+  const unsigned lane = lane_id();
+  uint32_t words = 1;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const uint32_t idx = blk * 128 + g * 32 + lane;
+    const uint32_t cur = v[idx];
+    const uint32_t prev = idx ? v[idx - 1] : cur;
+    const uint32_t m = __reduce_or_sync(0xffffffffu, zigzag(cur, prev));
+    words += (m & 1u) ? bitlen(m) : bitlen(m >> 1);
+  }
+  return words;
+}
+
+// writes 128-block `blk` of v at dst (header + groups); `stage` = 32 words private to the warp
+__device__ __forceinline__ void enc_block_emit_warp(const uint32_t* v, uint32_t blk, uint32_t* dst,
+                                                    uint32_t* stage) {
+  const unsigned lane = lane_id();
+  uint32_t coded[4];
+  int w[4];
+  uint32_t hdr = 0;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const uint32_t idx = blk * 128 + g * 32 + lane;
+    const uint32_t cur = v[idx];
+    const uint32_t prev = idx ? v[idx - 1] : cur;
+    const uint32_t z = zigzag(cur, prev);
+    const uint32_t m = __reduce_or_sync(0xffffffffu, z);
+    const uint32_t s = m & 1u;
+    w[g] = s ? bitlen(m) : bitlen(m >> 1);
+    coded[g] = s ? z : (cur - prev);
+    hdr |= ((s << 7) | (uint32_t)w[g]) << (24 - 8 * g);
+  }
+  if (lane == 0) dst[0] = hdr;
+  uint32_t pos = 1;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const int wd = w[g];
+    if (wd == 32) {
+      dst[pos + lane] = coded[g];
+    } else if (wd > 0) {
+      if ((int)lane < wd) stage[lane] = 0;
+      __syncwarp();
+      const uint32_t bit = lane * (uint32_t)wd, sh = bit & 31u;
+      atomicOr(&stage[bit >> 5], coded[g] << sh);
+      if (sh + (uint32_t)wd > 32u) atomicOr(&stage[(bit >> 5) + 1], coded[g] >> (32u - sh));
+      __syncwarp();
+      if ((int)lane < wd) dst[pos + lane] = stage[lane];
+      __syncwarp();
+    }
+    pos += (uint32_t)wd;
+  }
+}
+
+// Whole-CTA CompressUint32 of v[0..n) (global memory, n >= 128) to dst.  `table` = n/128 words
+// of global scratch (block sizes, then their exclusive prefix); `stage` = kStageWords of shared
+// memory per warp; `ws` = block-scan scratch (blockDim/32 + 2).  Every thread of the block
+// must call.  Returns the stream length in words (uniform).
+__device__ __forceinline__ uint32_t enc_emit_cta(const uint32_t* v, uint32_t n, uint32_t* dst,
+                                                 uint32_t* table, uint32_t* stage, uint64_t* ws) {
+  const unsigned lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
+  const uint32_t nb = n >> 7, tail = n & 127u;
+  for (uint32_t b = warp; b < nb; b += nwarps) {
+    const uint32_t wds = enc_block_size_warp(v, b);
+    if (lane == 0) table[b] = wds;
+  }
+  __syncthreads();
+  uint64_t run = 0;
+  for (uint32_t base = 0; base < nb; base += blockDim.x) {
+    const uint32_t b = base + threadIdx.x;
+    const uint64_t x = b < nb ? table[b] : 0u;
+    uint64_t tot;
+    const uint64_t ex = block_exclusive_scan(x, ws, tot);
+    if (b < nb) table[b] = (uint32_t)(run + ex);
+    run += tot;
+  }
+  __syncthreads();
+  uint32_t* my_stage = stage + warp * kStageWords;
+  for (uint32_t b = warp; b < nb; b += nwarps) enc_block_emit_warp(v, b, dst + 3 + table[b], my_stage);
+  uint32_t pos = 3 + (uint32_t)run;
+  if (warp == 0) {
+    if (lane == 0) {
+      dst[0] = nb * 128;
+      dst[1] = pos;
+      dst[2] = v[0];
+    }
+  }
+  uint32_t tail_words = 0;
+  if (tail) {  // var-byte tail: small, one warp; every warp computes the size
+    uint32_t bytes = 0;
+    for (uint32_t i = lane; i < tail; i += 32) {
+      const uint32_t idx = nb * 128 + i;
+      bytes += vbyte_len(zigzag(v[idx], i ? v[idx - 1] : 0u));
+    }
+    bytes = warp_sum(bytes);
+    tail_words = 1 + (bytes + 3) / 4;
+    if (warp == 0) {
+      if (lane == 0) dst[pos] = tail;
+      uint8_t* sb = reinterpret_cast<uint8_t*>(my_stage);
+      uint32_t bo = 0;
+      for (uint32_t t = 0; t < tail; t += 32) {
+        const uint32_t i = t + lane;
+        uint32_t z = 0, len = 0;
+        if (i < tail) {
+          const uint32_t idx = nb * 128 + i;
+          z = zigzag(v[idx], i ? v[idx - 1] : 0u);
+          len = vbyte_len(z);
+        }
+        const uint32_t inc = warp_inclusive_scan(len);
+        const uint32_t off = bo + inc - len;
+        for (uint32_t k = 0; k < len; k++) {
+          uint32_t byte = (z >> (7 * k)) & 0x7Fu;
+          if (k + 1 == len) byte |= 0x80u;
+          sb[off + k] = (uint8_t)byte;
+        }
+        bo += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      const uint32_t nwords = (bo + 3) / 4;
+      if (lane < nwords * 4 - bo) sb[bo + lane] = 0;
+      __syncwarp();
+      for (uint32_t j = lane; j < nwords; j += 32) dst[pos + 1 + j] = my_stage[j];
+    }
+  }
+  __syncthreads();
+  return pos + tail_words;
+}
+
 // ---- single-thread variants for lists below one block (n < 128: varbyte section only) --
 __device__ __forceinline__ uint32_t enc_size_thread_small(const uint32_t* v, uint32_t n) {
   if (n == 0) return 0;

@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(512) k2_large_tile_merge(const LargeArgs a, ui
 // one CTA per heavy group: in-place dedup + filter, encode, record, bucket totals
 __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
   __shared__ uint64_t s_ws[1024 / 32 + 2];
-  __shared__ uint32_t s_stage[intcomp::kStageWords];
+  __shared__ uint32_t s_stage[32 * intcomp::kStageWords];
   __shared__ uint32_t s_enc;
   const uint32_t g = blockIdx.x;
   const uint64_t n = a.len[g];
@@ -933,10 +933,17 @@ __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
   }
   __threadfence_block();
   __syncthreads();
-  if (warp_id() == 0) {
-    // TODO(perf): one warp encodes the whole list; block-parallel encode for very long lists
+  uint32_t* enc_dst = a.enc + a.eoff[g];
+  if (a.want_enc && outn >= 4096) {
+    // all 32 warps: block sizes -> prefix -> blocks in parallel.  The slot holds
+    // n + n/4 + 8 words; its last outn/128 words are free while the stream is written
+    // (the stream ends before them for every list of >= 670 values) and hold the block table.
+    uint32_t* table = enc_dst + (n + n / 4 + 8) - (outn >> 7);
+    const uint32_t enc = intcomp::enc_emit_cta(v, (uint32_t)outn, enc_dst, table, s_stage, s_ws);
+    if (threadIdx.x == 0) s_enc = enc;
+  } else if (warp_id() == 0) {
     uint32_t enc = 0;
-    if (a.want_enc && outn) enc = intcomp::enc_emit_warp(v, (uint32_t)outn, a.enc + a.eoff[g], s_stage);
+    if (a.want_enc && outn) enc = intcomp::enc_emit_warp(v, (uint32_t)outn, enc_dst, s_stage);
     if (lane_id() == 0) s_enc = enc;
   }
   __syncthreads();

@@ -5,6 +5,8 @@
 //   valuesOffset, file/writer.go:56) -> emit pass.
 // Lists below one 128-block are handled one per thread; longer lists one per warp
 // (32-lane groups match the codec's 32-value groups).
+#include <algorithm>
+
 #include "codec.cuh"
 #include "intcomp.cuh"
 #include "runtime.cuh"
@@ -72,8 +74,12 @@ k_dec_long(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff
 
 int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t nlists,
                        DevBuf<uint32_t>& out, DevBuf<uint64_t>& out_off, uint64_t* total_out,
-                       cudaStream_t s) {
-  II2_TRY(out_off.alloc(nlists + 1, s));
+                       cudaStream_t s, bool scratch_out) {
+  if (scratch_out) {
+    II2_TRY(out_off.alloc_scratch(nlists + 1, s));
+  } else {
+    II2_TRY(out_off.alloc(nlists + 1, s));
+  }
   if (nlists >= (1ull << 32)) {
     set_last_error("more than 2^32 lists in one decode batch");
     return II2_ERR_UNSUPPORTED;
@@ -81,10 +87,10 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
   DevBuf<int> err;
   DevBuf<uint32_t> n_work, worklist;
   DevBuf<uint64_t> d_total;
-  II2_TRY(err.alloc(1, s));
-  II2_TRY(n_work.alloc(1, s));
-  II2_TRY(d_total.alloc(1, s));
-  II2_TRY(worklist.alloc(nlists ? nlists : 1, s));
+  II2_TRY(err.alloc_scratch(1, s));
+  II2_TRY(n_work.alloc_scratch(1, s));
+  II2_TRY(d_total.alloc_scratch(1, s));
+  II2_TRY(worklist.alloc_scratch(nlists ? nlists : 1, s));
   II2_CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
   II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, sizeof(uint32_t), s));
   II2_CUDA_TRY(cudaMemsetAsync(out_off.p + nlists, 0, sizeof(uint64_t), s));
@@ -103,7 +109,11 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
     set_last_error("undecodable intcomp stream in batch");
     return II2_ERR_CORRUPT;
   }
-  II2_TRY(out.alloc(total, s));
+  if (scratch_out) {
+    II2_TRY(out.alloc_scratch(total, s, 16));
+  } else {
+    II2_TRY(out.alloc(total, s, 16));
+  }
   if (nlists) {
     k_dec_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
         d_words, d_woff, nlists, out_off.p, out.p, worklist.p, n_work.p, err.p);
@@ -124,9 +134,9 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
 
 int val_offsets_to_word_offsets(const uint64_t* d_val_off, uint64_t n, uint64_t val_size,
                                 DevBuf<uint64_t>& woff, cudaStream_t s) {
-  II2_TRY(woff.alloc(n + 1, s));
+  II2_TRY(woff.alloc_scratch(n + 1, s));
   DevBuf<int> err;
-  II2_TRY(err.alloc(1, s));
+  II2_TRY(err.alloc_scratch(1, s));
   II2_CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
   k_valoff_to_woff<<<div_up(n + 1, kCodecThreads), kCodecThreads, 0, s>>>(d_val_off, n, val_size,
                                                                           woff.p, err.p);
@@ -142,6 +152,10 @@ int val_offsets_to_word_offsets(const uint64_t* d_val_off, uint64_t n, uint64_t 
 }
 
 // ---------------------------------------------------------------- encode
+constexpr uint64_t kHugeList = 8192;  // values from which a whole CTA encodes one list
+
+// n_work[0] counts the warp-per-list entries (filled from the front of `worklist`), n_work[1]
+// the CTA-per-list entries (filled from the back)
 __global__ void __launch_bounds__(kCodecThreads)
 k_enc_size_short(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
                  uint64_t* __restrict__ sizes, uint32_t* __restrict__ worklist,
@@ -149,11 +163,59 @@ k_enc_size_short(const uint32_t* __restrict__ in, const uint64_t* __restrict__ o
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = off[i], n = off[i + 1] - a;
+  if (n >= kHugeList) {
+    worklist[nlists - 1 - atomicAdd(n_work + 1, 1u)] = (uint32_t)i;
+    return;
+  }
   if (n >= 128) {
     worklist[atomicAdd(n_work, 1u)] = (uint32_t)i;
     return;
   }
   sizes[i] = intcomp::enc_size_thread_small(in + a, (uint32_t)n);
+}
+
+// one CTA per huge list: Σ block sizes + tail
+__global__ void __launch_bounds__(1024)
+k_enc_size_huge(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
+                uint64_t* __restrict__ sizes, const uint32_t* __restrict__ worklist,
+                const uint32_t* __restrict__ n_work) {
+  __shared__ uint64_t ws[1024 / 32 + 2];
+  if (blockIdx.x >= n_work[1]) return;
+  const uint32_t i = worklist[nlists - 1 - blockIdx.x];
+  const uint32_t* v = in + off[i];
+  const uint32_t n = (uint32_t)(off[i + 1] - off[i]);
+  const uint32_t nb = n >> 7, tail = n & 127u;
+  uint64_t acc = 0;
+  for (uint32_t b = warp_id(); b < nb; b += blockDim.x >> 5) {
+    const uint32_t w = intcomp::enc_block_size_warp(v, b);
+    if (lane_id() == 0) acc += w;
+  }
+  if (tail && threadIdx.x < 32) {
+    uint32_t bytes = 0;
+    for (uint32_t t = threadIdx.x; t < tail; t += 32) {
+      const uint32_t idx = nb * 128 + t;
+      bytes += intcomp::vbyte_len(intcomp::zigzag(v[idx], t ? v[idx - 1] : 0u));
+    }
+    bytes = warp_sum(bytes);
+    if (threadIdx.x == 0) acc += 1 + (bytes + 3) / 4;
+  }
+  uint64_t tot;
+  block_exclusive_scan(acc, ws, tot);
+  if (threadIdx.x == 0) sizes[i] = 3 + tot;
+}
+
+__global__ void __launch_bounds__(1024)
+k_enc_emit_huge(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
+                const uint64_t* __restrict__ woff, uint32_t* __restrict__ words,
+                uint32_t* __restrict__ tables, const uint32_t* __restrict__ worklist,
+                const uint32_t* __restrict__ n_work) {
+  __shared__ uint64_t ws[1024 / 32 + 2];
+  __shared__ uint32_t stage[32 * intcomp::kStageWords];
+  if (blockIdx.x >= n_work[1]) return;
+  const uint32_t i = worklist[nlists - 1 - blockIdx.x];
+  // the block table of list i lives at (off[i] - off[0]) / 128 of the shared table scratch
+  intcomp::enc_emit_cta(in + off[i], (uint32_t)(off[i + 1] - off[i]), words + woff[i],
+                        tables + ((off[i] - off[0]) >> 7), stage, ws);
 }
 
 __global__ void __launch_bounds__(kCodecThreads)
@@ -195,20 +257,25 @@ k_enc_emit_long(const uint32_t* __restrict__ in, const uint64_t* __restrict__ of
 }
 
 int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nlists,
-                       DevBuf<uint32_t>& words, DevBuf<uint64_t>& woff, uint64_t* total_words,
-                       cudaStream_t s) {
+                       uint64_t nvals_hint, DevBuf<uint32_t>& words, DevBuf<uint64_t>& woff,
+                       uint64_t* total_words, cudaStream_t s) {
   if (nlists >= (1ull << 32)) {
     set_last_error("more than 2^32 lists in one encode batch");
     return II2_ERR_UNSUPPORTED;
   }
-  II2_TRY(woff.alloc(nlists + 1, s));
+  II2_TRY(woff.alloc_scratch(nlists + 1, s));
   DevBuf<uint32_t> n_work, worklist;
   DevBuf<uint64_t> d_total;
-  II2_TRY(n_work.alloc(1, s));
-  II2_TRY(d_total.alloc(1, s));
-  II2_TRY(worklist.alloc(nlists ? nlists : 1, s));
-  II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, sizeof(uint32_t), s));
+  II2_TRY(n_work.alloc_scratch(2, s));
+  II2_TRY(d_total.alloc_scratch(1, s));
+  II2_TRY(worklist.alloc_scratch(nlists ? nlists : 1, s));
+  II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, 2 * sizeof(uint32_t), s));
   II2_CUDA_TRY(cudaMemsetAsync(woff.p + nlists, 0, sizeof(uint64_t), s));
+  // at most n_vals / kHugeList lists can be huge; n_vals is only known on the device here, so
+  // the launch covers min(nlists, that bound from the caller) CTAs that exit when out of work
+  const unsigned huge_grid = (unsigned)std::min<uint64_t>(nlists, nvals_hint / kHugeList + 1);
+  DevBuf<uint32_t> tables;
+  II2_TRY(tables.alloc_scratch((nvals_hint >> 7) + nlists + 1, s));
   if (nlists) {
     k_enc_size_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
         d_in, d_off, nlists, woff.p, worklist.p, n_work.p);
@@ -216,18 +283,23 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
     k_enc_size_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_in, d_off, woff.p, worklist.p,
                                                           n_work.p);
     II2_LAUNCHED();
+    k_enc_size_huge<<<huge_grid, 1024, 0, s>>>(d_in, d_off, nlists, woff.p, worklist.p, n_work.p);
+    II2_LAUNCHED();
   }
   II2_TRY(exclusive_scan_u64(woff.p, nlists + 1, d_total.p, s));
   uint64_t total = 0;
   II2_CUDA_TRY(cudaMemcpyAsync(&total, d_total.p, sizeof(total), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
-  II2_TRY(words.alloc(total, s));
+  II2_TRY(words.alloc_scratch(total, s));
   if (nlists) {
     k_enc_emit_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(d_in, d_off, nlists,
                                                                              woff.p, words.p);
     II2_LAUNCHED();
     k_enc_emit_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_in, d_off, woff.p, words.p,
                                                           worklist.p, n_work.p);
+    II2_LAUNCHED();
+    k_enc_emit_huge<<<huge_grid, 1024, 0, s>>>(d_in, d_off, nlists, woff.p, words.p, tables.p,
+                                               worklist.p, n_work.p);
     II2_LAUNCHED();
   }
   if (total_words) *total_words = total;
@@ -251,8 +323,8 @@ int ii2_intcomp_encode_u32(const uint32_t* in, const uint64_t* off, uint64_t nli
   uint64_t first = nlists ? off[0] : 0, nvals = nlists ? off[nlists] - off[0] : 0;
   DevBuf<uint32_t> d_in, d_words;
   DevBuf<uint64_t> d_off, d_woff;
-  II2_TRY(d_in.alloc(nvals, s));
-  II2_TRY(d_off.alloc(nlists + 1, s));
+  II2_TRY(d_in.alloc_scratch(nvals, s));
+  II2_TRY(d_off.alloc_scratch(nlists + 1, s));
   if (nvals)
     II2_CUDA_TRY(cudaMemcpyAsync(d_in.p, in + first, nvals * 4, cudaMemcpyHostToDevice, s));
   if (nlists) {
@@ -263,7 +335,7 @@ int ii2_intcomp_encode_u32(const uint32_t* in, const uint64_t* off, uint64_t nli
   // offsets are relative to `in`; the device copy starts at off[0]
   const uint32_t* d_base = d_in.p - first;
   uint64_t total = 0;
-  II2_TRY(intcomp_encode_dev(d_base, d_off.p, nlists, d_words, d_woff, &total, s));
+  II2_TRY(intcomp_encode_dev(d_base, d_off.p, nlists, nvals, d_words, d_woff, &total, s));
   uint32_t* hw = static_cast<uint32_t*>(pinned_alloc(total * 4 + 4));
   uint64_t* ho = static_cast<uint64_t*>(pinned_alloc((nlists + 1) * 8));
   if (!hw || !ho) {
@@ -274,6 +346,7 @@ int ii2_intcomp_encode_u32(const uint32_t* in, const uint64_t* off, uint64_t nli
   if (total) II2_CUDA_TRY(cudaMemcpyAsync(hw, d_words.p, total * 4, cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaMemcpyAsync(ho, d_woff.p, (nlists + 1) * 8, cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  arena_reset(s);
   *words_out = hw;
   *word_off_out = ho;
   return II2_OK;
@@ -289,8 +362,8 @@ int ii2_intcomp_decode_u32(const uint32_t* words, const uint64_t* word_off, uint
   uint64_t first = nlists ? word_off[0] : 0, nw = nlists ? word_off[nlists] - word_off[0] : 0;
   DevBuf<uint32_t> d_words, d_out;
   DevBuf<uint64_t> d_woff, d_ooff;
-  II2_TRY(d_words.alloc(nw, s, 16));
-  II2_TRY(d_woff.alloc(nlists + 1, s));
+  II2_TRY(d_words.alloc_scratch(nw, s, 16));
+  II2_TRY(d_woff.alloc_scratch(nlists + 1, s));
   if (nw) II2_CUDA_TRY(cudaMemcpyAsync(d_words.p, words + first, nw * 4, cudaMemcpyHostToDevice, s));
   if (nlists) {
     II2_CUDA_TRY(cudaMemcpyAsync(d_woff.p, word_off, (nlists + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -298,7 +371,7 @@ int ii2_intcomp_decode_u32(const uint32_t* words, const uint64_t* word_off, uint
     II2_CUDA_TRY(cudaMemsetAsync(d_woff.p, 0, 8, s));
   }
   uint64_t total = 0;
-  II2_TRY(intcomp_decode_dev(d_words.p - first, d_woff.p, nlists, d_out, d_ooff, &total, s));
+  II2_TRY(intcomp_decode_dev(d_words.p - first, d_woff.p, nlists, d_out, d_ooff, &total, s, true));
   uint32_t* hv = static_cast<uint32_t*>(pinned_alloc(total * 4 + 4));
   uint64_t* ho = static_cast<uint64_t*>(pinned_alloc((nlists + 1) * 8));
   if (!hv || !ho) {
@@ -309,6 +382,7 @@ int ii2_intcomp_decode_u32(const uint32_t* words, const uint64_t* word_off, uint
   if (total) II2_CUDA_TRY(cudaMemcpyAsync(hv, d_out.p, total * 4, cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaMemcpyAsync(ho, d_ooff.p, (nlists + 1) * 8, cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  arena_reset(s);
   *out = hv;
   *out_off = ho;
   return II2_OK;

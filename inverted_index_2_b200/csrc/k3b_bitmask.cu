@@ -558,14 +558,14 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
   const uint32_t nchunks = (uint32_t)((max_bits + 65535) / 65536);
   DevBuf<uint32_t> d_vals, d_bits, d_card, d_cidx, d_cont;
   DevBuf<uint64_t> d_rank, d_poff, d_tot;
-  II2_TRY(d_vals.alloc(n, s));
-  II2_TRY(d_rank.alloc(n + 1, s));
-  II2_TRY(d_bits.alloc((size_t)(nchunks ? nchunks : 1) * CHUNK_WORDS, s));
-  II2_TRY(d_card.alloc(nchunks ? nchunks : 1, s));
-  II2_TRY(d_cidx.alloc(nchunks ? nchunks : 1, s));
-  II2_TRY(d_cont.alloc(nchunks ? nchunks : 1, s));
-  II2_TRY(d_poff.alloc(nchunks ? nchunks : 1, s));
-  II2_TRY(d_tot.alloc(4, s));
+  II2_TRY(d_vals.alloc_scratch(n, s));
+  II2_TRY(d_rank.alloc_scratch(n + 1, s));
+  II2_TRY(d_bits.alloc_scratch((size_t)(nchunks ? nchunks : 1) * CHUNK_WORDS, s));
+  II2_TRY(d_card.alloc_scratch(nchunks ? nchunks : 1, s));
+  II2_TRY(d_cidx.alloc_scratch(nchunks ? nchunks : 1, s));
+  II2_TRY(d_cont.alloc_scratch(nchunks ? nchunks : 1, s));
+  II2_TRY(d_poff.alloc_scratch(nchunks ? nchunks : 1, s));
+  II2_TRY(d_tot.alloc_scratch(4, s));
   II2_CUDA_TRY(cudaMemsetAsync(d_bits.p, 0, (size_t)(nchunks ? nchunks : 1) * CHUNK_WORDS * 4, s));
   uint64_t h_tot[4] = {0, 0, 0, 0};
   if (n) {
@@ -605,7 +605,7 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
     return II2_ERR_UNSUPPORTED;
   }
   DevBuf<uint8_t> d_out;
-  II2_TRY(d_out.alloc(total, s, 8));
+  II2_TRY(d_out.alloc_scratch(total, s, 8));
   k_bm_header<<<div_up((uint64_t)nc + 1, BM_THREADS), BM_THREADS, 0, s>>>(
       d_card.p, d_poff.p, d_cont.p, nc, has_run, d_out.p, desc_at, offs_at, has_off,
       (uint32_t)data_at);
@@ -624,6 +624,7 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
     set_last_error("bitmask put: %s", cudaGetErrorString(e));
     return II2_ERR_CUDA;
   }
+  arena_reset(s);
   *bytes = h;
   *nbytes = total;
   return II2_OK;
@@ -641,10 +642,10 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
   DevBuf<GetMeta> d_meta;
   DevBuf<uint64_t> d_info;
   DevBuf<int> d_err;
-  II2_TRY(d_enc.alloc(nenc, s, 16));
-  II2_TRY(d_meta.alloc(meta_cap, s));
-  II2_TRY(d_info.alloc(3, s));
-  II2_TRY(d_err.alloc(1, s));
+  II2_TRY(d_enc.alloc_scratch(nenc, s, 16));
+  II2_TRY(d_meta.alloc_scratch(meta_cap, s));
+  II2_TRY(d_info.alloc_scratch(3, s));
+  II2_TRY(d_err.alloc_scratch(1, s));
   if (nenc) II2_CUDA_TRY(cudaMemcpyAsync(d_enc.p, enc, nenc, cudaMemcpyHostToDevice, s));
   II2_CUDA_TRY(cudaMemsetAsync(d_err.p, 0, 4, s));
   k_bm_get_parse<<<1, 1024, 0, s>>>(d_enc.p, nenc, d_meta.p, meta_cap, d_info.p);
@@ -659,7 +660,7 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
   const uint32_t nc = (uint32_t)info[0];
   const uint64_t total = info[1];
   DevBuf<uint32_t> d_out;
-  II2_TRY(d_out.alloc(total, s));
+  II2_TRY(d_out.alloc_scratch(total, s));
   if (nc) {
     const uint32_t cookie = (uint32_t)enc[0] | ((uint32_t)enc[1] << 8);
     const uint64_t desc_at = cookie == 12347u ? 4 + ((uint64_t)nc + 7) / 8 : 8;
@@ -689,6 +690,7 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
     set_last_error("undecodable roaring buffer");
     return II2_ERR_CORRUPT;
   }
+  arena_reset(s);
   *vals = h;
   *n = total;
   return II2_OK;
