@@ -36,16 +36,17 @@ constexpr uint32_t REG_CAP = 256;  // values a warp sorts in registers
 constexpr uint32_t K1B_SMALL_D = 64;  // distinct terms ranked by counting instead of sorting
 constexpr uint16_t K1B_EMPTY = 0xFFFFu;
 constexpr uint32_t K12_PENDING = 0xFFFFFFFFu;
+constexpr uint32_t K1B_HEAVY = 0xFFFFFFFFu;   // pbase of a heavy term
 
 // What K1b knows about a distinct term, in merged order inside its bucket (index = bucket base
 // bk_pos[b] + rank, like GroupRec).
 struct GroupIn {
   uint32_t inst;   // global instance id of one source (names the term bytes)
   uint32_t tlen;   // term length
-  uint32_t src;    // first source in src_ptr / src_len
+  uint32_t src;    // first source in src_ptr / src_len (filled for heavy terms only)
   uint32_t c;      // number of sources
   uint32_t L;      // Σ source lengths if <= REG_CAP, anything larger otherwise
-  uint32_t pst;    // postings of the light terms before it in the bucket (decoded slot)
+  uint32_t pst;    // postings of the light terms before it in the bucket: its gather slot
   uint32_t eslot;  // `_val` staging words reserved before it in the bucket
   uint32_t pad;
 };
@@ -60,16 +61,39 @@ struct K1bArgs {
   const uint32_t* part;
   const uint64_t* bk_pos;
   const uint32_t* bk_cpl;
+  const uint64_t* bk_P;
   GroupIn* gin;
-  uint64_t* src_ptr;
+  uint32_t* gath;   // [N_in] light terms: the sources of a term copied back to back (its slot)
+  uint64_t* src_ptr;  // heavy terms only: (pointer, length) of every source
   uint32_t* src_len;
   uint32_t* bk_D;   // [B] distinct terms per bucket
   uint32_t bucket0; // first bucket of this launch (the grid covers a chunk of buckets)
 };
 
+// Order of two terms whose bytes before `skip` are equal and which both run past `skip`:
+// further 16-byte windows until one differs or a term ends.  Kept out of line: the compiler
+// must not hoist its offset loads into the callers' fast path.
+__device__ __noinline__ int k1b_tail_compare(const SegDesc* __restrict__ segs, uint32_t sx,
+                                             uint32_t ix, uint32_t nx, uint32_t sy, uint32_t iy,
+                                             uint32_t ny, uint32_t skip) {
+  const SegDesc& dx = segs[sx];
+  const SegDesc& dy = segs[sy];
+  const uint32_t ox = __ldg(dx.toff + (dx.lo + (ix - dx.base)));
+  const uint32_t oy = __ldg(dy.toff + (dy.lo + (iy - dy.base)));
+  for (uint32_t c = skip;; c += 16) {
+    uint64_t hx, lx, hy, ly;
+    load_key16(dx.tb, ox, nx, c, hx, lx);
+    load_key16(dy.tb, oy, ny, c, hy, ly);
+    if (hx != hy) return hx < hy ? -1 : 1;
+    if (lx != ly) return lx < ly ? -1 : 1;
+    if (!(nx > c + 16 && ny > c + 16)) break;
+  }
+  return nx < ny ? -1 : (nx > ny ? 1 : 0);
+}
+
 __host__ __device__ inline size_t k1b_smem_bytes(int k) {
   return (size_t)CAP_I * 16                      // key_hi, key_lo
-         + (size_t)CAP_I * 4 * 3                 // inst, cnt, gl
+         + (size_t)CAP_I * 4 * 4                 // inst, cnt, gl, pbase
          + (size_t)(5 * k + 1) * 4               // cur, mm, hi, endr, rstart
          + (size_t)CAP_I * 2 * 4                 // seg, tlen, grp, reps
          + (size_t)K1B_HT * 2 + 64;
@@ -89,6 +113,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
   uint32_t* cnt = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
   uint32_t* gl = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
   uint32_t* inst_a = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;  // global instance id
+  // by representative: slot of the term in the bucket's gather region, or K1B_HEAVY
+  uint32_t* pbase = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
   uint16_t* seg_a = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
   uint16_t* tlen = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
   uint16_t* grp = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
@@ -117,21 +143,24 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       endr[s] = a.part[(uint64_t)r1 * k + s];
     }
   }
-  __syncthreads();
   const uint64_t rec_base = a.bk_pos[b];
   const uint32_t cpl = a.bk_cpl[b];
+  uint32_t* const gath = a.gath + a.bk_P[b];
   uint32_t dcount = 0;   // distinct terms so far in this bucket
   uint32_t icount = 0;   // instances so far
   uint32_t pcount = 0;   // postings of light terms so far
   uint32_t ecount = 0;   // staging words so far
+  __syncthreads();
 
   while (W > 0) {
-    // ---------------- choose the sub-tile [cur, mm) ----------------
+    // ---------------- choose the sub-tile [cur, mmp) ----------------
     uint32_t size;
-    if (W <= CAP_I) {
-      for (int s = tid; s < k; s += K1B_THREADS) mm[s] = endr[s];
+    const uint32_t* mmp;   // run ends of the tile
+    if (W <= CAP_I) {      // the usual case: the whole (rest of the) bucket is one tile
+      mmp = endr;
       size = W;
     } else {
+      mmp = mm;
       for (int s = tid; s < k; s += K1B_THREADS) hib[s] = endr[s];
       __syncthreads();
       for (;;) {
@@ -166,8 +195,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         for (int s = tid; s < k; s += K1B_THREADS) hib[s] = mm[s];
         __syncthreads();
       }
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---------------- (1) run starts; reset of the tile state ----------------
     if (k <= 128) {  // every warp scans for itself (identical values): no warp waits for another
@@ -175,7 +204,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int s = lane * 4 + j;
-        v[j] = s < k ? mm[s] - cur[s] : 0u;
+        v[j] = s < k ? mmp[s] - cur[s] : 0u;
         sum += v[j];
       }
       uint32_t ex = warp_inclusive_scan(sum) - sum;
@@ -190,7 +219,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       uint32_t run = 0;
       for (int base = 0; base < k; base += K1B_THREADS) {
         const int s = base + tid;
-        const uint32_t v = s < k ? mm[s] - cur[s] : 0u;
+        const uint32_t v = s < k ? mmp[s] - cur[s] : 0u;
         uint32_t tot;
         const uint32_t ex = block_exclusive_scan(v, s_ws32, tot);
         if (s < k) rstart[s] = run + ex;
@@ -210,13 +239,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     auto tail_compare = [&](uint32_t x, uint32_t y) -> int {
       const uint32_t skip = cpl + 16;
       const uint32_t nx = tlen[x], ny = tlen[y];
-      if (nx > skip && ny > skip) {
-        const SegDesc& sx = a.segs[seg_a[x]];
-        const SegDesc& sy = a.segs[seg_a[y]];
-        const uint8_t* px = sx.tb + __ldg(sx.toff + (sx.lo + (inst_a[x] - sx.base))) + skip;
-        const uint8_t* py = sy.tb + __ldg(sy.toff + (sy.lo + (inst_a[y] - sy.base))) + skip;
-        return term_compare(px, nx - skip, py, ny - skip);
-      }
+      if (nx > skip && ny > skip)
+        return k1b_tail_compare(a.segs, seg_a[x], inst_a[x], nx, seg_a[y], inst_a[y], ny, skip);
       return nx < ny ? -1 : (nx > ny ? 1 : 0);
     };
     auto less = [&](uint16_t x, uint16_t y) -> bool {
@@ -229,8 +253,9 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
 
     // ---------------- (2) key windows + posting lengths ----------------
     constexpr int PER = CAP_I / K1B_THREADS;
-    uint64_t pp[PER];  // first posting of the thread's instances (kept for the source list)
-    uint32_t pl[PER];  // their lengths
+    uint64_t pp[PER];   // first posting of the thread's instances
+    uint32_t pl[PER];   // their lengths
+    uint32_t ofs[PER];  // where they go inside their term's gather slot
     {
       int sg[PER];
       uint32_t ix[PER], to[PER], tn[PER];
@@ -315,8 +340,10 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       }
       grp[i] = (uint16_t)rep;
       atomicAdd(&cnt[rep], 1u);
-      // term length, saturating per source so the sum cannot wrap: heavy iff sum > REG_CAP
-      atomicAdd(&gl[rep], pl[j] > REG_CAP ? REG_CAP + 1 : pl[j]);
+      // Σ source lengths, saturating per source so the sum cannot wrap: heavy iff sum > REG_CAP.
+      // For a light term every addend is exact, so the value before the add is where this
+      // source starts inside the term's gather slot.
+      ofs[j] = atomicAdd(&gl[rep], pl[j] > REG_CAP ? REG_CAP + 1 : pl[j]);
     }
     __syncthreads();
     const uint32_t D = s_nreps;
@@ -326,28 +353,30 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
 #pragma unroll 1
       for (uint32_t t = warp; t < D; t += K1B_WARPS) {
         const uint32_t me = reps[t];
-        uint32_t rank = 0;
-        uint64_t acc = 0;  // instances | postings << 16 | staging words << 36 of the smaller terms
+        uint32_t rank = 0, ib = 0, pst = 0, est = 0;  // smaller terms: count / instances / postings / staging words
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < D; j0 += 32) {
           const uint32_t j = j0 + lane;
-          uint64_t mine = 0;
+          uint32_t m_i = 0, m_p = 0, m_e = 0;
           bool lt = false;
           if (j < D) {
             const uint32_t o = reps[j];
             lt = o != me && less((uint16_t)o, (uint16_t)me);
             if (lt) {
               const uint32_t len = gl[o];
-              mine = cnt[o];
-              if (len <= REG_CAP) mine |= ((uint64_t)len << 16) | ((uint64_t)enc_slot_words(len) << 36);
+              m_i = cnt[o];
+              if (len <= REG_CAP) {
+                m_p = len;
+                m_e = enc_slot_words(len);
+              }
             }
           }
           rank += __popc(__ballot_sync(0xffffffffu, lt));
-          acc += warp_sum(mine);
+          ib += __reduce_add_sync(0xffffffffu, m_i);
+          pst += __reduce_add_sync(0xffffffffu, m_p);
+          est += __reduce_add_sync(0xffffffffu, m_e);
         }
         if (lane == 0) {
-          const uint32_t ib = (uint32_t)(acc & 0xFFFFu), pst = (uint32_t)((acc >> 16) & 0xFFFFFu),
-                         est = (uint32_t)(acc >> 36);
           const uint32_t len = gl[me];
           const bool light = len <= REG_CAP;
           GroupIn g;
@@ -361,6 +390,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
           g.pad = 0;
           a.gin[rec_base + dcount + rank] = g;
           sbase[me] = g.src;
+          pbase[me] = light ? g.pst : K1B_HEAVY;
           if (rank == D - 1) {
             s_tot[0] = pst + (light ? len : 0u);
             s_tot[1] = est + (light ? enc_slot_words(len) : 0u);
@@ -400,6 +430,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
           g.pad = 0;
           a.gin[rec_base + dcount + r] = g;
           sbase[me] = g.src;
+          pbase[me] = len <= REG_CAP ? g.pst : K1B_HEAVY;
         }
         run_i += ti;
         run_p += tp;
@@ -412,15 +443,42 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     }
     __syncthreads();
 
-    // ---------------- (5) source list of every term (any order: the union sorts) -------------
+    // ---------------- (5) sources of every term ---------------------------------------------
+    // light terms: the postings themselves, copied into the term's slot (any order: the union
+    // sorts; a single-source term is one copy, order kept); heavy terms: (pointer, length)
 #pragma unroll
     for (int j = 0; j < PER; j++) {
       const uint32_t i = tid + j * K1B_THREADS;
       if (i < size) {
         const uint32_t g = grp[i];
-        const uint32_t at = sbase[g] + (atomicSub(&cnt[g], 1u) - 1u);
-        a.src_ptr[at] = pp[j];
-        a.src_len[at] = pl[j];
+        const uint32_t pb = pbase[g];
+        if (pb != K1B_HEAVY) {
+          const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(pp[j]);
+          uint32_t* __restrict__ dst = gath + pb + ofs[j];
+          const uint32_t n = pl[j];
+          uint32_t t = 0;
+#pragma unroll 1
+          for (; t + 4 <= n; t += 4) {  // loads first: four in flight per thread
+            const uint32_t x0 = __ldg(src + t), x1 = __ldg(src + t + 1), x2 = __ldg(src + t + 2),
+                           x3 = __ldg(src + t + 3);
+            dst[t] = x0;
+            dst[t + 1] = x1;
+            dst[t + 2] = x2;
+            dst[t + 3] = x3;
+          }
+          if (t < n) {
+            const uint32_t x0 = __ldg(src + t);
+            const uint32_t x1 = t + 1 < n ? __ldg(src + t + 1) : 0u;
+            const uint32_t x2 = t + 2 < n ? __ldg(src + t + 2) : 0u;
+            dst[t] = x0;
+            if (t + 1 < n) dst[t + 1] = x1;
+            if (t + 2 < n) dst[t + 2] = x2;
+          }
+        } else {
+          const uint32_t at = sbase[g] + (atomicSub(&cnt[g], 1u) - 1u);
+          a.src_ptr[at] = pp[j];
+          a.src_len[at] = pl[j];
+        }
       }
     }
     dcount += D;
@@ -430,141 +488,205 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     W -= size;
     if (W == 0) break;
     __syncthreads();
-    for (int s = tid; s < k; s += K1B_THREADS) cur[s] = mm[s];
+    for (int s = tid; s < k; s += K1B_THREADS) cur[s] = mmp[s];
     __syncthreads();
   }
   if (tid == 0) a.bk_D[b] = dcount;
 }
 
-// ---- warp-level union of one group held in shared memory --------------------------------
-// Sorting network over 32*R values striped over the warp (element e = r*32 + lane): for each
-// block size a mirrored "flip" step, then half-cleaners.  The lower element of every pair
-// takes the minimum, so a compare-exchange is one shuffle + one predicated min/max.  The
-// shuffle stages run as LOOPS over the distance (only the few register-to-register stages are
-// unrolled): the kernel stays small enough for the instruction cache.
-template <int R>
-__device__ __forceinline__ void shuffle_stage(uint32_t (&v)[R], uint32_t mask, bool lower) {
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], mask);
-    v[r] = lower ? min(v[r], o) : max(v[r], o);
-  }
+// ---- union of one term by a group of W lanes (W = 16: two terms per warp; W = 32: one) ------
+// The term's values live BLOCKED in registers: lane hl of the group holds elements
+// hl*8 .. hl*8+7.  Eight values per lane keep most compare-exchanges of the sorting network
+// inside a thread (two min/max instructions, no shuffle): a local 19-comparator network sorts
+// the eight, then one bitonic merge level per doubling — a mirrored "flip" across lanes, the
+// half-cleaners whose distance is a whole number of lanes (one shuffle + one predicated
+// min/max per value), and three local half-cleaners (distance 4, 2, 1).  The shuffle pipe
+// and shared memory share one data path on the SM and were the busiest unit of the striped
+// version (ncu: lsu wavefronts 66 %), hence this layout: 80 shuffles sort two 128-value terms.
+__device__ __forceinline__ void cex(uint32_t& x, uint32_t& y) {
+  const uint32_t lo = min(x, y), hi = max(x, y);
+  x = lo;
+  y = hi;
 }
 
-template <int R>
-__device__ __forceinline__ void sort_regs(uint32_t (&v)[R]) {
-  const unsigned lane = lane_id();
-  // block sizes 2..32: everything stays inside one register row.  Up to four rows the network
-  // is small enough to unroll completely (5 KB of SASS); eight rows keep the distance loops.
-  if (R <= 4) {
+__device__ __forceinline__ void sort8_local(uint32_t (&v)[8]) {
+  cex(v[0], v[1]); cex(v[2], v[3]); cex(v[4], v[5]); cex(v[6], v[7]);
+  cex(v[0], v[2]); cex(v[1], v[3]); cex(v[4], v[6]); cex(v[5], v[7]);
+  cex(v[1], v[2]); cex(v[5], v[6]); cex(v[0], v[4]); cex(v[3], v[7]);
+  cex(v[1], v[5]); cex(v[2], v[6]);
+  cex(v[1], v[4]); cex(v[3], v[6]);
+  cex(v[2], v[4]); cex(v[3], v[5]);
+  cex(v[3], v[4]);
+}
+
+__device__ __forceinline__ void clean8_local(uint32_t (&v)[8]) {
+  cex(v[0], v[4]); cex(v[1], v[5]); cex(v[2], v[6]); cex(v[3], v[7]);
+  cex(v[0], v[2]); cex(v[1], v[3]); cex(v[4], v[6]); cex(v[5], v[7]);
+  cex(v[0], v[1]); cex(v[2], v[3]); cex(v[4], v[5]); cex(v[6], v[7]);
+}
+
+// one merge level: blocks of K elements (K/8 lanes) become sorted; K >= 16
+template <int K>
+__device__ __forceinline__ void merge_level(uint32_t (&v)[8], unsigned hl) {
+  {  // flip: element e pairs with e ^ (K-1) = (lane ^ (K/8-1), 7 - r)
+    const bool lower = (hl & (K / 16)) == 0;
+    uint32_t o[8];
 #pragma unroll
-    for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
-      shuffle_stage<R>(v, kk - 1, (lane & (kk >> 1)) == 0);
+    for (int r = 0; r < 8; r++) o[r] = __shfl_xor_sync(0xffffffffu, v[7 - r], K / 8 - 1);
 #pragma unroll
-      for (uint32_t j = kk >> 2; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
+    for (int r = 0; r < 8; r++) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
+  }
+#pragma unroll
+  for (int j = K / 4; j >= 8; j >>= 1) {  // half-cleaners across lanes
+    const bool lower = (hl & (j / 8)) == 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j / 8);
+      v[r] = lower ? min(v[r], o) : max(v[r], o);
     }
+  }
+  clean8_local(v);
+}
+
+// sorts the 8*W values of every group; nmax = largest real length in the warp (padding is
+// 0xFFFFFFFF at the end, so levels whose blocks would only hold padding are skipped)
+template <int W>
+__device__ __forceinline__ void sort_blocked(uint32_t (&v)[8], unsigned hl, uint32_t nmax) {
+  sort8_local(v);
+  if (nmax > 8) merge_level<16>(v, hl);
+  if (nmax > 16) merge_level<32>(v, hl);
+  if (nmax > 32) merge_level<64>(v, hl);
+  if (nmax > 64) merge_level<128>(v, hl);
+  if (W == 32 && nmax > 128) merge_level<256>(v, hl);
+}
+
+// Union of the term of this lane's group: L gathered values at `slot` (global) -> sorted
+// (slices.Sort) and deduped (slices.Compact) when the term has >= 2 sources (a single-source
+// term passes through in source order, duplicates kept: survey Q4) -> removed filter ->
+// survivors compacted into buf[0..outn) (shared, this group's).  Every lane of the warp must
+// call; groups with nothing to do pass L = 0.  Returns outn (uniform inside the group).
+template <int W>
+__device__ __forceinline__ uint32_t union_blocked(const uint32_t* slot, uint32_t* buf, uint32_t L,
+                                                  bool multi, const RemovedSet& rem) {
+  const unsigned lane = lane_id(), hl = lane & (W - 1);
+  uint32_t v[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const uint32_t e = hl * 8 + r;
+    v[r] = e < L ? slot[e] : 0xFFFFFFFFu;
+  }
+  const bool any_multi = __any_sync(0xffffffffu, multi && L > 1);
+  if (any_multi) {
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, multi ? L : 0u);
+    sort_blocked<W>(v, hl, nmax);
+    if (!multi) {  // the other group of the warp holds a pass-through term: undo
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const uint32_t e = hl * 8 + r;
+        v[r] = e < L ? slot[e] : 0xFFFFFFFFu;
+      }
+    }
+  }
+  // all membership probes first: eight independent loads in flight per lane
+  uint32_t keep = 0;
+  if (rem.bitmap) {  // bit v of the bitmap <=> v removed, for v < bitmap_bits (<= 2^29)
+    const uint32_t nbits = (uint32_t)rem.bitmap_bits;
+    uint32_t word[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const bool probe = hl * 8 + r < L && v[r] < nbits;
+      word[r] = probe ? __ldg(rem.bitmap + (v[r] >> 5)) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      keep |= (hl * 8 + r < L && !((word[r] >> (v[r] & 31u)) & 1u)) ? 1u << r : 0u;
   } else {
-#pragma unroll 1
-    for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
-      shuffle_stage<R>(v, kk - 1, (lane & (kk >> 1)) == 0);
-#pragma unroll 1
-      for (uint32_t j = kk >> 2; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
-    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (hl * 8 + r < L && !is_removed(rem, v[r])) keep |= 1u << r;
   }
-  // block sizes 64..32R: flip and the first half-cleaners pair register rows
+  const uint32_t up = __shfl_up_sync(0xffffffffu, v[7], 1, W);  // last value of the lane below
+  if (multi) {  // drop a value equal to its predecessor (sorted order)
+    if (hl > 0 && up == v[0]) keep &= ~1u;
 #pragma unroll
-  for (uint32_t kk = 64; kk <= 32u * R; kk <<= 1) {
-    const int rm = (int)(kk >> 5) - 1, hb = (int)(kk >> 6);
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      if ((r & hb) == 0) {
-        const int r2 = r ^ rm;
-        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, v[r2], 31);
-        const uint32_t o2 = __shfl_xor_sync(0xffffffffu, v[r], 31);
-        v[r] = min(v[r], o1);
-        v[r2] = max(v[r2], o2);
-      }
-    }
-#pragma unroll
-    for (uint32_t j = kk >> 2; j >= 32; j >>= 1) {
-      const int dr = (int)(j >> 5);
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        if ((r & dr) == 0) {
-          const uint32_t x = v[r], y = v[r | dr];
-          v[r] = min(x, y);
-          v[r | dr] = max(x, y);
-        }
-      }
-    }
-    if (R <= 4) {
-#pragma unroll
-      for (uint32_t j = 16; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
-    } else {
-#pragma unroll 1
-      for (uint32_t j = 16; j > 0; j >>= 1) shuffle_stage<R>(v, j, (lane & j) == 0);
-    }
+    for (int r = 1; r < 8; r++)
+      if (v[r] == v[r - 1]) keep &= ~(1u << r);
   }
-}
-
-// value before element (r, lane) in striped order (undefined for element 0)
-template <int R>
-__device__ __forceinline__ uint32_t prev_striped(const uint32_t (&v)[R], int r) {
-  uint32_t prev = __shfl_up_sync(0xffffffffu, v[r], 1);
-  if (r > 0) {
-    const uint32_t p31 = __shfl_sync(0xffffffffu, v[r - 1], 31);
-    if (lane_id() == 0) prev = p31;
-  }
-  return prev;
-}
-
-// Sort (slices.Sort) + dedup (slices.Compact) + removed filter of base[0..L), compacted back
-// to base[0..outn).  Returns outn.
-template <int R>
-__device__ __forceinline__ uint32_t union_regs(uint32_t* base, uint32_t L, const RemovedSet& rem) {
-  const unsigned lane = lane_id();
-  uint32_t v[R];
+  const uint32_t cnt = __popc(keep);
+  uint32_t inc = cnt;
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    const uint32_t e = r * 32 + lane;
-    v[r] = e < L ? base[e] : 0xFFFFFFFFu;  // padding sorts to the end; only L values are used
+  for (int d = 1; d < W; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d, W);
+    if (hl >= (unsigned)d) inc += o;
   }
-  sort_regs<R>(v);
-  __syncwarp();
-  const unsigned lt = (1u << lane) - 1u;
-  uint32_t outn = 0;
+  const uint32_t outn = __shfl_sync(0xffffffffu, inc, W - 1, W);
+  uint32_t* dst = buf + (inc - cnt);
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    const uint32_t e = r * 32 + lane;
-    const uint32_t prev = prev_striped<R>(v, r);
-    const bool keep = e < L && (e == 0 || prev != v[r]) && !is_removed(rem, v[r]);
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) base[outn + __popc(bal & lt)] = v[r];
-    outn += __popc(bal);
+  for (int r = 0; r < 8; r++) {  // predicated store + pointer bump: no branches
+    const bool k = (keep >> r) & 1u;
+    if (k) *dst = v[r];
+    dst += k ? 1 : 0;
   }
   __syncwarp();
   return outn;
 }
 
-// single-source pass-through: order and duplicates kept, only the filter (in place)
-__device__ __forceinline__ uint32_t filter_inplace_warp(uint32_t* base, uint32_t L,
-                                                     const RemovedSet& rem) {
-  if (rem.n == 0) return L;
-  const unsigned lane = lane_id();
-  const unsigned lt = (1u << lane) - 1u;
-  uint32_t outn = 0;
-  for (uint32_t e0 = 0; e0 < L; e0 += 32) {
-    const uint32_t e = e0 + lane;
-    const bool valid = e < L;
-    const uint32_t v = valid ? base[e] : 0u;
-    const bool keep = valid && !is_removed(rem, v);
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    __syncwarp();
-    if (keep) base[outn + __popc(bal & lt)] = v;
-    outn += __popc(bal);
-    __syncwarp();
+// intcomp.CompressUint32 of v[0..n), n <= 127 (one var-byte section: count word, then
+// zigzag deltas, 7 bits per byte, low group first, last byte |= 0x80, first delta against 0;
+// oracle/intcomp_ref.c), by a group of W lanes: lane hl codes values hl*8 .. hl*8+7.
+// v and out are the group's shared buffers (16-byte aligned).  Returns the words (uniform in
+// the group); n = 0 -> 0.  Every lane of the warp must call.
+template <int W>
+__device__ __forceinline__ uint32_t encode_small_blocked(const uint32_t* v, uint32_t n,
+                                                         uint32_t* out) {
+  const unsigned hl = lane_id() & (W - 1);
+  const uint32_t e0 = hl * 8;
+  // values past n read as garbage inside the group's buffer and get length 0
+  const uint4 a = *reinterpret_cast<const uint4*>(v + e0);
+  const uint4 b = *reinterpret_cast<const uint4*>(v + e0 + 4);
+  const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t prev = e0 ? v[e0 - 1] : 0u;
+  uint32_t z[8], lens = 0, bytes = 0;  // lens: 4 bits per value
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    z[r] = intcomp::zigzag(x[r], prev);
+    prev = x[r];
+    // ceil(bitlen / 7) for bitlen in 1..32 (z = 0 codes as one byte): (bitlen + 6) * 37 >> 8
+    const uint32_t bl = 32u - __clz(z[r] | 1u);
+    const uint32_t len = e0 + r < n ? ((bl + 6u) * 37u) >> 8 : 0u;
+    lens |= len << (4 * r);
+    bytes += len;
   }
-  return outn;
+  uint32_t inc = bytes;
+#pragma unroll
+  for (int d = 1; d < W; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d, W);
+    if (hl >= (unsigned)d) inc += o;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, W - 1, W);
+  uint8_t* sb = reinterpret_cast<uint8_t*>(out + 1) + (inc - bytes);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const uint32_t zz = z[r];
+    const uint32_t len = (lens >> (4 * r)) & 15u;
+    // the low four 7-bit groups spread over four bytes, terminator bit on the last byte
+    uint32_t w = (zz & 0x7Fu) | ((zz << 1) & 0x7F00u) | ((zz << 2) & 0x7F0000u) |
+                 ((zz << 3) & 0x7F000000u);
+    if (len <= 4) w |= 0x80u << ((8 * len - 8) & 31u);  // len 0 stores nothing
+    if (len > 0) sb[0] = (uint8_t)w;
+    if (len > 1) sb[1] = (uint8_t)(w >> 8);
+    if (len > 2) sb[2] = (uint8_t)(w >> 16);
+    if (len > 3) sb[3] = (uint8_t)(w >> 24);
+    if (len > 4) sb[4] = (uint8_t)((zz >> 28) | 0x80u);
+    sb += len;
+  }
+  if (n) {
+    if (hl == 0) out[0] = n;
+    uint8_t* end = reinterpret_cast<uint8_t*>(out + 1) + total;
+    if (hl < ((4u - (total & 3u)) & 3u)) end[hl] = 0;  // zero padding of the last word
+  }
+  __syncwarp();  // no lane leaves early: the groups of a warp meet here
+  return n ? 1 + (total + 3) / 4 : 0u;
 }
 
 // intcomp.CompressUint32 of v[0..n) (shared memory) into out (shared memory, a different
@@ -642,10 +764,13 @@ __device__ __forceinline__ uint32_t encode_shared_warp(const uint32_t* v, uint32
   return pos;
 }
 
-// ---------------------------------------------------------------- K2b: one warp per term
-constexpr int K2B_THREADS = 256;
+// ---------------------------------------------------------------- K2b: two terms per warp
+constexpr int K2B_THREADS = 128;
 constexpr int K2B_WARPS = K2B_THREADS / 32;
+constexpr uint32_t K2B_HALF = 128;  // a 16-lane group handles terms of fewer values than this
 constexpr uint32_t K2B_ENC_WORDS = 3 + 2 * 129 + 1 + (5 * 127 + 3) / 4 + 1;  // enc_bound(255)
+constexpr uint32_t K2B_EBUF = (K2B_ENC_WORDS + 7) & ~7u;  // per warp; a half gets half of it
+static_assert(K2B_EBUF / 2 >= 1 + (5 * 127 + 3) / 4, "var-byte stream of 127 values fits a half");
 
 struct K2bArgs {
   const uint64_t* bk_pos;
@@ -653,12 +778,10 @@ struct K2bArgs {
   const uint64_t* bk_E;   // exclusive prefixes of the staging words
   const uint32_t* bk_D;
   const GroupIn* gin;
-  const uint64_t* src_ptr;
-  const uint32_t* src_len;
   RemovedSet rem;
   int want_enc, want_dec, keep_empty;
   GroupRec* recs;
-  uint32_t* tmp_post;
+  uint32_t* gath;     // gather slots filled by K1b; the decoded result replaces them in place
   uint32_t* tmp_enc;
   uint64_t* bk_raw;  // [4][nb1], zeroed
   uint32_t nb1;
@@ -668,101 +791,122 @@ struct K2bArgs {
   uint32_t bucket0;  // first bucket of this launch
 };
 
-__global__ void __launch_bounds__(K2B_THREADS, 6) k2b_union_kernel(const K2bArgs a) {
-  __shared__ uint32_t s_buf[K2B_WARPS][REG_CAP];
-  __shared__ uint32_t s_enc[K2B_WARPS][K2B_ENC_WORDS + 3];
+#ifndef K2B_MIN_CTAS
+#define K2B_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(const K2bArgs a) {
+  __shared__ __align__(16) uint32_t s_buf[K2B_WARPS][REG_CAP];
+  __shared__ __align__(16) uint32_t s_enc[K2B_WARPS][K2B_EBUF];
   const unsigned lane = lane_id(), warp = warp_id();
+  const unsigned half = lane >> 4, hl = lane & 15u;
   const uint32_t b = a.bucket0 + blockIdx.x;
   const uint32_t D = a.bk_D[b];
   if (D == 0) return;
   const uint64_t rec_base = a.bk_pos[b];
-  uint32_t* buf = s_buf[warp];
-  uint32_t* ebuf = s_enc[warp];
-  uint32_t acc_t = 0, acc_tb = 0, acc_e = 0;
+  uint32_t* const gath = a.gath + a.bk_P[b];
+  uint32_t* const enc_base = a.tmp_enc + a.bk_E[b];
+  uint32_t acc_t = 0, acc_tb = 0, acc_e = 0;  // per group leader (hl == 0) and warp leader
   uint64_t acc_p = 0;
 #pragma unroll 1
-  for (uint32_t r = warp; r < D; r += K2B_WARPS) {
-    const GroupIn g = a.gin[rec_base + r];
-    GroupRec rec;
-    rec.inst = g.inst;
-    rec.tlen = g.tlen;
-    rec.dec = 0;
-    rec.eoff = 0;
-    rec.enc = 0;
-    if (g.L > REG_CAP) {  // heavy: the multi-CTA path works from the same source list
-      if (lane == 0) {
-        const uint32_t slot = atomicAdd(a.n_large, 1u);
-        a.large_rec[slot] = (uint32_t)(rec_base + r);
-        a.large_bucket[slot] = b;
-        rec.cnt = K12_PENDING;
-        a.recs[rec_base + r] = rec;
-      }
-      continue;
-    }
-    const uint32_t L = g.L;
-    // gather the sources into the warp's slot: lane j copies source j
-    uint32_t filled = 0;
-#pragma unroll 1
-    for (uint32_t j0 = 0; j0 < g.c; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      uint32_t n = 0;
-      const uint32_t* src = nullptr;
-      if (j < g.c) {
-        n = a.src_len[g.src + j];
-        src = reinterpret_cast<const uint32_t*>(a.src_ptr[g.src + j]);
-      }
-      const uint32_t inc = warp_inclusive_scan(n);
-      uint32_t* dst = buf + filled + (inc - n);
-      uint32_t t = 0;
-#pragma unroll 1
-      for (; t + 4 <= n; t += 4) {
-        const uint32_t x0 = __ldg(src + t), x1 = __ldg(src + t + 1), x2 = __ldg(src + t + 2),
-                       x3 = __ldg(src + t + 3);
-        dst[t] = x0;
-        dst[t + 1] = x1;
-        dst[t + 2] = x2;
-        dst[t + 3] = x3;
-      }
-#pragma unroll 1
-      for (; t < n; t++) dst[t] = __ldg(src + t);
-      filled += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    __syncwarp();
-    uint32_t outn;
-    if (g.c == 1) {
-      outn = filter_inplace_warp(buf, L, a.rem);
-    } else if (L <= 64) {
-      outn = union_regs<2>(buf, L, a.rem);
-    } else if (L <= 128) {
-      outn = union_regs<4>(buf, L, a.rem);
-    } else {
-      outn = union_regs<8>(buf, L, a.rem);
-    }
-    uint32_t* dec = a.want_dec ? a.tmp_post + a.bk_P[b] + g.pst : nullptr;
-    uint32_t* enc_dst = a.want_enc ? a.tmp_enc + a.bk_E[b] + g.eslot : nullptr;
-    uint32_t enc = 0;
-    if (a.want_dec)
-      for (uint32_t e = lane; e < outn; e += 32) dec[e] = buf[e];
-    if (a.want_enc && outn) {
-      enc = encode_shared_warp(buf, outn, ebuf);
-      for (uint32_t e = lane; e < enc; e += 32) enc_dst[e] = ebuf[e];
-    }
-    __syncwarp();
-    if (lane == 0) {
-      rec.dec = reinterpret_cast<uint64_t>(dec);
-      rec.eoff = reinterpret_cast<uint64_t>(enc_dst);
-      rec.cnt = outn;
-      rec.enc = enc;
+  for (uint32_t p0 = 2 * warp; p0 < D; p0 += 2 * K2B_WARPS) {
+    // ---- the pair of terms of this warp: one per 16-lane group ----
+    const uint32_t r = p0 + half;
+    const bool has = r < D;
+    GroupIn g = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (has) g = a.gin[rec_base + r];
+    const bool heavy = has && g.L > REG_CAP;
+    const bool wide = has && !heavy && g.L >= K2B_HALF;
+    if (heavy && hl == 0) {  // the multi-CTA path works from the source list
+      const uint32_t slot = atomicAdd(a.n_large, 1u);
+      a.large_rec[slot] = (uint32_t)(rec_base + r);
+      a.large_bucket[slot] = b;
+      GroupRec rec;
+      rec.inst = g.inst;
+      rec.tlen = g.tlen;
+      rec.dec = 0;
+      rec.eoff = 0;
+      rec.enc = 0;
+      rec.cnt = K12_PENDING;
       a.recs[rec_base + r] = rec;
     }
-    if (outn || a.keep_empty) {
-      acc_t += 1;
-      acc_tb += g.tlen;
-      acc_p += outn;
-      acc_e += enc;
+    {
+      const bool mine = has && !heavy && !wide;
+      const uint32_t L = mine ? g.L : 0u;
+      uint32_t* const slot = gath + g.pst;
+      uint32_t* const buf = s_buf[warp] + half * K2B_HALF;
+      uint32_t* const ebuf = s_enc[warp] + half * (K2B_EBUF / 2);
+      const uint32_t outn = union_blocked<16>(slot, buf, L, g.c > 1, a.rem);
+      if (a.want_dec)
+        for (uint32_t e = hl; e < outn; e += 16) slot[e] = buf[e];
+      uint32_t enc = 0;
+      uint32_t* const enc_dst = enc_base + g.eslot;
+      if (a.want_enc) {
+        enc = encode_small_blocked<16>(buf, outn, ebuf);
+        for (uint32_t e = hl; e < enc; e += 16) enc_dst[e] = ebuf[e];
+      }
+      if (mine && hl == 0) {
+        GroupRec rec;
+        rec.inst = g.inst;
+        rec.tlen = g.tlen;
+        rec.dec = reinterpret_cast<uint64_t>(slot);
+        rec.eoff = a.want_enc ? reinterpret_cast<uint64_t>(enc_dst) : 0ull;
+        rec.cnt = outn;
+        rec.enc = enc;
+        a.recs[rec_base + r] = rec;
+        if (outn || a.keep_empty) {
+          acc_t += 1;
+          acc_tb += g.tlen;
+          acc_p += outn;
+          acc_e += enc;
+        }
+      }
+      __syncwarp();
+    }
+    // ---- terms of 128 .. 256 values: the whole warp, one after the other ----
+    unsigned wmask = __ballot_sync(0xffffffffu, wide && hl == 0);
+    while (wmask) {
+      const int src = __ffs(wmask) - 1;  // lane 0 or 16: leader of the group that owns the term
+      wmask &= wmask - 1;
+      GroupIn w;
+      w.inst = __shfl_sync(0xffffffffu, g.inst, src);
+      w.tlen = __shfl_sync(0xffffffffu, g.tlen, src);
+      w.c = __shfl_sync(0xffffffffu, g.c, src);
+      w.L = __shfl_sync(0xffffffffu, g.L, src);
+      w.pst = __shfl_sync(0xffffffffu, g.pst, src);
+      w.eslot = __shfl_sync(0xffffffffu, g.eslot, src);
+      const uint32_t rw = p0 + (src >> 4);
+      uint32_t* const slot = gath + w.pst;
+      uint32_t* const buf = s_buf[warp];
+      uint32_t* const ebuf = s_enc[warp];
+      const uint32_t outn = union_blocked<32>(slot, buf, w.L, w.c > 1, a.rem);
+      if (a.want_dec)
+        for (uint32_t e = lane; e < outn; e += 32) slot[e] = buf[e];
+      uint32_t enc = 0;
+      uint32_t* const enc_dst = enc_base + w.eslot;
+      if (a.want_enc && outn) {
+        enc = encode_shared_warp(buf, outn, ebuf);
+        for (uint32_t e = lane; e < enc; e += 32) enc_dst[e] = ebuf[e];
+      }
+      if (lane == 0) {
+        GroupRec rec;
+        rec.inst = w.inst;
+        rec.tlen = w.tlen;
+        rec.dec = reinterpret_cast<uint64_t>(slot);
+        rec.eoff = a.want_enc ? reinterpret_cast<uint64_t>(enc_dst) : 0ull;
+        rec.cnt = outn;
+        rec.enc = enc;
+        a.recs[rec_base + rw] = rec;
+        if (outn || a.keep_empty) {
+          acc_t += 1;
+          acc_tb += w.tlen;
+          acc_p += outn;
+          acc_e += enc;
+        }
+      }
+      __syncwarp();
     }
   }
-  if (lane == 0 && acc_t) {
+  if (hl == 0 && acc_t) {
     unsigned long long* bo = reinterpret_cast<unsigned long long*>(a.bk_raw);
     atomicAdd(&bo[0ull * a.nb1 + b], (unsigned long long)acc_t);
     atomicAdd(&bo[1ull * a.nb1 + b], (unsigned long long)acc_tb);
@@ -999,7 +1143,8 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   // bases are the plan's upper-bound prefix, so nothing has to be read back before K2b
   const uint64_t enc_cap = n_in + n_in / 4 + 6ull * N + 64;
   if (want_enc) II2_TRY(u.tmp_enc.alloc_scratch(enc_cap, s));
-  if (want_dec) II2_TRY(u.tmp_post.alloc_scratch(n_in, s));
+  // gather slots of the light terms (K1b -> K2b); the decoded union replaces them in place
+  II2_TRY(u.tmp_post.alloc_scratch(n_in, s, 16));
   const uint32_t large_cap = (uint32_t)std::min<uint64_t>(N, n_in / REG_CAP + 1);
   DevBuf<uint32_t> large_u32;
   II2_TRY(large_u32.alloc_scratch(2 * (size_t)large_cap, s));
@@ -1012,7 +1157,9 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   a1.part = plan.part.p;
   a1.bk_pos = plan.bk_pos();
   a1.bk_cpl = plan.bk_cpl.p;
+  a1.bk_P = plan.bk_P();
   a1.gin = gin.p;
+  a1.gath = u.tmp_post.p;
   a1.src_ptr = src_ptr.p;
   a1.src_len = src_len.p;
   a1.bk_D = u.bk_D.p;
@@ -1022,14 +1169,12 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   a2.bk_E = plan.bk_E();
   a2.bk_D = u.bk_D.p;
   a2.gin = gin.p;
-  a2.src_ptr = src_ptr.p;
-  a2.src_len = src_len.p;
   a2.rem = rem;
   a2.want_enc = want_enc ? 1 : 0;
   a2.want_dec = want_dec ? 1 : 0;
   a2.keep_empty = keep_empty ? 1 : 0;
   a2.recs = u.recs.p;
-  a2.tmp_post = u.tmp_post.p;
+  a2.gath = u.tmp_post.p;
   a2.tmp_enc = u.tmp_enc.p;
   a2.bk_raw = u.bk_raw.p;
   a2.nb1 = B + 1;
@@ -1043,30 +1188,18 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
                                       (int)k1b_smem_bytes(kMaxSegs)));
     attr = k1b_smem_bytes(kMaxSegs);
   }
+  // (running the two kernels chunk-wise on two streams was measured slower on B200 than back
+  // to back: 3.27 vs 2.94 ms)
+  a1.bucket0 = a2.bucket0 = 0;
   {
-    // K1b is barrier/latency bound, K2b issue bound: chunks of buckets flow through the two
-    // kernels on two streams so the grouping of chunk c+1 overlaps the union of chunk c
-    ProfScope scope("k12_group_union", s);
-    const uint32_t n_chunks = 1;  // measured on B200: overlapping the two kernels over 8 chunks is slower (3.27 vs 2.94 ms)
-    cudaStream_t s2 = n_chunks > 1 ? aux_stream() : s;
-    for (uint32_t c = 0; c < n_chunks; c++) {
-      const uint32_t b0 = (uint32_t)((uint64_t)B * c / n_chunks);
-      const uint32_t b1 = (uint32_t)((uint64_t)B * (c + 1) / n_chunks);
-      if (b1 == b0) continue;
-      a1.bucket0 = a2.bucket0 = b0;
-      k1b_group_kernel<<<b1 - b0, K1B_THREADS, smem, s>>>(a1);
-      II2_LAUNCHED();
-      if (n_chunks > 1) {
-        II2_CUDA_TRY(cudaEventRecord(aux_event((int)c), s));
-        II2_CUDA_TRY(cudaStreamWaitEvent(s2, aux_event((int)c), 0));
-      }
-      k2b_union_kernel<<<b1 - b0, K2B_THREADS, 0, s2>>>(a2);
-      II2_LAUNCHED();
-    }
-    if (n_chunks > 1) {
-      II2_CUDA_TRY(cudaEventRecord(aux_event(15), s2));
-      II2_CUDA_TRY(cudaStreamWaitEvent(s, aux_event(15), 0));
-    }
+    ProfScope scope("k1b_group", s);
+    k1b_group_kernel<<<B, K1B_THREADS, smem, s>>>(a1);
+    II2_LAUNCHED();
+  }
+  {
+    ProfScope scope("k2b_union", s);
+    k2b_union_kernel<<<B, K2B_THREADS, 0, s>>>(a2);
+    II2_LAUNCHED();
   }
   k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
   II2_LAUNCHED();

@@ -7,6 +7,8 @@
 // bucket walks the bucket's records in chunks of 256, a block scan over the surviving terms
 // gives every term its output slots (bucket bases come from the bucket-level scan), then warps
 // copy term bytes, encoded words and/or decoded postings.  Pure HBM copy work.
+#include <algorithm>
+
 #include "keys.cuh"
 #include "union.cuh"
 
@@ -46,16 +48,35 @@ struct K6Work {
   uint32_t enc;
 };
 
-__global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
+constexpr uint32_t K6_MAX_GROUP = 32;  // buckets per CTA
+
+// One CTA places the records of `group` consecutive buckets: their records, bucket after
+// bucket, form one flat sequence (buckets are in merged order and bk_out is the exclusive
+// prefix over buckets, so the running output positions simply continue across the buckets of
+// the group).  About 256 records per CTA: one set of block scans per 256 terms.
+__global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a, uint32_t group,
+                                                             uint32_t n_buckets) {
   __shared__ K6Work s_work[K6_THREADS];
   __shared__ uint64_t s_ws64[K6_WARPS + 2];
-  const uint32_t tid = threadIdx.x, b = blockIdx.x;
-  const uint32_t nrec = a.bk_D[b];
-  const GroupRec* recs = a.recs + a.bk_pos[b];
-  uint64_t run_t = a.bk_out[0ull * a.nb1 + b];
-  uint64_t run_tb = a.bk_out[1ull * a.nb1 + b];
-  uint64_t run_p = a.bk_out[2ull * a.nb1 + b];
-  uint64_t run_e = a.bk_out[3ull * a.nb1 + b];
+  __shared__ uint32_t s_pref[K6_MAX_GROUP + 1];
+  __shared__ uint64_t s_base[K6_MAX_GROUP];
+  const uint32_t tid = threadIdx.x, b0 = blockIdx.x * group;
+  const uint32_t nb = min(group, n_buckets - b0);
+  if (tid < 32) {
+    const uint32_t d = tid < nb ? a.bk_D[b0 + tid] : 0u;
+    const uint32_t inc = warp_inclusive_scan(d);
+    if (tid < nb) {
+      s_pref[tid + 1] = inc;
+      s_base[tid] = a.bk_pos[b0 + tid];
+    }
+    if (tid == 0) s_pref[0] = 0;
+  }
+  __syncthreads();
+  const uint32_t nrec = s_pref[nb];
+  uint64_t run_t = a.bk_out[0ull * a.nb1 + b0];
+  uint64_t run_tb = a.bk_out[1ull * a.nb1 + b0];
+  uint64_t run_p = a.bk_out[2ull * a.nb1 + b0];
+  uint64_t run_e = a.bk_out[3ull * a.nb1 + b0];
   for (uint32_t q = 0; q < nrec; q += K6_THREADS) {
     const uint32_t r = q + tid;
     GroupRec g;
@@ -64,18 +85,20 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
     g.tlen = 0;
     uint32_t surv = 0;
     if (r < nrec) {
-      g = recs[r];
+      uint32_t j = 0;  // bucket of flat record r
+      while (s_pref[j + 1] <= r) j++;
+      g = a.recs[s_base[j] + (r - s_pref[j])];
       surv = (g.cnt != K6_PENDING && (g.cnt || a.keep_empty)) ? 1u : 0u;
     }
     const uint32_t tl = surv ? g.tlen : 0u;
     const uint32_t cnt = surv ? g.cnt : 0u;
     const uint32_t enc = surv ? g.enc : 0u;
     // (terms, term bytes) share one scan; postings and words can be large, one each
-    uint64_t tot_a, tot_p, tot_e;
+    uint64_t tot_a, tot_p = 0, tot_e = 0;
     const uint64_t ex_a = block_exclusive_scan<uint64_t>((uint64_t)surv | ((uint64_t)tl << 32),
                                                          s_ws64, tot_a);
-    const uint64_t ex_p = block_exclusive_scan<uint64_t>(cnt, s_ws64, tot_p);
-    const uint64_t ex_e = block_exclusive_scan<uint64_t>(enc, s_ws64, tot_e);
+    const uint64_t ex_p = a.want_dec ? block_exclusive_scan<uint64_t>(cnt, s_ws64, tot_p) : 0ull;
+    const uint64_t ex_e = a.want_enc ? block_exclusive_scan<uint64_t>(enc, s_ws64, tot_e) : 0ull;
     const uint32_t n_surv = (uint32_t)tot_a;
     if (surv) {
       const uint64_t t = run_t + (uint32_t)ex_a;
@@ -113,8 +136,8 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a) {
     run_e += tot_e;
     __syncthreads();
   }
-  // terminal offsets, written once by the last bucket
-  if (b == gridDim.x - 1 && tid == 0) {
+  // terminal offsets, written once by the CTA of the last bucket
+  if (b0 + nb == n_buckets && tid == 0) {
     a.o_term_off[run_t] = (uint32_t)run_tb;
     if (a.want_dec) a.o_post_off[run_t] = run_p;
   }
@@ -155,7 +178,11 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   a.o_val_words = out.val_words.p;
   a.o_val_off = out.val_off.p;
   ProfScope scope("k6_emit", s);
-  k6_emit_kernel<<<plan.n_buckets, K6_THREADS, 0, s>>>(a);
+  // buckets per CTA: about one CTA-width of records
+  const uint64_t tm = u.terms_merged ? u.terms_merged : 1;
+  const uint32_t group = (uint32_t)std::min<uint64_t>(
+      K6_MAX_GROUP, std::max<uint64_t>(1, (uint64_t)K6_THREADS * plan.n_buckets / tm));
+  k6_emit_kernel<<<div_up(plan.n_buckets, group), K6_THREADS, 0, s>>>(a, group, plan.n_buckets);
   II2_LAUNCHED();
   return II2_OK;
 }

@@ -17,7 +17,7 @@ struct GroupRec {
 
 struct UnionOut {
   DevBuf<GroupRec> recs;       // [N_T]
-  DevBuf<uint32_t> tmp_post;   // [N_in] decoded union results (only if decoded output is wanted)
+  DevBuf<uint32_t> tmp_post;   // [N_in] gather slots of the light terms, replaced by their unions
   DevBuf<uint32_t> tmp_enc;    // encoded streams, one upper-bound slot per light term
   DevBuf<uint32_t> large_enc;  // the same for heavy terms
   DevBuf<uint32_t> large_tmp;  // sort space of the multi-CTA path for heavy terms

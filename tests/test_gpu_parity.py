@@ -202,6 +202,45 @@ def test_heavy_terms_multi_cta_union(engine, orc):
                        orc.merge(segs, removed, decoded=True))
 
 
+def test_union_width_boundaries(engine, orc):
+    """Union kernel paths: two terms per warp (< 128 values), one term per warp (128..256),
+    multi-CTA (> 256); single-source terms (unsorted, duplicates kept: Q4) paired with
+    multi-source ones in the same warp; values needing 5 var-byte bytes and negative deltas."""
+    rng = np.random.default_rng(21)
+    lens = [0, 1, 2, 7, 8, 9, 15, 16, 17, 63, 64, 65, 120, 126, 127, 128, 129, 130, 200, 255, 256,
+            257, 300, 511, 512, 513]
+    items = [[], [], []]
+    for i, L in enumerate(lens):
+        for mode in range(4):
+            term = b"t%03d_%d" % (i, mode)
+            if mode == 0:    # three sources that share values: union shrinks
+                pool = rng.integers(0, max(4, 2 * L), size=L).astype(np.uint32)
+                cut = sorted(rng.integers(0, L + 1, size=2).tolist())
+                parts = [pool[:cut[0]], pool[cut[0]:cut[1]], pool[cut[1]:]]
+                for s in range(3):
+                    items[s].append((term, np.unique(parts[s]).tolist()))
+            elif mode == 1:  # single source, unsorted with duplicates, huge values
+                vals = rng.integers(0, 1 << 32, size=L, dtype=np.uint64).astype(np.uint32)
+                if L > 2:
+                    vals[1] = vals[0]
+                items[i % 3].append((term, vals.tolist()))
+            elif mode == 2:  # two sources, exactly L distinct values in total (nothing merges)
+                vals = rng.choice(1 << 30, size=L, replace=False).astype(np.uint32) * np.uint32(4)
+                items[0].append((term, np.sort(vals[: L // 2]).tolist()))
+                items[1].append((term, np.sort(vals[L // 2:]).tolist()))
+            else:            # same list in every segment
+                vals = np.unique(rng.integers(0, 1 << 20, size=L)).tolist()
+                for s in range(3):
+                    items[s].append((term, vals))
+    segs = [FlatSegment.from_items(sorted(it)) for it in items]
+    for removed in (None, np.unique(rng.integers(0, 1 << 12, size=600)).astype(np.uint32),
+                    np.array([1, 5, 4000000000], dtype=np.uint32)):   # last: no bitmap (sparse)
+        exp = orc.merge(segs, removed, decoded=True)
+        got = engine.merge(segs, removed, decoded=True)
+        assert_merge_equal(got, exp)
+        assert_read_equal(engine.read_range(segs), orc.read_range(segs))
+
+
 # ---------------------------------------------------------------- range reads vs oracle
 def test_read_range_matches_oracle(engine, orc):
     w = synth.make_workload(20000, 12, 300000, universe=1 << 16, seed=21)
