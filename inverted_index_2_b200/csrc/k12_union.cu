@@ -20,6 +20,7 @@
 // Terms whose lists exceed 256 values go to the multi-CTA global-memory path at the end of
 // this file.  Integer/byte work, HBM-bound by design.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "intcomp.cuh"
@@ -34,13 +35,13 @@ constexpr uint32_t CAP_I = 1024;   // instances per sub-tile
 constexpr uint32_t K1B_HT = 2048;  // hash slots
 constexpr uint32_t REG_CAP = 256;  // values a warp sorts in registers
 constexpr uint32_t K1B_SMALL_D = 64;  // distinct terms ranked by counting instead of sorting
-constexpr uint16_t K1B_EMPTY = 0xFFFFu;
+constexpr uint32_t K1B_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t K12_PENDING = 0xFFFFFFFFu;
 constexpr uint32_t K1B_HEAVY = 0xFFFFFFFFu;   // pbase of a heavy term
 
 // What K1b knows about a distinct term, in merged order inside its bucket (index = bucket base
 // bk_pos[b] + rank, like GroupRec).
-struct GroupIn {
+struct __align__(16) GroupIn {
   uint32_t inst;   // global instance id of one source (names the term bytes)
   uint32_t tlen;   // term length
   uint32_t src;    // first source in src_ptr / src_len (filled for heavy terms only)
@@ -73,13 +74,16 @@ struct K1bArgs {
 // Order of two terms whose bytes before `skip` are equal and which both run past `skip`:
 // further 16-byte windows until one differs or a term ends.  Kept out of line: the compiler
 // must not hoist its offset loads into the callers' fast path.
-__device__ __noinline__ int k1b_tail_compare(const SegDesc* __restrict__ segs, uint32_t sx,
-                                             uint32_t ix, uint32_t nx, uint32_t sy, uint32_t iy,
-                                             uint32_t ny, uint32_t skip) {
+__device__ __noinline__ int k1b_tail_compare(const SegDesc* __restrict__ segs, int k, uint32_t ix,
+                                             uint32_t nx, uint32_t iy, uint32_t ny, uint32_t skip) {
+  int sx, sy;
+  uint32_t tx, ty;
+  locate_instance(segs, k, ix, sx, tx);
+  locate_instance(segs, k, iy, sy, ty);
   const SegDesc& dx = segs[sx];
   const SegDesc& dy = segs[sy];
-  const uint32_t ox = __ldg(dx.toff + (dx.lo + (ix - dx.base)));
-  const uint32_t oy = __ldg(dy.toff + (dy.lo + (iy - dy.base)));
+  const uint32_t ox = __ldg(dx.toff + tx);
+  const uint32_t oy = __ldg(dy.toff + ty);
   for (uint32_t c = skip;; c += 16) {
     uint64_t hx, lx, hy, ly;
     load_key16(dx.tb, ox, nx, c, hx, lx);
@@ -92,14 +96,17 @@ __device__ __noinline__ int k1b_tail_compare(const SegDesc* __restrict__ segs, u
 }
 
 __host__ __device__ inline size_t k1b_smem_bytes(int k) {
-  return (size_t)CAP_I * 16                      // key_hi, key_lo
-         + (size_t)CAP_I * 4 * 4                 // inst, cnt, gl, pbase
-         + (size_t)(5 * k + 1) * 4               // cur, mm, hi, endr, rstart
-         + (size_t)CAP_I * 2 * 4                 // seg, tlen, grp, reps
-         + (size_t)K1B_HT * 2 + 64;
+  return (size_t)CAP_I * 24                      // key_hi, key_lo, key_x
+         + (size_t)CAP_I * 4 * 3                 // inst, count|length, pbase
+         + (size_t)(4 * k) * 4 + (size_t)(2 * k + 2) * 4   // cur, mm, hi, endr; rstart (padded to 2^n + 1)
+         + (size_t)CAP_I * 2 * 2                 // tlen, reps
+         + (size_t)K1B_HT * 4 + 64;
 }
 
-__global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs a) {
+#ifndef K1B_MIN_CTAS
+#define K1B_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(const K1bArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t s_ws64[K1B_WARPS + 2];
   __shared__ uint32_t s_ws32[K1B_WARPS + 2];
@@ -109,24 +116,27 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
   uint8_t* sp = smem_raw;
   uint64_t* key_hi = reinterpret_cast<uint64_t*>(sp); sp += CAP_I * 8;
   uint64_t* key_lo = reinterpret_cast<uint64_t*>(sp); sp += CAP_I * 8;
-  // by representative: sources / Σ source lengths (each saturated at REG_CAP + 1)
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
-  uint32_t* gl = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
+  uint64_t* key_x = reinterpret_cast<uint64_t*>(sp); sp += CAP_I * 8;  // bytes 16..23 of the window
+  // by representative: sources << 20 | Σ source lengths (each saturated at REG_CAP + 1, so the
+  // sum stays below 2^19 for the <= 1024 instances of a tile)
+  uint32_t* cg = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
   uint32_t* inst_a = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;  // global instance id
   // by representative: slot of the term in the bucket's gather region, or K1B_HEAVY
   uint32_t* pbase = reinterpret_cast<uint32_t*>(sp); sp += CAP_I * 4;
-  uint16_t* seg_a = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
   uint16_t* tlen = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
-  uint16_t* grp = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
   uint16_t* reps = reinterpret_cast<uint16_t*>(sp); sp += CAP_I * 2;
-  uint16_t* table = reinterpret_cast<uint16_t*>(sp); sp += K1B_HT * 2;  // 16-byte aligned
+  sp += (16 - (reinterpret_cast<uintptr_t>(sp) & 15)) & 15;
+  uint32_t* table = reinterpret_cast<uint32_t*>(sp); sp += K1B_HT * 4;  // 16-byte aligned
   uint32_t* cur = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* mm = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* hib = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   uint32_t* endr = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
-  uint32_t* rstart = reinterpret_cast<uint32_t*>(sp); sp += (k + 1) * 4;
-  // alias, valid once the hash table is done (K1B_HT u16 slots = CAP_I u32 words)
-  uint32_t* sbase = reinterpret_cast<uint32_t*>(table);  // by representative: first source slot
+  // run starts inside the tile, padded with `size` up to kp2 = the power of two >= k
+  uint32_t* rstart = reinterpret_cast<uint32_t*>(sp);
+  // alias, valid once the hash table is done: first source slot by representative
+  uint32_t* sbase = table;
+  uint32_t kp2 = 1;
+  while (kp2 < (uint32_t)k) kp2 <<= 1;
 
   const uint32_t tid = threadIdx.x;
   const unsigned lane = lane_id(), warp = warp_id();
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         if (s < k) rstart[s] = ex;
         ex += v[j];
       }
-      if (lane == 0) rstart[k] = size;
+      for (uint32_t s2 = k + lane; s2 <= kp2; s2 += 32) rstart[s2] = size;
     } else {
       uint32_t run = 0;
       for (int base = 0; base < k; base += K1B_THREADS) {
@@ -225,22 +235,22 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         if (s < k) rstart[s] = run + ex;
         run += tot;
       }
-      if (tid == 0) rstart[k] = size;
+      for (uint32_t s2 = k + tid; s2 <= kp2; s2 += K1B_THREADS) rstart[s2] = size;
     }
-    static_assert(K1B_HT * 2 == K1B_THREADS * 16, "one 16-byte store per thread resets the table");
+    static_assert(K1B_HT * 4 == K1B_THREADS * 32, "two 16-byte stores per thread reset the table");
     reinterpret_cast<uint4*>(table)[tid] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    // cnt and gl are adjacent: 2 * CAP_I words, zeroed four at a time
-    for (uint32_t i = 4 * tid; i < 2 * CAP_I; i += 4 * K1B_THREADS)
-      *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(table)[tid + K1B_THREADS] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (uint32_t i = 4 * tid; i < CAP_I; i += 4 * K1B_THREADS)
+      *reinterpret_cast<uint4*>(cg + i) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_nreps = 0;
     __syncthreads();
 
-    // bytes past the 16-byte window, only needed for terms longer than cpl+16
+    // bytes past the 24-byte window, only needed for terms longer than cpl+24
     auto tail_compare = [&](uint32_t x, uint32_t y) -> int {
-      const uint32_t skip = cpl + 16;
+      const uint32_t skip = cpl + 24;
       const uint32_t nx = tlen[x], ny = tlen[y];
       if (nx > skip && ny > skip)
-        return k1b_tail_compare(a.segs, seg_a[x], inst_a[x], nx, seg_a[y], inst_a[y], ny, skip);
+        return k1b_tail_compare(a.segs, k, inst_a[x], nx, inst_a[y], ny, skip);
       return nx < ny ? -1 : (nx > ny ? 1 : 0);
     };
     auto less = [&](uint16_t x, uint16_t y) -> bool {
@@ -248,6 +258,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       if (hx != hy) return hx < hy;
       const uint64_t lx = key_lo[x], ly = key_lo[y];
       if (lx != ly) return lx < ly;
+      const uint64_t xx = key_x[x], xy = key_x[y];
+      if (xx != xy) return xx < xy;
       return tail_compare(x, y) < 0;
     };
 
@@ -256,6 +268,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     uint64_t pp[PER];   // first posting of the thread's instances
     uint32_t pl[PER];   // their lengths
     uint32_t ofs[PER];  // where they go inside their term's gather slot
+    uint32_t grp[PER];  // their term's representative
     {
       int sg[PER];
       uint32_t ix[PER], to[PER], tn[PER];
@@ -265,15 +278,21 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         const uint32_t i = tid + j * K1B_THREADS;
         sg[j] = -1;
         if (i < size) {
-          int lo = 0, hi = k;  // first s with rstart[s+1] > i
+#ifdef K1B_SEARCH_BRANCHY
+          uint32_t lo = 0, hi = k;  // first s with rstart[s+1] > i
           while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
+            const uint32_t mid = (lo + hi) >> 1;
             if (rstart[mid + 1] <= i)
               lo = mid + 1;
             else
               hi = mid;
           }
-          sg[j] = lo;
+#else
+          uint32_t lo = 0;  // last s with rstart[s] <= i: the run that holds instance i
+          for (uint32_t step = kp2 >> 1; step > 0; step >>= 1)
+            if (rstart[lo + step] <= i) lo += step;
+#endif
+          sg[j] = (int)lo;
           ix[j] = cur[lo] + (i - rstart[lo]);
         }
       }
@@ -296,10 +315,10 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
           load_key16(a.segs[sg[j]].tb, to[j], n, cpl, kh, kl);
           key_hi[i] = kh;
           key_lo[i] = kl;
+          key_x[i] = load_key_x(a.segs[sg[j]].tb, to[j], n, cpl);
           tlen[i] = (uint16_t)n;
           const SegDesc& sd = a.segs[sg[j]];
           inst_a[i] = sd.base + (ix[j] - sd.lo);
-          seg_a[i] = (uint16_t)sg[j];
           pl[j] = (p1[j] - pp[j]) > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)(p1[j] - pp[j]);
           pp[j] = reinterpret_cast<uint64_t>(sd.post + pp[j]);
         }
@@ -315,6 +334,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       const uint32_t i = tid + j * K1B_THREADS;
       if (i >= size) break;
       const uint64_t kh = key_hi[i], kl = key_lo[i];
+#ifdef K1B_HASH64
       uint64_t h = kh * 0x9E3779B97F4A7C15ull;
       h ^= (kl + 0xD6E8FEB86659FD93ull + (h << 6) + (h >> 2));
       h *= 0xFF51AFD7ED558CCDull;
@@ -322,28 +342,34 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
       h += tlen[i] * 0xC2B2AE3D27D4EB4Full;
       h ^= h >> 29;
       uint32_t slot = (uint32_t)h & (K1B_HT - 1);
+#else
+      // four 32-bit multiplies folded together; the top bits pick the slot
+      uint32_t h = (uint32_t)kh * 0x9E3779B1u ^ (uint32_t)(kh >> 32) * 0x85EBCA77u ^
+                   (uint32_t)kl * 0xC2B2AE3Du ^ (uint32_t)(kl >> 32) * 0x27D4EB2Fu;
+      h = (h ^ (h >> 15)) * 0x2C1B3C6Du + tlen[i];
+      uint32_t slot = (h ^ (h >> 13)) & (K1B_HT - 1);
+#endif
       uint32_t rep;
       for (;;) {
-        const unsigned short prev = atomicCAS(reinterpret_cast<unsigned short*>(&table[slot]),
-                                              (unsigned short)K1B_EMPTY, (unsigned short)i);
+        const uint32_t prev = atomicCAS(&table[slot], K1B_EMPTY, i);
         if (prev == K1B_EMPTY) {
           rep = i;
           reps[atomicAdd(&s_nreps, 1u)] = (uint16_t)i;
           break;
         }
         if (*(volatile uint64_t*)&key_hi[prev] == kh && *(volatile uint64_t*)&key_lo[prev] == kl &&
-            *(volatile uint16_t*)&tlen[prev] == tlen[i] && tail_compare(i, prev) == 0) {
+            *(volatile uint16_t*)&tlen[prev] == tlen[i] &&
+            *(volatile uint64_t*)&key_x[prev] == key_x[i] && tail_compare(i, prev) == 0) {
           rep = prev;
           break;
         }
         slot = (slot + 1) & (K1B_HT - 1);
       }
-      grp[i] = (uint16_t)rep;
-      atomicAdd(&cnt[rep], 1u);
+      grp[j] = rep;
       // Σ source lengths, saturating per source so the sum cannot wrap: heavy iff sum > REG_CAP.
       // For a light term every addend is exact, so the value before the add is where this
       // source starts inside the term's gather slot.
-      ofs[j] = atomicAdd(&gl[rep], pl[j] > REG_CAP ? REG_CAP + 1 : pl[j]);
+      ofs[j] = atomicAdd(&cg[rep], (1u << 20) | (pl[j] > REG_CAP ? REG_CAP + 1 : pl[j])) & 0xFFFFFu;
     }
     __syncthreads();
     const uint32_t D = s_nreps;
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
 #pragma unroll 1
       for (uint32_t t = warp; t < D; t += K1B_WARPS) {
         const uint32_t me = reps[t];
-        uint32_t rank = 0, ib = 0, pst = 0, est = 0;  // smaller terms: count / instances / postings / staging words
+        uint32_t rank = 0, ib = 0, pst = 0, est = 0;
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < D; j0 += 32) {
           const uint32_t j = j0 + lane;
@@ -363,8 +389,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
             const uint32_t o = reps[j];
             lt = o != me && less((uint16_t)o, (uint16_t)me);
             if (lt) {
-              const uint32_t len = gl[o];
-              m_i = cnt[o];
+              const uint32_t len = cg[o] & 0xFFFFFu;
+              m_i = cg[o] >> 20;
               if (len <= REG_CAP) {
                 m_p = len;
                 m_e = enc_slot_words(len);
@@ -377,20 +403,14 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
           est += __reduce_add_sync(0xffffffffu, m_e);
         }
         if (lane == 0) {
-          const uint32_t len = gl[me];
+          const uint32_t len = cg[me] & 0xFFFFFu;
           const bool light = len <= REG_CAP;
-          GroupIn g;
-          g.inst = inst_a[me];
-          g.tlen = tlen[me];
-          g.src = (uint32_t)rec_base + icount + ib;
-          g.c = cnt[me];
-          g.L = len;
-          g.pst = pcount + pst;
-          g.eslot = ecount + est;
-          g.pad = 0;
-          a.gin[rec_base + dcount + rank] = g;
-          sbase[me] = g.src;
-          pbase[me] = light ? g.pst : K1B_HEAVY;
+          const uint32_t src = (uint32_t)rec_base + icount + ib;
+          uint4* rec = reinterpret_cast<uint4*>(a.gin + rec_base + dcount + rank);
+          rec[0] = make_uint4(inst_a[me], tlen[me], src, cg[me] >> 20);
+          rec[1] = make_uint4(len, pcount + pst, ecount + est, 0u);
+          sbase[me] = src;
+          pbase[me] = light ? pcount + pst : K1B_HEAVY;
           if (rank == D - 1) {
             s_tot[0] = pst + (light ? len : 0u);
             s_tot[1] = est + (light ? enc_slot_words(len) : 0u);
@@ -407,8 +427,8 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
         uint32_t len = 0;
         if (r < D) {
           me = reps[r];
-          ci = cnt[me];
-          len = gl[me];
+          ci = cg[me] >> 20;
+          len = cg[me] & 0xFFFFFu;
           if (len <= REG_CAP) {
             li = len;
             ei = enc_slot_words(li);
@@ -450,7 +470,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
     for (int j = 0; j < PER; j++) {
       const uint32_t i = tid + j * K1B_THREADS;
       if (i < size) {
-        const uint32_t g = grp[i];
+        const uint32_t g = grp[j];
         const uint32_t pb = pbase[g];
         if (pb != K1B_HEAVY) {
           const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(pp[j]);
@@ -475,7 +495,7 @@ __global__ void __launch_bounds__(K1B_THREADS, 4) k1b_group_kernel(const K1bArgs
             if (t + 2 < n) dst[t + 2] = x2;
           }
         } else {
-          const uint32_t at = sbase[g] + (atomicSub(&cnt[g], 1u) - 1u);
+          const uint32_t at = sbase[g] + ((atomicSub(&cg[g], 1u << 20) >> 20) - 1u);
           a.src_ptr[at] = pp[j];
           a.src_len[at] = pl[j];
         }
@@ -664,7 +684,9 @@ __device__ __forceinline__ uint32_t encode_small_blocked(const uint32_t* v, uint
     if (hl >= (unsigned)d) inc += o;
   }
   const uint32_t total = __shfl_sync(0xffffffffu, inc, W - 1, W);
-  uint8_t* sb = reinterpret_cast<uint8_t*>(out + 1) + (inc - bytes);
+  // byte stores predicated in PTX: the compiler would chain branches (len > 1 implies
+  // len > 0 ...), five of them per value
+  uint32_t sb = (uint32_t)__cvta_generic_to_shared(out + 1) + (inc - bytes);
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const uint32_t zz = z[r];
@@ -672,12 +694,30 @@ __device__ __forceinline__ uint32_t encode_small_blocked(const uint32_t* v, uint
     // the low four 7-bit groups spread over four bytes, terminator bit on the last byte
     uint32_t w = (zz & 0x7Fu) | ((zz << 1) & 0x7F00u) | ((zz << 2) & 0x7F0000u) |
                  ((zz << 3) & 0x7F000000u);
-    if (len <= 4) w |= 0x80u << ((8 * len - 8) & 31u);  // len 0 stores nothing
-    if (len > 0) sb[0] = (uint8_t)w;
-    if (len > 1) sb[1] = (uint8_t)(w >> 8);
-    if (len > 2) sb[2] = (uint8_t)(w >> 16);
-    if (len > 3) sb[3] = (uint8_t)(w >> 24);
-    if (len > 4) sb[4] = (uint8_t)((zz >> 28) | 0x80u);
+    const uint32_t term = 0x80u << ((8 * len - 8) & 31u);
+    w |= len <= 4 ? term : 0u;  // (len 0 stores nothing)
+    const uint32_t b4 = (zz >> 28) | 0x80u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p1, p2, p3, p4;\n\t"
+        ".reg .b32 t1, t2, t3;\n\t"
+        "setp.gt.u32 p0, %1, 0;\n\t"
+        "setp.gt.u32 p1, %1, 1;\n\t"
+        "setp.gt.u32 p2, %1, 2;\n\t"
+        "setp.gt.u32 p3, %1, 3;\n\t"
+        "setp.gt.u32 p4, %1, 4;\n\t"
+        "shr.u32 t1, %2, 8;\n\t"
+        "shr.u32 t2, %2, 16;\n\t"
+        "shr.u32 t3, %2, 24;\n\t"
+        "@p0 st.shared.u8 [%0], %2;\n\t"
+        "@p1 st.shared.u8 [%0+1], t1;\n\t"
+        "@p2 st.shared.u8 [%0+2], t2;\n\t"
+        "@p3 st.shared.u8 [%0+3], t3;\n\t"
+        "@p4 st.shared.u8 [%0+4], %3;\n\t"
+        "}"
+        :
+        : "r"(sb), "r"(len), "r"(w), "r"(b4)
+        : "memory");
     sb += len;
   }
   if (n) {
@@ -807,13 +847,20 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
   uint32_t* const enc_base = a.tmp_enc + a.bk_E[b];
   uint32_t acc_t = 0, acc_tb = 0, acc_e = 0;  // per group leader (hl == 0) and warp leader
   uint64_t acc_p = 0;
+  const GroupIn g_none = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  GroupIn g_next = g_none;
+  if (2 * warp + half < D) g_next = a.gin[rec_base + 2 * warp + half];
 #pragma unroll 1
   for (uint32_t p0 = 2 * warp; p0 < D; p0 += 2 * K2B_WARPS) {
     // ---- the pair of terms of this warp: one per 16-lane group ----
     const uint32_t r = p0 + half;
     const bool has = r < D;
-    GroupIn g = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (has) g = a.gin[rec_base + r];
+    const GroupIn g = g_next;
+    {  // the record of the next round: in flight while this one is processed
+      const uint32_t rn = r + 2 * K2B_WARPS;
+      g_next = g_none;
+      if (rn < D) g_next = a.gin[rec_base + rn];
+    }
     const bool heavy = has && g.L > REG_CAP;
     const bool wide = has && !heavy && g.L >= K2B_HALF;
     if (heavy && hl == 0) {  // the multi-CTA path works from the source list
@@ -1181,12 +1228,18 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   a2.n_large = reinterpret_cast<uint32_t*>(u.totals.p + 6);
   a2.large_rec = large_u32.p;
   a2.large_bucket = large_u32.p + large_cap;
-  const size_t smem = k1b_smem_bytes(k);
+  // II2_K1B_PAD=<bytes>: occupancy experiments (extra dynamic shared memory per CTA)
+  static const size_t pad = [] {
+    const char* e = getenv("II2_K1B_PAD");
+    return e ? (size_t)atol(e) : (size_t)0;
+  }();
+  const size_t smem = k1b_smem_bytes(k) + pad;
   static size_t attr = 0;
   if (smem > attr) {
+    const size_t want = std::max(k1b_smem_bytes(kMaxSegs), smem);
     II2_CUDA_TRY(cudaFuncSetAttribute(k1b_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)k1b_smem_bytes(kMaxSegs)));
-    attr = k1b_smem_bytes(kMaxSegs);
+                                      (int)want));
+    attr = want;
   }
   // (running the two kernels chunk-wise on two streams was measured slower on B200 than back
   // to back: 3.27 vs 2.94 ms)
