@@ -2,6 +2,7 @@
 // resident segments / removed sets / results, the device pipelines, and the host-buffer
 // convenience calls that stage through them.
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -43,6 +44,7 @@ struct ii2_result {
   uint64_t postings_in = 0, terms_merged = 0;
   bool has_dec = false, has_enc = false;
   bool has_minmax = false;
+  bool rebased = false;  // offsets already carry the base of a pipelined download
   std::string min_term, max_term;
 };
 
@@ -71,6 +73,93 @@ k_seg_check(const uint32_t* __restrict__ toff, uint32_t n, const uint64_t* __res
   if (b < a) atomicExch(&stats[1], 1u);
   else atomicMax(&stats[0], b - a);
   if (poff && poff[i + 1] < poff[i]) atomicExch(&stats[1], 1u);
+}
+
+// offsets of a slice of a larger segment: subtract the first one
+__global__ void __launch_bounds__(256)
+k_rebase_u32(uint32_t* __restrict__ off, uint64_t n, uint32_t first) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] -= first;
+}
+__global__ void __launch_bounds__(256)
+k_rebase_u64(uint64_t* __restrict__ off, uint64_t n, uint64_t first) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] -= first;
+}
+
+// Slices of many segments staged into shared blocks by one range of the pipelined ii2_merge:
+// the k_seg_check tests for all of them in one launch (grid.y = slice).
+struct SliceRef {
+  const uint32_t* toff;  // [n + 1]
+  const uint64_t* poff;  // [n + 1]
+  uint32_t n;
+  uint32_t pad;
+};
+__global__ void __launch_bounds__(256)
+k_slices_check(const SliceRef* __restrict__ sl, uint32_t* __restrict__ stats) {
+  const SliceRef f = sl[blockIdx.y];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < f.n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = f.toff[i], b = f.toff[i + 1];
+    if (b < a) atomicExch(&stats[1], 1u);
+    else atomicMax(&stats[0], b - a);
+    if (f.poff[i + 1] < f.poff[i]) atomicExch(&stats[1], 1u);
+  }
+}
+
+// Staging kernel of the pipelined ii2_merge: gathers many host arrays (pinned, mapped into the
+// device address space by unified addressing) into device blocks with plain loads over the
+// bus.  One launch per term range replaces hundreds of copy-engine requests (measured ~7 us
+// of engine time each, more than the small slices take to transfer).  src and dst of a job
+// share their phase modulo 16 bytes, so the body moves as 16-byte vectors.
+struct GatherJob {
+  const uint8_t* src;  // host
+  uint8_t* dst;        // device
+  uint64_t bytes;
+  uint64_t vec0;       // 16-byte vectors of the jobs before this one (exclusive prefix)
+};
+constexpr int kGatherThreads = 256;
+constexpr int kGatherUnroll = 4;
+
+__global__ void __launch_bounds__(kGatherThreads)
+k_gather_host(const GatherJob* __restrict__ jobs, uint32_t njobs, uint64_t nvec_total) {
+  // ragged ends (< 16 bytes at either side of every job): one thread per job
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < njobs; j += gridDim.x * blockDim.x) {
+    const GatherJob g = jobs[j];
+    const uint64_t ph = (16 - (reinterpret_cast<uintptr_t>(g.src) & 15)) & 15;
+    const uint64_t head = g.bytes < ph ? g.bytes : ph;
+    for (uint64_t i = 0; i < head; i++) g.dst[i] = g.src[i];
+    const uint64_t body = (g.bytes - head) & ~15ull;
+    for (uint64_t i = head + body; i < g.bytes; i++) g.dst[i] = g.src[i];
+  }
+  const uint64_t tile = (uint64_t)kGatherThreads * kGatherUnroll;
+  for (uint64_t v0 = (uint64_t)blockIdx.x * tile; v0 < nvec_total; v0 += (uint64_t)gridDim.x * tile) {
+    uint4 x[kGatherUnroll];
+    uint4* d[kGatherUnroll];
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++) {
+      const uint64_t v = v0 + (uint64_t)u * kGatherThreads + threadIdx.x;
+      d[u] = nullptr;
+      if (v < nvec_total) {
+        uint32_t lo = 0, hi = njobs;  // last job with vec0 <= v
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (jobs[mid].vec0 <= v)
+            lo = mid;
+          else
+            hi = mid;
+        }
+        const GatherJob g = jobs[lo];
+        const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(g.src) & 15)) & 15;
+        const uint64_t at = head + (v - g.vec0) * 16;
+        x[u] = *reinterpret_cast<const uint4*>(g.src + at);
+        d[u] = reinterpret_cast<uint4*>(g.dst + at);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++)
+      if (d[u]) *d[u] = x[u];
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -152,7 +241,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   DevBuf<SegDesc> d_segs;
   II2_TRY(d_segs.alloc_scratch(nsegx, s));
   if (nseg)
-    II2_CUDA_TRY(cudaMemcpyAsync(d_segs.p, h, sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, s));
+    II2_TRY(small_copy(d_segs.p, h, sizeof(SegDesc) * nseg, s));
   uint32_t n_total = (uint32_t)n_total64;
   const bool ranged = has_min || has_max;
   if (ranged && nseg) {
@@ -163,12 +252,12 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     if (has_min && minlen) memcpy(h_bounds, min, minlen);
     if (has_max && maxlen) memcpy(h_bounds + minlen, max, maxlen);
     if (minlen + maxlen)
-      II2_CUDA_TRY(cudaMemcpyAsync(d_bounds.p, h_bounds, minlen + maxlen, cudaMemcpyHostToDevice, s));
+      II2_TRY(small_copy(d_bounds.p, h_bounds, minlen + maxlen, s));
     k4_windows<<<1, 1024, 0, s>>>(d_segs.p, nseg, d_bounds.p, (uint32_t)minlen, has_min ? 1 : 0,
                                   (uint32_t)maxlen, has_max ? 1 : 0, d_nt.p);
     II2_LAUNCHED();
     // the windows come back: the planner spreads its samples over them
-    II2_CUDA_TRY(cudaMemcpyAsync(h, d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, s));
+    II2_TRY(small_copy(h, d_segs.p, sizeof(SegDesc) * nseg, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
     n_total64 = 0;
     for (int i = 0; i < nseg; i++) n_total64 += h[i].hi - h[i].lo;
@@ -200,8 +289,8 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   plan.segs = d_segs.p;
   II2_TRY(k1_build_plan(plan, h, h_sbase, s));
   if (ranged) {  // Σ input postings inside the windows sizes the union buffers
-    uint64_t h_plan_tot[2] = {0, 0};
-    II2_CUDA_TRY(cudaMemcpyAsync(h_plan_tot, plan.totals.p, 16, cudaMemcpyDeviceToHost, s));
+    uint64_t* h_plan_tot = pinned_scratch() + 16;
+    II2_TRY(small_copy(h_plan_tot, plan.totals.p, 16, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
     n_in = h_plan_tot[1];
   }
@@ -234,7 +323,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   if (want_minmax) {
     mm = static_cast<uint8_t*>(pinned_alloc(8 + 2 * 65536));
     if (!mm) return II2_ERR_NOMEM;
-    cudaError_t e = cudaMemcpyAsync(mm, d_mm.p, 4096, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = small_copy(mm, d_mm.p, 4096, s) == II2_OK ? cudaSuccess : cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     uint32_t ln[2] = {0, 0};
     if (e == cudaSuccess) {
@@ -302,28 +391,63 @@ int d2h(T** dst, const T* src, size_t n, HostOwner& own, cudaStream_t s) {
   return II2_OK;
 }
 
+// reads the accumulated result of k_seg_check (synchronises s)
+int seg_check_result(const uint32_t* d_stats, cudaStream_t s) {
+  uint32_t* hs = static_cast<uint32_t*>(pinned_alloc(8));
+  if (!hs) return II2_ERR_NOMEM;
+  hs[0] = hs[1] = 0;
+  cudaError_t e = small_copy(hs, d_stats, 8, s) == II2_OK ? cudaSuccess : cudaErrorUnknown;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  const uint32_t maxlen = hs[0], bad = hs[1];
+  pinned_free(hs);
+  if (e != cudaSuccess) {
+    set_last_error("segment check: %s", cudaGetErrorString(e));
+    return II2_ERR_CUDA;
+  }
+  if (bad) {
+    set_last_error("segment offsets are not monotone");
+    return II2_ERR_INVALID;
+  }
+  if (maxlen > 65535) {
+    set_last_error("term of %u bytes (max 65535)", maxlen);
+    return II2_ERR_UNSUPPORTED;
+  }
+  return II2_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ C-ABI
 extern "C" {
 
-int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
-  if (!v || !seg_out) return II2_ERR_INVALID;
+// Upload one segment view on stream s.  The offset arrays may belong to a slice of a larger
+// segment (term_off[0], post_off[0], val_off[0] != 0): the bytes / values of the slice are
+// copied and the offsets rebased on the device.  d_stats != nullptr defers the offset sanity
+// check: the check kernel accumulates into d_stats ([0] = max term length, [1] = bad flag) and
+// the caller reads it once for many segments (no host synchronisation here for DECODED and
+// DIRECT views; `_val` views synchronise to size their decoded lists).
+static int seg_upload_impl(const ii2_seg_view* v, cudaStream_t s, uint32_t* d_stats,
+                           ii2_seg** seg_out) {
   *seg_out = nullptr;
-  II2_TRY(ctx_require());
-  cudaStream_t s = cur_stream();
   const uint64_t n = v->n_terms;
   if (n >= 0xFFFFFFFFull) {
     set_last_error("segment with %llu terms (max 2^32-2)", (unsigned long long)n);
     return II2_ERR_UNSUPPORTED;
   }
-  if (n && (!v->term_off || (v->term_off[n] && !v->term_bytes))) return II2_ERR_INVALID;
+  if (n && !v->term_off) return II2_ERR_INVALID;
+  const uint32_t tfirst = n ? v->term_off[0] : 0u;
+  if (n && v->term_off[n] < tfirst) return II2_ERR_INVALID;
+  if (n && v->term_off[n] > tfirst && !v->term_bytes) return II2_ERR_INVALID;
   std::unique_ptr<ii2_seg> g(new ii2_seg());
   g->n_terms = (uint32_t)n;
-  g->term_bytes_len = n ? v->term_off[n] : 0;
-  II2_TRY(h2d(g->tb, v->term_bytes, (size_t)g->term_bytes_len, s, 32));
+  g->term_bytes_len = n ? v->term_off[n] - tfirst : 0;
+  II2_TRY(h2d(g->tb, v->term_bytes ? v->term_bytes + tfirst : nullptr, (size_t)g->term_bytes_len, s, 32));
   if (n) {
     II2_TRY(h2d(g->toff, v->term_off, (size_t)n + 1, s));
+    if (tfirst) {
+      k_rebase_u32<<<div_up(n + 1, 256), 256, 0, s>>>(g->toff.p, n + 1, tfirst);
+      II2_LAUNCHED();
+    }
   } else {
     II2_TRY(g->toff.alloc(1, s));
     II2_CUDA_TRY(cudaMemsetAsync(g->toff.p, 0, 4, s));
@@ -331,41 +455,54 @@ int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
   if (v->mode == II2_SEG_DECODED) {
     if (n && !v->post_off) return II2_ERR_INVALID;
     const uint64_t first = n ? v->post_off[0] : 0;
+    if (n && v->post_off[n] < first) return II2_ERR_INVALID;
     g->n_post = n ? v->post_off[n] - first : 0;
     if (g->n_post && !v->post) return II2_ERR_INVALID;
     II2_TRY(h2d(g->post, v->post ? v->post + first : nullptr, (size_t)g->n_post, s, 16));
-    if (n && first == 0) {
+    if (n) {
       II2_TRY(h2d(g->poff, v->post_off, (size_t)n + 1, s));
+      if (first) {
+        k_rebase_u64<<<div_up(n + 1, 256), 256, 0, s>>>(g->poff.p, n + 1, first);
+        II2_LAUNCHED();
+      }
     } else {
-      std::vector<uint64_t> rebased(n + 1, 0);
-      for (uint64_t i = 0; i <= n && n; i++) rebased[i] = v->post_off[i] - first;
-      II2_TRY(h2d(g->poff, rebased.data(), (size_t)n + 1, s));
-      II2_CUDA_TRY(cudaStreamSynchronize(s));
+      II2_TRY(g->poff.alloc(1, s));
+      II2_CUDA_TRY(cudaMemsetAsync(g->poff.p, 0, 8, s));
     }
   } else if (v->mode == II2_SEG_DIRECT) {
     if (n && !v->val_off) return II2_ERR_INVALID;
     DevBuf<uint64_t> d_vo;
-    II2_TRY(h2d(d_vo, v->val_off, (size_t)n, s));
+    II2_TRY(d_vo.alloc_scratch((size_t)n, s));
+    if (n)
+      II2_CUDA_TRY(cudaMemcpyAsync(d_vo.p, v->val_off, n * 8, cudaMemcpyHostToDevice, s));
     II2_TRY(g->post.alloc(n, s, 16));
     II2_TRY(g->poff.alloc(n + 1, s));
     k_direct_to_lists<<<div_up(n + 1, 256), 256, 0, s>>>(d_vo.p, (uint32_t)n, g->post.p, g->poff.p);
     II2_LAUNCHED();
     g->n_post = n;
-    II2_CUDA_TRY(cudaStreamSynchronize(s));
   } else if (v->mode == II2_SEG_VAL) {
     if (n && !v->val_off) return II2_ERR_INVALID;
     if (v->val_size && !v->val_bytes) return II2_ERR_INVALID;
-    if (v->val_size & 3) {
+    const uint64_t vfirst = n ? v->val_off[0] : 0;
+    if (vfirst > v->val_size) return II2_ERR_INVALID;
+    const uint64_t vsize = v->val_size - vfirst;
+    if ((vsize & 3) || (vfirst & 3)) {
       set_last_error("_val size %llu is not a multiple of 4", (unsigned long long)v->val_size);
       return II2_ERR_CORRUPT;
     }
     DevBuf<uint64_t> d_vo, d_woff;
     DevBuf<uint32_t> d_words;
-    II2_TRY(h2d(d_vo, v->val_off, (size_t)n, s));
-    II2_TRY(d_words.alloc_scratch(v->val_size / 4, s, 16));
-    if (v->val_size)
-      II2_CUDA_TRY(cudaMemcpyAsync(d_words.p, v->val_bytes, v->val_size, cudaMemcpyHostToDevice, s));
-    II2_TRY(val_offsets_to_word_offsets(d_vo.p, n, v->val_size, d_woff, s));
+    II2_TRY(d_vo.alloc_scratch((size_t)n, s));
+    if (n)
+      II2_CUDA_TRY(cudaMemcpyAsync(d_vo.p, v->val_off, n * 8, cudaMemcpyHostToDevice, s));
+    if (n && vfirst) {
+      k_rebase_u64<<<div_up(n, 256), 256, 0, s>>>(d_vo.p, n, vfirst);
+      II2_LAUNCHED();
+    }
+    II2_TRY(d_words.alloc_scratch(vsize / 4, s, 16));
+    if (vsize)
+      II2_CUDA_TRY(cudaMemcpyAsync(d_words.p, v->val_bytes + vfirst, vsize, cudaMemcpyHostToDevice, s));
+    II2_TRY(val_offsets_to_word_offsets(d_vo.p, n, vsize, d_woff, s));
     uint64_t total = 0;
     II2_TRY(intcomp_decode_dev(d_words.p, d_woff.p, n, g->post, g->poff, &total, s, false));
     g->n_post = total;
@@ -373,28 +510,32 @@ int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
     set_last_error("unknown segment mode %d", v->mode);
     return II2_ERR_INVALID;
   }
-  // sanity: term lengths must fit the tile kernel's 16-bit length field
+  // sanity: monotone offsets; term lengths must fit the tile kernel's 16-bit length field
   DevBuf<uint32_t> stats;
-  II2_TRY(stats.alloc_scratch(2, s));
-  II2_CUDA_TRY(cudaMemsetAsync(stats.p, 0, 8, s));
+  uint32_t* st = d_stats;
+  if (!st) {
+    II2_TRY(stats.alloc_scratch(2, s));
+    II2_CUDA_TRY(cudaMemsetAsync(stats.p, 0, 8, s));
+    st = stats.p;
+  }
   if (n) {
-    k_seg_check<<<div_up(n, 256), 256, 0, s>>>(g->toff.p, (uint32_t)n, g->poff.p, stats.p);
+    k_seg_check<<<div_up(n, 256), 256, 0, s>>>(g->toff.p, (uint32_t)n, g->poff.p, st);
     II2_LAUNCHED();
   }
-  uint32_t hs[2] = {0, 0};
-  II2_CUDA_TRY(cudaMemcpyAsync(hs, stats.p, 8, cudaMemcpyDeviceToHost, s));
-  II2_CUDA_TRY(cudaStreamSynchronize(s));
-  if (hs[1]) {
-    set_last_error("segment offsets are not monotone");
-    return II2_ERR_INVALID;
-  }
-  if (hs[0] > 65535) {
-    set_last_error("term of %u bytes (max 65535)", hs[0]);
-    return II2_ERR_UNSUPPORTED;
-  }
-  arena_reset(s);
+  if (!d_stats) II2_TRY(seg_check_result(st, s));
   *seg_out = g.release();
   return II2_OK;
+}
+
+int ii2_seg_upload(const ii2_seg_view* v, ii2_seg** seg_out) {
+  if (!v || !seg_out) return II2_ERR_INVALID;
+  *seg_out = nullptr;
+  II2_TRY(ctx_require());
+  cudaStream_t s = cur_stream();
+  const int rc = seg_upload_impl(v, s, nullptr, seg_out);
+  if (rc != II2_OK) cudaStreamSynchronize(s);
+  arena_reset(s);
+  return rc;
 }
 
 void ii2_seg_release(ii2_seg* seg) { delete seg; }
@@ -560,16 +701,44 @@ void ii2_read_out_free(ii2_read_out* o) {
 // ---- host-buffer entry points: upload, run, download --------------------------------
 struct SegList {
   std::vector<ii2_seg*> v;
+  // pipelined ii2_merge: the slices of one range live in four shared blocks
+  DevBuf<uint8_t> blk_tb;
+  DevBuf<uint32_t> blk_toff, blk_post;
+  DevBuf<uint64_t> blk_poff;
+  DevBuf<SliceRef> blk_ref;
+  DevBuf<GatherJob> blk_job;
   ~SegList() {
     for (ii2_seg* g : v) delete g;
   }
 };
 
-int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted, uint64_t nrem,
-              uint32_t flags, ii2_merge_out* out) {
-  if (!out || nseg < 0 || (nseg && !segs)) return II2_ERR_INVALID;
-  memset(out, 0, sizeof(*out));
-  II2_TRY(ctx_require());
+// ---- ii2_merge over host buffers, pipelined by term range -----------------------------
+// A compaction needs every segment, so H2D staging (PCIe) cannot overlap the kernels of the
+// same terms.  It can overlap the kernels of OTHER terms: the term space is cut into P ranges
+// at terms of the largest segment (host binary searches), every range is an independent
+// compaction whose outputs concatenate (ranges are in term order), and the slices of range
+// p+1 are uploaded on a second stream while range p is merged and its result flows back.
+static int host_term_cmp(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb) {
+  const int c = memcmp(a, b, na < nb ? na : nb);
+  if (c) return c;
+  return na < nb ? -1 : (na > nb ? 1 : 0);
+}
+
+static uint64_t host_lower_bound(const ii2_seg_view& v, const uint8_t* t, uint32_t nt) {
+  uint64_t lo = 0, hi = v.n_terms;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    const uint32_t o = v.term_off[mid], n = v.term_off[mid + 1] - o;
+    if (host_term_cmp(v.term_bytes + o, n, t, nt) < 0)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+static int merge_single_shot(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted,
+                             uint64_t nrem, uint32_t flags, ii2_merge_out* out) {
   SegList list;
   for (int i = 0; i < nseg; i++) {
     ii2_seg* g = nullptr;
@@ -585,6 +754,389 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
                         &res));
   std::unique_ptr<ii2_result> res_guard(res);
   return ii2_result_download_merge(res, flags, out);
+}
+
+struct EventList {
+  std::vector<cudaEvent_t> v;
+  ~EventList() {
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+  }
+};
+
+static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted,
+                           uint64_t nrem, uint32_t flags, ii2_merge_out* out, int P,
+                           std::unique_ptr<HostOwner>& own) {
+  cudaStream_t sB = cur_stream(), sA = aux_stream();
+  const bool want_dec = (flags & II2_MERGE_WANT_DECODED) != 0;
+  // ---- range bounds: rows of nseg term indices, row 0 = starts, row P = ends
+  int big = 0;
+  for (int i = 1; i < nseg; i++)
+    if (segs[i].n_terms > segs[big].n_terms) big = i;
+  std::vector<uint64_t> bounds((size_t)(P + 1) * nseg, 0);
+  uint64_t inst_total = 0;
+  for (int i = 0; i < nseg; i++) {
+    bounds[(size_t)P * nseg + i] = segs[i].n_terms;
+    inst_total += segs[i].n_terms;
+  }
+  for (int p = 1; p < P; p++) {
+    const uint64_t at = segs[big].n_terms * (uint64_t)p / P;
+    const uint32_t o = segs[big].term_off[at], n = segs[big].term_off[at + 1] - o;
+    for (int i = 0; i < nseg; i++)
+      bounds[(size_t)p * nseg + i] =
+          i == big ? at : host_lower_bound(segs[i], segs[big].term_bytes + o, n);
+  }
+  ii2_removed* rem = nullptr;
+  if (nrem) II2_TRY(ii2_removed_upload(removed_sorted, nrem, &rem));
+  std::unique_ptr<ii2_removed> rem_guard(rem);
+  DevBuf<uint32_t> d_stats;
+  II2_TRY(d_stats.alloc(2 * (size_t)P, sA));
+  II2_CUDA_TRY(cudaMemsetAsync(d_stats.p, 0, 8 * (size_t)P, sA));
+  EventList ev;
+  for (int p = 0; p < P; p++) {
+    cudaEvent_t e;
+    II2_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev.v.push_back(e);
+  }
+  std::vector<std::unique_ptr<SegList>> parts(P);
+  std::vector<std::unique_ptr<ii2_result>> results(P);
+  // Are the caller's arrays pinned and visible to the device (unified addressing)?  Then a
+  // kernel gathers them (k_gather_host); pageable arrays go through the copy engines.
+  struct DevAlias {
+    const uint8_t* tb;
+    const uint8_t* toff;
+    const uint8_t* post;
+    const uint8_t* poff;
+  };
+  std::vector<DevAlias> alias(nseg);
+  bool gather = getenv("II2_MERGE_NO_GATHER") == nullptr;
+  auto dev_alias = [&](const void* hp, size_t align, const uint8_t** out_p) {
+    *out_p = nullptr;
+    if (!hp) return;  // empty array: nothing to read
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, hp) != cudaSuccess) {
+      cudaGetLastError();
+      gather = false;
+      return;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer ||
+        (reinterpret_cast<uintptr_t>(at.devicePointer) & (align - 1)) !=
+            (reinterpret_cast<uintptr_t>(hp) & (align - 1)) ||
+        (reinterpret_cast<uintptr_t>(hp) & (align - 1)) != 0) {
+      gather = false;
+      return;
+    }
+    *out_p = static_cast<const uint8_t*>(at.devicePointer);
+  };
+  for (int i = 0; i < nseg && gather; i++) {
+    dev_alias(segs[i].term_bytes, 4, &alias[i].tb);
+    dev_alias(segs[i].term_off, 4, &alias[i].toff);
+    dev_alias(segs[i].post, 4, &alias[i].post);
+    dev_alias(segs[i].post_off, 8, &alias[i].poff);
+  }
+
+  // Stage the slices of range p: four allocations and one check launch for all segments (an
+  // allocation + a kernel per slice would cost more host time than the copies take).  Offsets
+  // stay absolute: the slice's base pointers are moved back by its first offset instead.  Every
+  // slice lands at the same phase modulo 16 bytes as its source (vector copies; the moved term
+  // pointer keeps the 4-byte alignment the key loads need).
+  const size_t nx = (size_t)nseg;
+  const size_t ref_bytes = (sizeof(SliceRef) * nx + 15) & ~(size_t)15;
+  const size_t job_bytes = sizeof(GatherJob) * 4 * nx;
+  uint8_t* h_tab = static_cast<uint8_t*>(pinned_alloc((ref_bytes + job_bytes) * P));
+  struct PinGuard {
+    void* p;
+    ~PinGuard() { pinned_free(p); }
+  } tab_guard{h_tab};
+  if (!h_tab) return II2_ERR_NOMEM;
+  auto enqueue_upload = [&](int p) -> int {
+    parts[p].reset(new SegList());
+    SegList& L = *parts[p];
+    const uint64_t* lo = &bounds[(size_t)p * nseg];
+    const uint64_t* hi = &bounds[(size_t)(p + 1) * nseg];
+    size_t tb_bytes = 0, toff_bytes = 0, post_bytes = 0, poff_bytes = 0;
+    for (int i = 0; i < nseg; i++) {
+      const ii2_seg_view& v = segs[i];
+      const size_t n1 = (size_t)(hi[i] - lo[i]) + 1;
+      tb_bytes += (size_t)(v.term_off[hi[i]] - v.term_off[lo[i]]) + 64;  // phase + tail padding
+      toff_bytes += n1 * 4 + 32;
+      post_bytes += (size_t)(v.post_off[hi[i]] - v.post_off[lo[i]]) * 4 + 32;
+      poff_bytes += n1 * 8 + 32;
+    }
+    II2_TRY(L.blk_tb.alloc(tb_bytes, sA, 64));
+    II2_TRY(L.blk_toff.alloc(toff_bytes / 4, sA));
+    II2_TRY(L.blk_post.alloc(post_bytes / 4, sA, 16));
+    II2_TRY(L.blk_poff.alloc(poff_bytes / 8, sA));
+    II2_TRY(L.blk_ref.alloc(nx, sA));
+    if (gather) II2_TRY(L.blk_job.alloc(4 * nx, sA));
+    SliceRef* refs = reinterpret_cast<SliceRef*>(h_tab + (ref_bytes + job_bytes) * p);
+    GatherJob* jobs = reinterpret_cast<GatherJob*>(h_tab + (ref_bytes + job_bytes) * p + ref_bytes);
+    uint32_t njobs = 0;
+    uint64_t nvec = 0;
+    size_t at_tb = 0, at_toff = 0, at_post = 0, at_poff = 0;  // byte cursors
+    uint32_t max_n = 0;
+    // one array slice: place it at the phase of its source, queue its copy
+    auto place = [&](uint8_t* blk, size_t& cursor, const void* hsrc, const uint8_t* dsrc,
+                     uint64_t bytes, uint8_t** dst_out) -> int {
+      const uint8_t* src = gather ? dsrc : static_cast<const uint8_t*>(hsrc);
+      cursor = ((cursor + 15) & ~(size_t)15) + (reinterpret_cast<uintptr_t>(src) & 15);
+      uint8_t* dst = blk + cursor;
+      *dst_out = dst;
+      cursor += bytes;
+      if (!bytes) return II2_OK;
+      if (gather) {
+        GatherJob& g = jobs[njobs++];
+        g.src = src;
+        g.dst = dst;
+        g.bytes = bytes;
+        g.vec0 = nvec;
+        const uint64_t head = std::min<uint64_t>(bytes, (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15);
+        nvec += (bytes - head) >> 4;
+      } else {
+        II2_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sA));
+      }
+      return II2_OK;
+    };
+    for (int i = 0; i < nseg; i++) {
+      const ii2_seg_view& v = segs[i];
+      const uint64_t n = hi[i] - lo[i];
+      const uint32_t tfirst = v.term_off[lo[i]];
+      const uint64_t tlen = v.term_off[hi[i]] - tfirst;
+      const uint64_t pfirst = v.post_off[lo[i]], plen = v.post_off[hi[i]] - pfirst;
+      if (v.term_off[hi[i]] < tfirst || v.post_off[hi[i]] < pfirst) return II2_ERR_INVALID;
+      if ((tlen && !v.term_bytes) || (plen && !v.post)) return II2_ERR_INVALID;
+      uint8_t *d_tb, *d_toff, *d_post, *d_poff;
+      II2_TRY(place(L.blk_tb.p, at_tb, v.term_bytes ? v.term_bytes + tfirst : nullptr,
+                    alias[i].tb ? alias[i].tb + tfirst : nullptr, tlen, &d_tb));
+      at_tb += 32;  // key loads read past the last term
+      II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_toff.p), at_toff, v.term_off + lo[i],
+                    alias[i].toff + 4 * lo[i], (n + 1) * 4, &d_toff));
+      II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_post.p), at_post, v.post ? v.post + pfirst : nullptr,
+                    alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, &d_post));
+      II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_poff.p), at_poff, v.post_off + lo[i],
+                    alias[i].poff + 8 * lo[i], (n + 1) * 8, &d_poff));
+      std::unique_ptr<ii2_seg> g(new ii2_seg());
+      g->n_terms = (uint32_t)n;
+      g->n_post = plen;
+      g->term_bytes_len = tlen;
+      // non-owning views into the blocks (scratch = true: never freed through the view)
+      g->tb.p = d_tb - tfirst;
+      g->tb.scratch = true;
+      g->toff.p = reinterpret_cast<uint32_t*>(d_toff);
+      g->toff.scratch = true;
+      g->post.p = reinterpret_cast<uint32_t*>(d_post) - pfirst;
+      g->post.scratch = true;
+      g->poff.p = reinterpret_cast<uint64_t*>(d_poff);
+      g->poff.scratch = true;
+      refs[i].toff = g->toff.p;
+      refs[i].poff = g->poff.p;
+      refs[i].n = (uint32_t)n;
+      refs[i].pad = 0;
+      max_n = std::max<uint32_t>(max_n, (uint32_t)n);
+      L.v.push_back(g.release());
+    }
+    II2_TRY(small_copy(L.blk_ref.p, refs, sizeof(SliceRef) * nx, sA));
+    if (gather && njobs) {
+      II2_TRY(small_copy(L.blk_job.p, jobs, sizeof(GatherJob) * njobs, sA));
+      const unsigned grid = (unsigned)std::min<uint64_t>(
+          64, std::max<uint64_t>(1, div_up(nvec, (uint64_t)kGatherThreads * kGatherUnroll)));
+      k_gather_host<<<grid, kGatherThreads, 0, sA>>>(L.blk_job.p, njobs, nvec);
+      II2_LAUNCHED();
+    }
+    if (max_n) {
+      const dim3 grid(std::min<unsigned>(div_up(max_n, 256), 64u), (unsigned)nseg);
+      k_slices_check<<<grid, 256, 0, sA>>>(L.blk_ref.p, d_stats.p + 2 * p);
+      II2_LAUNCHED();
+    }
+    II2_CUDA_TRY(cudaEventRecord(ev.v[p], sA));
+    return II2_OK;
+  };
+
+  // ---- output buffers: sized from the first range's result, exact re-copy if that was short
+  own.reset(new HostOwner());
+  uint64_t capT = 0, capTB = 0, capE = 0, capP = 0;
+  uint64_t runT = 0, runTB = 0, runE = 0, runP = 0;
+  bool overflow = false;
+  uint64_t terms_merged = 0, postings_in = 0;
+  std::string min_term, max_term;
+  bool has_minmax = false;
+  auto alloc_out = [&](uint64_t T, uint64_t TB, uint64_t E, uint64_t Pn) -> int {
+    own.reset(new HostOwner());
+    out->term_bytes = own->alloc<uint8_t>(TB);
+    out->term_off = own->alloc<uint32_t>(T + 1);
+    out->val_off = own->alloc<uint64_t>(T);
+    out->val_bytes = reinterpret_cast<uint8_t*>(own->alloc<uint32_t>(E));
+    if (!out->term_bytes || !out->term_off || !out->val_off || !out->val_bytes) return II2_ERR_NOMEM;
+    if (want_dec) {
+      out->post = own->alloc<uint32_t>(Pn);
+      out->post_off = own->alloc<uint64_t>(T + 1);
+      if (!out->post || !out->post_off) return II2_ERR_NOMEM;
+    }
+    capT = T; capTB = TB; capE = E; capP = Pn;
+    return II2_OK;
+  };
+  // copies result r to the output at the running offsets (offset arrays get their base added
+  // on the device first, once)
+  auto copy_out = [&](ii2_result* r, uint64_t bT, uint64_t bTB, uint64_t bE, uint64_t bP,
+                      bool rebase) -> int {
+    if (rebase && r->T) {
+      if (bTB) {
+        k_rebase_u32<<<div_up(r->T, 256), 256, 0, sB>>>(r->out.term_off.p, r->T, (uint32_t)(0u - (uint32_t)bTB));
+        II2_LAUNCHED();
+      }
+      if (bE) {
+        k_rebase_u64<<<div_up(r->T, 256), 256, 0, sB>>>(r->out.val_off.p, r->T, 0ull - 4ull * bE);
+        II2_LAUNCHED();
+      }
+      if (want_dec && bP) {
+        k_rebase_u64<<<div_up(r->T, 256), 256, 0, sB>>>(r->out.post_off.p, r->T, 0ull - bP);
+        II2_LAUNCHED();
+      }
+    }
+    if (r->TB)
+      II2_CUDA_TRY(cudaMemcpyAsync(out->term_bytes + bTB, r->out.term_bytes.p, r->TB, cudaMemcpyDeviceToHost, sB));
+    if (r->T) {
+      II2_CUDA_TRY(cudaMemcpyAsync(out->term_off + bT, r->out.term_off.p, r->T * 4, cudaMemcpyDeviceToHost, sB));
+      II2_CUDA_TRY(cudaMemcpyAsync(out->val_off + bT, r->out.val_off.p, r->T * 8, cudaMemcpyDeviceToHost, sB));
+    }
+    if (r->E)
+      II2_CUDA_TRY(cudaMemcpyAsync(out->val_bytes + 4 * bE, r->out.val_words.p, r->E * 4, cudaMemcpyDeviceToHost, sB));
+    if (want_dec) {
+      if (r->P)
+        II2_CUDA_TRY(cudaMemcpyAsync(out->post + bP, r->out.post.p, r->P * 4, cudaMemcpyDeviceToHost, sB));
+      if (r->T)
+        II2_CUDA_TRY(cudaMemcpyAsync(out->post_off + bT, r->out.post_off.p, r->T * 8, cudaMemcpyDeviceToHost, sB));
+    }
+    return II2_OK;
+  };
+
+  {
+    ProfScope sc("e2e_enqueue_upload", sA);
+    II2_TRY(enqueue_upload(0));
+  }
+  for (int p = 0; p < P; p++) {
+    if (p + 1 < P) {  // in flight while range p is merged
+      ProfScope sc("e2e_enqueue_upload", sA);
+      II2_TRY(enqueue_upload(p + 1));
+    }
+    II2_CUDA_TRY(cudaStreamWaitEvent(sB, ev.v[p], 0));
+    {
+      ProfScope sc("e2e_wait_upload", sB);
+      II2_TRY(seg_check_result(d_stats.p + 2 * p, sB));
+    }
+    ii2_result* res = nullptr;
+    II2_TRY(run_pipeline(parts[p]->v.data(), nseg, nullptr, 0, false, nullptr, 0, false, rem,
+                         want_dec, true, true, false, &res));
+    results[p].reset(res);
+    parts[p].reset();  // the stream is drained: the slices can go
+    terms_merged += res->terms_merged;
+    postings_in += res->postings_in;
+    if (res->has_minmax) {
+      if (!has_minmax) min_term = res->min_term;
+      max_term = res->max_term;
+      has_minmax = true;
+    }
+    if (p == 0) {  // extrapolate by instances, a quarter of slack
+      uint64_t inst0 = 0;
+      for (int i = 0; i < nseg; i++) inst0 += bounds[(size_t)nseg + i];
+      // II2_MERGE_SLACK=<x> replaces the 1.25 (tests: a small value forces the exact re-copy)
+      const char* env_slack = getenv("II2_MERGE_SLACK");
+      const double slack = env_slack ? atof(env_slack) : 1.25;
+      const double f = inst0 ? slack * (double)inst_total / (double)inst0 : (double)P;
+      II2_TRY(alloc_out((uint64_t)(res->T * f) + 4096, (uint64_t)(res->TB * f) + 65536,
+                        (uint64_t)(res->E * f) + 65536, want_dec ? (uint64_t)(res->P * f) + 65536 : 0));
+    }
+    if (runT + res->T > capT || runTB + res->TB > capTB || runE + res->E > capE ||
+        (want_dec && runP + res->P > capP))
+      overflow = true;
+    if (!overflow) {
+      ProfScope sc("e2e_enqueue_download", sB);
+      II2_TRY(copy_out(res, runT, runTB, runE, runP, true));
+      res->rebased = true;
+    }
+    runT += res->T;
+    runTB += res->TB;
+    runE += res->E;
+    runP += res->P;
+    if (runTB >= (1ull << 32)) {
+      set_last_error("merged term dictionary exceeds 4 GiB of term bytes");
+      return II2_ERR_UNSUPPORTED;
+    }
+  }
+  if (overflow) {  // the estimate was short: exact buffers, copy every range again
+    II2_CUDA_TRY(cudaStreamSynchronize(sB));
+    II2_TRY(alloc_out(runT, runTB, runE, want_dec ? runP : 0));
+    uint64_t bT = 0, bTB = 0, bE = 0, bP = 0;
+    for (int p = 0; p < P; p++) {
+      ii2_result* r = results[p].get();
+      II2_TRY(copy_out(r, bT, bTB, bE, bP, !r->rebased));  // same bases as in the first pass
+      r->rebased = true;
+      bT += r->T;
+      bTB += r->TB;
+      bE += r->E;
+      bP += r->P;
+    }
+  }
+  {
+    ProfScope sc("e2e_final_sync", sB);
+    II2_CUDA_TRY(cudaStreamSynchronize(sB));
+  }
+  out->term_off[runT] = (uint32_t)runTB;
+  if (want_dec) out->post_off[runT] = runP;
+  out->terms_count = runT;
+  out->val_size = runE * 4;
+  out->has_minmax = has_minmax ? 1 : 0;
+  if (has_minmax) {
+    out->min_term = own->alloc<uint8_t>(min_term.size() + 1);
+    out->max_term = own->alloc<uint8_t>(max_term.size() + 1);
+    if (!out->min_term || !out->max_term) return II2_ERR_NOMEM;
+    memcpy(out->min_term, min_term.data(), min_term.size());
+    memcpy(out->max_term, max_term.data(), max_term.size());
+    out->min_term_len = (uint32_t)min_term.size();
+    out->max_term_len = (uint32_t)max_term.size();
+  }
+  out->terms_merged = terms_merged;
+  out->postings_in = postings_in;
+  out->postings_out = runP;
+  out->_owner = own.release();
+  return II2_OK;
+}
+
+int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted, uint64_t nrem,
+              uint32_t flags, ii2_merge_out* out) {
+  if (!out || nseg < 0 || (nseg && !segs)) return II2_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  II2_TRY(ctx_require());
+  // term-range pipelining pays once staging dominates: DECODED views (no per-segment host
+  // synchronisation), at least ~200 MB per range
+  uint64_t bytes = 0;
+  bool all_decoded = nseg > 0;
+  for (int i = 0; i < nseg; i++) {
+    const ii2_seg_view& v = segs[i];
+    if (v.mode != II2_SEG_DECODED || (v.n_terms && (!v.term_off || !v.post_off))) {
+      all_decoded = false;
+      break;
+    }
+    if (v.n_terms)
+      bytes += (uint64_t)(v.term_off[v.n_terms] - v.term_off[0]) + 12ull * v.n_terms +
+               4ull * (v.post_off[v.n_terms] - v.post_off[0]);
+  }
+  // II2_MERGE_PARTS=<n> forces the number of ranges (tests and tuning; 1 = single shot)
+  const char* env_parts = getenv("II2_MERGE_PARTS");
+  const int forced = env_parts ? atoi(env_parts) : 0;
+  // measured on B200 (1.25 GB of inputs): 35.6 ms single shot, 31.1 ms with 6 ranges, 32.1 with 8
+  int P = forced > 0 ? forced : (int)std::min<uint64_t>(6, bytes / (192ull << 20));
+  if (!all_decoded || P < 2) return merge_single_shot(segs, nseg, removed_sorted, nrem, flags, out);
+  uint64_t max_terms = 0;
+  for (int i = 0; i < nseg; i++) max_terms = std::max<uint64_t>(max_terms, segs[i].n_terms);
+  if (max_terms < (uint64_t)P) return merge_single_shot(segs, nseg, removed_sorted, nrem, flags, out);
+  std::unique_ptr<HostOwner> own;  // outlives any copy still in flight when a step fails
+  const int rc = merge_pipelined(segs, nseg, removed_sorted, nrem, flags, out, P, own);
+  if (rc != II2_OK) {
+    cudaStreamSynchronize(cur_stream());
+    cudaStreamSynchronize(aux_stream());
+    memset(out, 0, sizeof(*out));
+  }
+  return rc;
 }
 
 int ii2_read_range(const ii2_seg_view* segs, int nseg, const uint8_t* min, size_t minlen,

@@ -267,8 +267,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     constexpr int PER = CAP_I / K1B_THREADS;
     uint64_t pp[PER];   // first posting of the thread's instances
     uint32_t pl[PER];   // their lengths
-    uint32_t ofs[PER];  // where they go inside their term's gather slot
-    uint32_t grp[PER];  // their term's representative
+    uint32_t og[PER];   // representative of their term << 20 | where they go inside its gather slot
     {
       int sg[PER];
       uint32_t ix[PER], to[PER], tn[PER];
@@ -365,11 +364,11 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
         }
         slot = (slot + 1) & (K1B_HT - 1);
       }
-      grp[j] = rep;
       // Σ source lengths, saturating per source so the sum cannot wrap: heavy iff sum > REG_CAP.
       // For a light term every addend is exact, so the value before the add is where this
       // source starts inside the term's gather slot.
-      ofs[j] = atomicAdd(&cg[rep], (1u << 20) | (pl[j] > REG_CAP ? REG_CAP + 1 : pl[j])) & 0xFFFFFu;
+      og[j] = (rep << 20) |
+              (atomicAdd(&cg[rep], (1u << 20) | (pl[j] > REG_CAP ? REG_CAP + 1 : pl[j])) & 0xFFFFFu);
     }
     __syncthreads();
     const uint32_t D = s_nreps;
@@ -470,11 +469,11 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     for (int j = 0; j < PER; j++) {
       const uint32_t i = tid + j * K1B_THREADS;
       if (i < size) {
-        const uint32_t g = grp[j];
+        const uint32_t g = og[j] >> 20;
         const uint32_t pb = pbase[g];
         if (pb != K1B_HEAVY) {
           const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(pp[j]);
-          uint32_t* __restrict__ dst = gath + pb + ofs[j];
+          uint32_t* __restrict__ dst = gath + pb + (og[j] & 0xFFFFFu);
           const uint32_t n = pl[j];
           uint32_t t = 0;
 #pragma unroll 1
@@ -1256,12 +1255,13 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   }
   k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
   II2_LAUNCHED();
-  uint64_t h_tot[8];
+  uint64_t* h_tot = pinned_scratch();  // 8 words
+  if (!h_tot) return II2_ERR_NOMEM;
   // optimistic: scan right away; redone only if heavy terms were deferred
   {
     ProfScope scope("k12_scan_sync", s);
     II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
-    II2_CUDA_TRY(cudaMemcpyAsync(h_tot, u.totals.p, 64, cudaMemcpyDeviceToHost, s));
+    II2_TRY(small_copy(h_tot, u.totals.p, 64, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
   }
   const uint32_t h_nl = (uint32_t)h_tot[6];
@@ -1339,7 +1339,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       II2_LAUNCHED();
     }
     II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
-    II2_CUDA_TRY(cudaMemcpyAsync(h_tot, u.totals.p, 64, cudaMemcpyDeviceToHost, s));
+    II2_TRY(small_copy(h_tot, u.totals.p, 64, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));  // also keeps `offs` alive until its copy is done
   }
   for (int i = 0; i < 4; i++) u.h_totals[i] = h_tot[i];

@@ -325,7 +325,7 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   II2_TRY(d_base.alloc_scratch(2 * (size_t)(k + 1), s));
   II2_TRY(d_u64.alloc_scratch(6 * Sx, s));
   II2_TRY(d_u32.alloc_scratch(4 * Sx, s));
-  II2_CUDA_TRY(cudaMemcpyAsync(d_base.p, sbase, 2 * (size_t)(k + 1) * 4, cudaMemcpyHostToDevice, s));
+  II2_TRY(small_copy(d_base.p, sbase, 2 * (size_t)(k + 1) * 4, s));  // sbase is pinned
   const uint32_t* d_sbase = d_base.p;
   const uint32_t* d_cbase = d_base.p + (k + 1);
   SampleArrays sa{d_u64.p, d_u64.p + Sx, d_u64.p + 2 * Sx, d_u32.p, d_u32.p + Sx, d_u32.p + 2 * Sx};

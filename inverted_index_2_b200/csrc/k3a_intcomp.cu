@@ -102,9 +102,11 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
   II2_TRY(exclusive_scan_u64(out_off.p, nlists + 1, d_total.p, s));
   uint64_t total = 0;
   int herr = 0;
-  II2_CUDA_TRY(cudaMemcpyAsync(&total, d_total.p, sizeof(total), cudaMemcpyDeviceToHost, s));
-  II2_CUDA_TRY(cudaMemcpyAsync(&herr, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 20, d_total.p, sizeof(total), cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 21, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  total = pinned_scratch()[20];
+  herr = *reinterpret_cast<const int*>(pinned_scratch() + 21);
   if (herr) {
     set_last_error("undecodable intcomp stream in batch");
     return II2_ERR_CORRUPT;

@@ -94,6 +94,37 @@ static size_t size_class(size_t bytes) {
   return c;
 }
 
+__global__ void __launch_bounds__(256)
+k_small_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nw = bytes >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3) == 0;
+  if (aligned) {
+    if (i < nw) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    if (i < (bytes & 3)) dst[(nw << 2) + i] = src[(nw << 2) + i];
+  } else {
+    for (size_t j = i * 4; j < bytes && j < i * 4 + 4; j++) dst[j] = src[j];
+  }
+}
+
+int small_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return II2_OK;
+  k_small_copy<<<div_up((bytes + 3) / 4, 256), 256, 0, s>>>(static_cast<uint8_t*>(dst),
+                                                            static_cast<const uint8_t*>(src), bytes);
+  II2_LAUNCHED();
+  return II2_OK;
+}
+
+uint64_t* pinned_scratch() {
+  static thread_local uint64_t* p = nullptr;
+  if (!p) {
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, 256, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    p = static_cast<uint64_t*>(q);
+  }
+  return p;
+}
+
 void* pinned_alloc(size_t bytes) {
   size_t c = size_class(bytes ? bytes : 1);
   {

@@ -89,6 +89,16 @@ struct ProfScope {
 // Pinned host memory with a size-class cache (cudaHostAlloc is far too slow per call).
 void* pinned_alloc(size_t bytes);
 void pinned_free(void* p);  // also accepts nullptr
+// 256 bytes of pinned memory owned by the calling thread: the landing place of the small
+// device->host readbacks (totals, flags).  A pageable destination would make the copy wait for
+// every other transfer in flight, including the next range's staging on the second stream.
+uint64_t* pinned_scratch();
+
+// Copy a few bytes between PINNED host memory and device memory (either direction) with a
+// kernel instead of a copy engine.  The copy engines serve requests in order: a 64-byte
+// readback queued behind the next range's hundreds of MB of staging would wait for all of it.
+// A kernel reads / writes the pinned page directly over the bus and only obeys stream order.
+int small_copy(void* dst, const void* src, size_t bytes, cudaStream_t s);
 
 // In-place exclusive scan of d[0..n) (u64); total written to *d_total (device) if non-null.
 int exclusive_scan_u64(uint64_t* d, uint64_t n, uint64_t* d_total, cudaStream_t s);

@@ -202,6 +202,47 @@ def test_heavy_terms_multi_cta_union(engine, orc):
                        orc.merge(segs, removed, decoded=True))
 
 
+def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
+    """ii2_merge over host buffers cuts the term space into ranges and overlaps staging with
+    the kernels; the concatenated result is the single-shot result, also when the output
+    estimate taken from the first range is too small (exact re-copy) and for slices of
+    segments that start past offset 0."""
+    w = synth.make_workload(30000, 7, 400000, universe=1 << 16, removed_frac=0.1, seed=31,
+                            max_len=300)
+    segs = list(w.segments)
+    segs.append(FlatSegment.from_items([(b"zzzz_only_here", [5, 3, 3])]))  # single-source tail
+    exp = orc.merge(segs, w.removed, decoded=True)
+    for parts, slack in (("1", None), ("2", None), ("5", None), ("8", "0.05"), ("3", "0.0")):
+        monkeypatch.setenv("II2_MERGE_PARTS", parts)
+        if slack is None:
+            monkeypatch.delenv("II2_MERGE_SLACK", raising=False)
+        else:
+            monkeypatch.setenv("II2_MERGE_SLACK", slack)
+        assert_merge_equal(engine.merge(segs, w.removed, decoded=True), exp)
+        assert_merge_equal(engine.merge(segs, None, decoded=False),
+                           orc.merge(segs, None, decoded=False), decoded=False)
+    # pinned host arrays are gathered by a kernel instead of the copy engines
+    import torch
+    keep = []
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+    psegs = [FlatSegment(pinned(x.term_bytes), pinned(x.term_off), x.mode, post=pinned(x.post),
+                         post_off=pinned(x.post_off)) for x in segs]
+    for parts in ("2", "7"):
+        monkeypatch.setenv("II2_MERGE_PARTS", parts)
+        monkeypatch.delenv("II2_MERGE_SLACK", raising=False)
+        assert_merge_equal(engine.merge(psegs, w.removed, decoded=True), exp)
+    # everything removed in the first ranges: min/max still come from the first / last range
+    monkeypatch.setenv("II2_MERGE_PARTS", "4")
+    monkeypatch.delenv("II2_MERGE_SLACK", raising=False)
+    allrem = np.arange(0, 1 << 16, dtype=np.uint32)
+    assert_merge_equal(engine.merge(segs, allrem, decoded=True), orc.merge(segs, allrem, decoded=True))
+    monkeypatch.delenv("II2_MERGE_PARTS", raising=False)
+
+
 def test_union_width_boundaries(engine, orc):
     """Union kernel paths: two terms per warp (< 128 values), one term per warp (128..256),
     multi-CTA (> 256); single-source terms (unsorted, duplicates kept: Q4) paired with
