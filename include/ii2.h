@@ -208,6 +208,33 @@ void ii2_result_release(ii2_result* res);
 /* Block until everything queued by this thread's stream is done. */
 int ii2_sync(void);
 
+/* ---- PrefixSearch: replaces the per-shard scan of InvertedIndex.PrefixSearch
+ *      (inverted_index.go:239-292) ------------------------------------------ */
+typedef struct ii2_prefix_out {
+  uint64_t n_prefixes;
+  /* matched[i] != 0 <=> at least one term starts with prefix i, i.e. prefix i
+   * is a key of the map PrefixSearch returns (inverted_index.go:274-279; a
+   * matching term with an empty list still creates the key). */
+  uint8_t* matched;
+  /* found[prefix i] = values[value_off[i] .. value_off[i+1]): the values of
+   * every term with that prefix over all segments, sorted and compacted
+   * (slices.Sort + slices.Compact, inverted_index.go:289-292). */
+  uint32_t* values;
+  uint64_t* value_off; /* n_prefixes + 1 */
+  void* _owner;
+} ii2_prefix_out;
+
+/* Prefix i = prefix_bytes[prefix_off[i] .. prefix_off[i+1]); any order,
+ * duplicates and the empty prefix allowed (the reference sorts them only to
+ * bound its scan, inverted_index.go:196,266-271).  `segs` may be the segments
+ * of ALL shards at once: shard selection by min/max (:211-236) only skips
+ * shards that cannot match.  No removed filter (reads never filter, shard.go:72-75). */
+int ii2_prefix_search_dev(ii2_seg* const* segs, int nseg, const uint8_t* prefix_bytes,
+                          const uint32_t* prefix_off, uint32_t nprefix, ii2_prefix_out* out);
+int ii2_prefix_search(const ii2_seg_view* segs, int nseg, const uint8_t* prefix_bytes,
+                      const uint32_t* prefix_off, uint32_t nprefix, ii2_prefix_out* out);
+void ii2_prefix_out_free(ii2_prefix_out* out);
+
 /* ---- posting codec: replaces intcomp.CompressUint32 (file/writer.go:49) and
  *      intcomp.UncompressUint32 (file/reader.go:100), batched ---------------- */
 /* list i = in[off[i] .. off[i+1]); out words of list i =

@@ -79,6 +79,16 @@ class ReadOut(C.Structure):
     ]
 
 
+class PrefixOut(C.Structure):
+    _fields_ = [
+        ("n_prefixes", C.c_uint64),
+        ("matched", u8p),
+        ("values", u32p),
+        ("value_off", u64p),
+        ("_owner", C.c_void_p),
+    ]
+
+
 class ResultInfo(C.Structure):
     _fields_ = [
         ("terms_count", C.c_uint64),
@@ -133,6 +143,11 @@ PROTOTYPES = {
     "ii2_result_to_seg": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ii2_result_release": (None, [C.c_void_p]),
     "ii2_sync": (C.c_int, []),
+    "ii2_prefix_search_dev": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, u8p, u32p, C.c_uint32,
+                                        C.POINTER(PrefixOut)]),
+    "ii2_prefix_search": (C.c_int, [C.POINTER(SegView), C.c_int, u8p, u32p, C.c_uint32,
+                                    C.POINTER(PrefixOut)]),
+    "ii2_prefix_out_free": (None, [C.POINTER(PrefixOut)]),
     "ii2_intcomp_encode_u32": (C.c_int, [u32p, u64p, C.c_uint64, C.POINTER(u32p),
                                          C.POINTER(u64p)]),
     "ii2_intcomp_decode_u32": (C.c_int, [u32p, u64p, C.c_uint64, C.POINTER(u32p),

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "codec.cuh"
+#include "prefix.cuh"
 #include "union.cuh"
 
 using namespace ii2;
@@ -686,6 +687,92 @@ int ii2_result_to_seg(ii2_result* r, ii2_seg** seg_out) {
 
 void ii2_result_release(ii2_result* r) { delete r; }
 
+// ------------------------------------------------------------------ PrefixSearch
+static int prefix_search_impl(ii2_seg* const* segs, int nseg, const uint8_t* prefix_bytes,
+                              const uint32_t* prefix_off, uint32_t nprefix, ii2_prefix_out* o,
+                              cudaStream_t s) {
+  ProfScope pipe_scope("prefix_total", s);
+  if (nseg > kMaxSegs) {
+    set_last_error("%d segments in one call (max %d per pass)", nseg, kMaxSegs);
+    return II2_ERR_UNSUPPORTED;
+  }
+  const size_t pbytes = nprefix ? prefix_off[nprefix] : 0;
+  for (uint32_t i = 0; i < nprefix; i++)
+    if (prefix_off[i + 1] < prefix_off[i]) return II2_ERR_INVALID;
+  // segment table + prefixes through one pinned block (no pageable copy on the stream)
+  const size_t nsegx = nseg ? nseg : 1;
+  const size_t off_bytes = ((size_t)nprefix + 1) * 4;
+  const size_t stage_bytes = sizeof(SegDesc) * nsegx + off_bytes + pbytes + 64;
+  struct PinnedBlock {
+    void* p = nullptr;
+    ~PinnedBlock() { pinned_free(p); }
+  } stage;
+  stage.p = pinned_alloc(stage_bytes);
+  if (!stage.p) return II2_ERR_NOMEM;
+  SegDesc* h = static_cast<SegDesc*>(stage.p);
+  uint32_t* h_off = reinterpret_cast<uint32_t*>(h + nsegx);
+  uint8_t* h_pb = reinterpret_cast<uint8_t*>(h_off + nprefix + 1);
+  for (int i = 0; i < nseg; i++) {
+    const ii2_seg* g = segs[i];
+    if (!g) return II2_ERR_INVALID;
+    h[i].tb = g->tb.p;
+    h[i].toff = g->toff.p;
+    h[i].post = g->post.p;
+    h[i].poff = g->poff.p;
+    h[i].n = g->n_terms;
+    h[i].lo = 0;
+    h[i].hi = g->n_terms;
+    h[i].base = 0;
+  }
+  if (nprefix) {
+    memcpy(h_off, prefix_off, off_bytes);
+    if (pbytes) memcpy(h_pb, prefix_bytes, pbytes);
+  } else {
+    h_off[0] = 0;
+  }
+  DevBuf<uint8_t> d_stage;
+  II2_TRY(d_stage.alloc_scratch(stage_bytes, s, 32));
+  II2_CUDA_TRY(cudaMemcpyAsync(d_stage.p, stage.p, stage_bytes, cudaMemcpyHostToDevice, s));
+  const SegDesc* d_segs = reinterpret_cast<const SegDesc*>(d_stage.p);
+  const uint32_t* d_off = reinterpret_cast<const uint32_t*>(d_segs + nsegx);
+  const uint8_t* d_pb = reinterpret_cast<const uint8_t*>(d_off + nprefix + 1);
+  PrefixOut po;
+  II2_TRY(k5_prefix_search(d_segs, nseg, d_pb, d_off, nprefix, po, s));
+  std::unique_ptr<HostOwner> own(new HostOwner());
+  uint32_t* h_matched = nullptr;
+  II2_TRY(d2h(&o->values, po.values.p, (size_t)po.total, *own, s));
+  II2_TRY(d2h(&o->value_off, po.value_off.p, (size_t)nprefix + 1, *own, s));
+  II2_TRY(d2h(&h_matched, po.matched.p, (size_t)(nprefix ? nprefix : 1), *own, s));
+  II2_CUDA_TRY(cudaStreamSynchronize(s));
+  o->matched = own->alloc<uint8_t>((size_t)nprefix + 1);
+  if (!o->matched) return II2_ERR_NOMEM;
+  for (uint32_t i = 0; i < nprefix; i++) o->matched[i] = h_matched[i] ? 1 : 0;
+  o->n_prefixes = nprefix;
+  o->_owner = own.release();
+  return II2_OK;
+}
+
+int ii2_prefix_search_dev(ii2_seg* const* segs, int nseg, const uint8_t* prefix_bytes,
+                          const uint32_t* prefix_off, uint32_t nprefix, ii2_prefix_out* out) {
+  if (!out || nseg < 0 || (nseg && !segs) || (nprefix && !prefix_off)) return II2_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  II2_TRY(ctx_require());
+  cudaStream_t s = cur_stream();
+  const int rc = prefix_search_impl(segs, nseg, prefix_bytes, prefix_off, nprefix, out, s);
+  if (rc != II2_OK) {
+    cudaStreamSynchronize(s);
+    memset(out, 0, sizeof(*out));
+  }
+  arena_reset(s);
+  return rc;
+}
+
+void ii2_prefix_out_free(ii2_prefix_out* o) {
+  if (!o) return;
+  delete static_cast<HostOwner*>(o->_owner);
+  memset(o, 0, sizeof(*o));
+}
+
 void ii2_merge_out_free(ii2_merge_out* o) {
   if (!o) return;
   delete static_cast<HostOwner*>(o->_owner);
@@ -1158,6 +1245,20 @@ int ii2_read_range(const ii2_seg_view* segs, int nseg, const uint8_t* min, size_
   II2_TRY(ii2_read_range_dev(list.v.data(), nseg, min, minlen, max, maxlen, rem, &res));
   std::unique_ptr<ii2_result> res_guard(res);
   return ii2_result_download_read(res, out);
+}
+
+int ii2_prefix_search(const ii2_seg_view* segs, int nseg, const uint8_t* prefix_bytes,
+                      const uint32_t* prefix_off, uint32_t nprefix, ii2_prefix_out* out) {
+  if (!out || nseg < 0 || (nseg && !segs)) return II2_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  II2_TRY(ctx_require());
+  SegList list;
+  for (int i = 0; i < nseg; i++) {
+    ii2_seg* g = nullptr;
+    II2_TRY(ii2_seg_upload(&segs[i], &g));
+    list.v.push_back(g);
+  }
+  return ii2_prefix_search_dev(list.v.data(), nseg, prefix_bytes, prefix_off, nprefix, out);
 }
 
 }  // extern "C"

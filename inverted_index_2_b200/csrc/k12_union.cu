@@ -39,19 +39,6 @@ constexpr uint32_t K1B_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t K12_PENDING = 0xFFFFFFFFu;
 constexpr uint32_t K1B_HEAVY = 0xFFFFFFFFu;   // pbase of a heavy term
 
-// What K1b knows about a distinct term, in merged order inside its bucket (index = bucket base
-// bk_pos[b] + rank, like GroupRec).
-struct __align__(16) GroupIn {
-  uint32_t inst;   // global instance id of one source (names the term bytes)
-  uint32_t tlen;   // term length
-  uint32_t src;    // first source in src_ptr / src_len (filled for heavy terms only)
-  uint32_t c;      // number of sources
-  uint32_t L;      // Σ source lengths if <= REG_CAP, anything larger otherwise
-  uint32_t pst;    // postings of the light terms before it in the bucket: its gather slot
-  uint32_t eslot;  // `_val` staging words reserved before it in the bucket
-  uint32_t pad;
-};
-
 // staging words that certainly hold the intcomp stream of n values (oracle/intcomp_ref.c
 // orc_intcomp_bound: 3 + 129 per block + 1 + ceil(5 * tail / 4) + 1; at most two blocks here)
 __host__ __device__ __forceinline__ uint32_t enc_slot_words(uint32_t n) { return n + (n >> 2) + 6; }
@@ -70,6 +57,7 @@ struct K1bArgs {
   uint32_t* bk_D;   // [B] distinct terms per bucket
   uint32_t bucket0; // first bucket of this launch (the grid covers a chunk of buckets)
 };
+
 
 // Order of two terms whose bytes before `skip` are equal and which both run past `skip`:
 // further 16-byte windows until one differs or a term ends.  Kept out of line: the compiler
@@ -465,6 +453,8 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     // ---------------- (5) sources of every term ---------------------------------------------
     // light terms: the postings themselves, copied into the term's slot (any order: the union
     // sorts; a single-source term is one copy, order kept); heavy terms: (pointer, length)
+    // (requesting the first values of all four sources before storing any was measured
+    // slower: 1.59 vs 1.44 ms — more loads in flight only thrash the L1)
 #pragma unroll
     for (int j = 0; j < PER; j++) {
       const uint32_t i = tid + j * K1B_THREADS;
@@ -962,24 +952,6 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
 }
 
 // ---------------------------------------------------------------- heavy terms (global memory)
-struct LargeArgs {
-  const uint32_t* rec;     // record index of the term (same index in gin and recs)
-  const uint32_t* bucket;
-  const GroupIn* gin;
-  const uint64_t* src_ptr;
-  const uint32_t* src_len;
-  uint64_t* len;           // Σ source lengths
-  const uint64_t* off;     // offset into tmp
-  const uint64_t* eoff;    // offset into enc (upper-bound slots)
-  uint32_t* tmp;
-  uint32_t* enc;
-  GroupRec* recs;
-  RemovedSet rem;
-  int want_enc, keep_empty;
-  uint64_t* bk_raw;
-  uint32_t nb1;
-};
-
 __global__ void __launch_bounds__(256) k2_large_len(const LargeArgs a, uint32_t n) {
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= n) return;
@@ -1028,7 +1000,7 @@ constexpr uint32_t LG_TILE = 4096;
 // sort every aligned LG_TILE tile of every heavy group in shared memory
 __global__ void __launch_bounds__(512) k2_large_tile_sort(const LargeArgs a) {
   __shared__ uint32_t tile[LG_TILE];
-  if (a.gin[a.rec[blockIdx.y]].c == 1) return;  // single source: passes through unsorted (Q4)
+  if (a.gin[a.rec[blockIdx.y]].c == 1 && !a.always_sort) return;  // single source: passes through unsorted (Q4)
   const uint64_t n = a.len[blockIdx.y];
   uint32_t* base = a.tmp + a.off[blockIdx.y];
   for (uint64_t t0 = (uint64_t)blockIdx.x * LG_TILE; t0 < n; t0 += (uint64_t)gridDim.x * LG_TILE) {
@@ -1046,7 +1018,7 @@ __global__ void __launch_bounds__(512) k2_large_tile_sort(const LargeArgs a) {
 // one global stage of the direction-free bitonic network: flip (kk, j == 0) or half-cleaner j
 __global__ void __launch_bounds__(256) k2_large_stage(const LargeArgs a, uint64_t kk, uint64_t j) {
   const uint64_t n = a.len[blockIdx.y];
-  if ((kk >> 1) >= n || a.gin[a.rec[blockIdx.y]].c == 1) return;  // sorted / pass-through
+  if ((kk >> 1) >= n || (a.gin[a.rec[blockIdx.y]].c == 1 && !a.always_sort)) return;  // sorted / pass-through
   uint32_t* v = a.tmp + a.off[blockIdx.y];
   const uint64_t half = j ? j : (kk >> 1);
   const uint64_t limit = (n + 1) / 2 + half;
@@ -1074,7 +1046,7 @@ __global__ void __launch_bounds__(256) k2_large_stage(const LargeArgs a, uint64_
 __global__ void __launch_bounds__(512) k2_large_tile_merge(const LargeArgs a, uint64_t kk) {
   __shared__ uint32_t tile[LG_TILE];
   const uint64_t n = a.len[blockIdx.y];
-  if ((kk >> 1) >= n || a.gin[a.rec[blockIdx.y]].c == 1) return;
+  if ((kk >> 1) >= n || (a.gin[a.rec[blockIdx.y]].c == 1 && !a.always_sort)) return;
   uint32_t* base = a.tmp + a.off[blockIdx.y];
   for (uint64_t t0 = (uint64_t)blockIdx.x * LG_TILE; t0 < n; t0 += (uint64_t)gridDim.x * LG_TILE) {
     const uint32_t m = (uint32_t)((n - t0) < LG_TILE ? (n - t0) : LG_TILE);
@@ -1106,7 +1078,7 @@ __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
   __shared__ uint32_t s_enc;
   const uint32_t g = blockIdx.x;
   const uint64_t n = a.len[g];
-  const bool single = a.gin[a.rec[g]].c == 1;  // pass-through: duplicates stay
+  const bool single = a.gin[a.rec[g]].c == 1 && !a.always_sort;  // pass-through: duplicates stay
   uint32_t* v = a.tmp + a.off[g];
   uint64_t outn = 0;
   for (uint64_t e0 = 0; e0 < n; e0 += 1024) {
@@ -1143,7 +1115,7 @@ __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
     r.enc = s_enc;
     r.dec = reinterpret_cast<uint64_t>(v);
     r.eoff = reinterpret_cast<uint64_t>(a.enc + a.eoff[g]);
-    if (outn || a.keep_empty) {
+    if (a.bk_raw && (outn || a.keep_empty)) {
       const uint32_t b = a.bucket[g];
       unsigned long long* bo = reinterpret_cast<unsigned long long*>(a.bk_raw);
       atomicAdd(&bo[0ull * a.nb1 + b], 1ull);
@@ -1163,6 +1135,76 @@ k12_sum_D(const uint32_t* __restrict__ d, uint32_t n, uint64_t* __restrict__ out
   uint64_t tot;
   block_exclusive_scan(acc, ws, tot);
   if (threadIdx.x == 0) *out = tot;
+}
+
+// The multi-CTA union of `h_nl` heavy groups (also the per-prefix union of k5_prefix.cu).  The
+// caller fills rec / bucket / gin / src_ptr / src_len / recs / rem / flags / bk_raw; sizes,
+// offsets and the sort space are set up here.  Synchronises the stream.
+int k2_large_run(LargeArgs la, uint32_t h_nl, DevBuf<uint32_t>& large_tmp,
+                 DevBuf<uint32_t>& large_enc, cudaStream_t s) {
+  if (h_nl == 0) return II2_OK;
+  const bool want_enc = la.want_enc != 0;
+  DevBuf<uint64_t> d_len, d_off;
+  II2_TRY(d_len.alloc_scratch(h_nl, s));
+  II2_TRY(d_off.alloc_scratch(2 * (size_t)h_nl, s));
+  la.len = d_len.p;
+  la.off = d_off.p;
+  la.eoff = d_off.p + h_nl;
+  la.tmp = nullptr;
+  la.enc = nullptr;
+  k2_large_len<<<div_up((uint64_t)h_nl * 32, 256), 256, 0, s>>>(la, h_nl);
+  II2_LAUNCHED();
+  std::vector<uint64_t> lens(h_nl), offs(2 * (size_t)h_nl);
+  II2_CUDA_TRY(cudaMemcpyAsync(lens.data(), d_len.p, (size_t)h_nl * 8, cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaStreamSynchronize(s));
+  uint64_t total = 0, etotal = 0;
+  for (uint32_t i = 0; i < h_nl; i++) {
+    if (lens[i] >= (1ull << 32)) {
+      set_last_error("a single term unions %llu postings (max 2^32-1)",
+                     (unsigned long long)lens[i]);
+      return II2_ERR_UNSUPPORTED;
+    }
+    offs[i] = total;
+    offs[h_nl + i] = etotal;
+    total += lens[i];
+    etotal += lens[i] + lens[i] / 4 + 8;
+  }
+  II2_TRY(large_tmp.alloc_scratch(total, s));
+  if (want_enc) II2_TRY(large_enc.alloc_scratch(etotal, s));
+  la.tmp = large_tmp.p;
+  la.enc = large_enc.p;
+  II2_CUDA_TRY(cudaMemcpyAsync(d_off.p, offs.data(), 2 * (size_t)h_nl * 8, cudaMemcpyHostToDevice, s));
+  for (uint32_t y0 = 0; y0 < h_nl; y0 += 32768) {  // grid.y limit
+    const uint32_t ny = std::min<uint32_t>(32768, h_nl - y0);
+    uint64_t maxL = 0;
+    for (uint32_t i = 0; i < ny; i++) maxL = std::max(maxL, lens[y0 + i]);
+    LargeArgs b2 = la;
+    b2.rec += y0;
+    if (b2.bucket) b2.bucket += y0;
+    b2.len += y0;
+    b2.off += y0;
+    b2.eoff += y0;
+    const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((maxL + 4095) / 4096, 2048));
+    dim3 grid(gx, ny);
+    k2_large_gather<<<grid, 256, 0, s>>>(b2);
+    II2_LAUNCHED();
+    k2_large_tile_sort<<<grid, 512, 0, s>>>(b2);
+    II2_LAUNCHED();
+    for (uint64_t kk = 2ull * LG_TILE; (kk >> 1) < maxL; kk <<= 1) {
+      k2_large_stage<<<grid, 256, 0, s>>>(b2, kk, 0);
+      II2_LAUNCHED();
+      for (uint64_t j = kk >> 2; j >= LG_TILE; j >>= 1) {
+        k2_large_stage<<<grid, 256, 0, s>>>(b2, kk, j);
+        II2_LAUNCHED();
+      }
+      k2_large_tile_merge<<<grid, 512, 0, s>>>(b2, kk);
+      II2_LAUNCHED();
+    }
+    k2_large_finish<<<ny, 1024, 0, s>>>(b2);
+    II2_LAUNCHED();
+  }
+  II2_CUDA_TRY(cudaStreamSynchronize(s));  // keeps `offs` alive until its copy is done
+  return II2_OK;
 }
 
 // ---------------------------------------------------------------- host driver
@@ -1267,80 +1309,23 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   const uint32_t h_nl = (uint32_t)h_tot[6];
   if (h_nl > 0) {
     ProfScope scope("k2_large", s);
-    DevBuf<uint64_t> d_len, d_off;
-    II2_TRY(d_len.alloc_scratch(h_nl, s));
-    II2_TRY(d_off.alloc_scratch(2 * (size_t)h_nl, s));
     LargeArgs la;
     la.rec = large_u32.p;
     la.bucket = large_u32.p + large_cap;
     la.gin = gin.p;
     la.src_ptr = src_ptr.p;
     la.src_len = src_len.p;
-    la.len = d_len.p;
-    la.off = d_off.p;
-    la.eoff = d_off.p + h_nl;
-    la.tmp = nullptr;
-    la.enc = nullptr;
     la.recs = u.recs.p;
     la.rem = rem;
     la.want_enc = want_enc ? 1 : 0;
     la.keep_empty = keep_empty ? 1 : 0;
+    la.always_sort = 0;
     la.bk_raw = u.bk_raw.p;
     la.nb1 = B + 1;
-    k2_large_len<<<div_up((uint64_t)h_nl * 32, 256), 256, 0, s>>>(la, h_nl);
-    II2_LAUNCHED();
-    std::vector<uint64_t> lens(h_nl), offs(2 * (size_t)h_nl);
-    II2_CUDA_TRY(cudaMemcpyAsync(lens.data(), d_len.p, (size_t)h_nl * 8, cudaMemcpyDeviceToHost, s));
-    II2_CUDA_TRY(cudaStreamSynchronize(s));
-    uint64_t total = 0, etotal = 0;
-    for (uint32_t i = 0; i < h_nl; i++) {
-      if (lens[i] >= (1ull << 32)) {
-        set_last_error("a single term unions %llu postings (max 2^32-1)",
-                       (unsigned long long)lens[i]);
-        return II2_ERR_UNSUPPORTED;
-      }
-      offs[i] = total;
-      offs[h_nl + i] = etotal;
-      total += lens[i];
-      etotal += lens[i] + lens[i] / 4 + 8;
-    }
-    II2_TRY(u.large_tmp.alloc_scratch(total, s));
-    if (want_enc) II2_TRY(u.large_enc.alloc_scratch(etotal, s));
-    la.tmp = u.large_tmp.p;
-    la.enc = u.large_enc.p;
-    II2_CUDA_TRY(cudaMemcpyAsync(d_off.p, offs.data(), 2 * (size_t)h_nl * 8, cudaMemcpyHostToDevice, s));
-    for (uint32_t y0 = 0; y0 < h_nl; y0 += 32768) {  // grid.y limit
-      const uint32_t ny = std::min<uint32_t>(32768, h_nl - y0);
-      uint64_t maxL = 0;
-      for (uint32_t i = 0; i < ny; i++) maxL = std::max(maxL, lens[y0 + i]);
-      LargeArgs b2 = la;
-      b2.rec += y0;
-      b2.bucket += y0;
-      b2.len += y0;
-      b2.off += y0;
-      b2.eoff += y0;
-      const unsigned gx = (unsigned)std::min<uint64_t>((maxL + 4095) / 4096, 2048);
-      dim3 grid(gx, ny);
-      k2_large_gather<<<grid, 256, 0, s>>>(b2);
-      II2_LAUNCHED();
-      k2_large_tile_sort<<<grid, 512, 0, s>>>(b2);
-      II2_LAUNCHED();
-      for (uint64_t kk = 2ull * LG_TILE; (kk >> 1) < maxL; kk <<= 1) {
-        k2_large_stage<<<grid, 256, 0, s>>>(b2, kk, 0);
-        II2_LAUNCHED();
-        for (uint64_t j = kk >> 2; j >= LG_TILE; j >>= 1) {
-          k2_large_stage<<<grid, 256, 0, s>>>(b2, kk, j);
-          II2_LAUNCHED();
-        }
-        k2_large_tile_merge<<<grid, 512, 0, s>>>(b2, kk);
-        II2_LAUNCHED();
-      }
-      k2_large_finish<<<ny, 1024, 0, s>>>(b2);
-      II2_LAUNCHED();
-    }
+    II2_TRY(k2_large_run(la, h_nl, u.large_tmp, u.large_enc, s));
     II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
     II2_TRY(small_copy(h_tot, u.totals.p, 64, s));
-    II2_CUDA_TRY(cudaStreamSynchronize(s));  // also keeps `offs` alive until its copy is done
+    II2_CUDA_TRY(cudaStreamSynchronize(s));
   }
   for (int i = 0; i < 4; i++) u.h_totals[i] = h_tot[i];
   u.terms_merged = h_tot[4];

@@ -15,6 +15,42 @@ struct GroupRec {
   uint32_t enc;   // intcomp words of that list
 };
 
+// What K1b knows about a distinct term, in merged order inside its bucket (index = bucket base
+// bk_pos[b] + rank, like GroupRec).
+struct __align__(16) GroupIn {
+  uint32_t inst;   // global instance id of one source (names the term bytes)
+  uint32_t tlen;   // term length
+  uint32_t src;    // first source in src_ptr / src_len (filled for heavy terms only)
+  uint32_t c;      // number of sources
+  uint32_t L;      // Σ source lengths if <= REG_CAP, anything larger otherwise
+  uint32_t pst;    // postings of the light terms before it in the bucket: its gather slot
+  uint32_t eslot;  // `_val` staging words reserved before it in the bucket
+  uint32_t pad;
+};
+
+
+struct LargeArgs {
+  const uint32_t* rec;     // record index of the term (same index in gin and recs)
+  const uint32_t* bucket;
+  const GroupIn* gin;
+  const uint64_t* src_ptr;
+  const uint32_t* src_len;
+  uint64_t* len;           // Σ source lengths
+  const uint64_t* off;     // offset into tmp
+  const uint64_t* eoff;    // offset into enc (upper-bound slots)
+  uint32_t* tmp;
+  uint32_t* enc;
+  GroupRec* recs;
+  RemovedSet rem;
+  int want_enc, keep_empty;
+  int always_sort;         // sort + dedup single-source groups too (prefix search)
+  uint64_t* bk_raw;        // per-bucket totals to add to, or null
+  uint32_t nb1;
+};
+
+int k2_large_run(LargeArgs la, uint32_t n_groups, DevBuf<uint32_t>& large_tmp,
+                 DevBuf<uint32_t>& large_enc, cudaStream_t s);
+
 struct UnionOut {
   DevBuf<GroupRec> recs;       // [N_T]
   DevBuf<uint32_t> tmp_post;   // [N_in] gather slots of the light terms, replaced by their unions

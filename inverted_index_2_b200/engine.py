@@ -304,6 +304,47 @@ class Engine:
                     "read_range_dev")
         return DeviceResult(self, h.value)
 
+    # ---- PrefixSearch (inverted_index.go:192-295) ----------------------------------------
+    @staticmethod
+    def _prefix_args(prefixes: list[bytes]):
+        off = np.zeros(len(prefixes) + 1, dtype=np.uint32)
+        if prefixes:
+            off[1:] = np.cumsum([len(p) for p in prefixes], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(prefixes) + b"\0", dtype=np.uint8).copy()
+        return blob, off
+
+    def _prefix_result(self, prefixes: list[bytes], out: A.PrefixOut) -> dict[bytes, np.ndarray]:
+        try:
+            n = int(out.n_prefixes)
+            off = A.from_ptr(out.value_off, n + 1, np.uint64)
+            vals = A.from_ptr(out.values, int(off[-1]) if n else 0, np.uint32)
+            matched = A.from_ptr(out.matched, n, np.uint8)
+            return {p: vals[int(off[i]):int(off[i + 1])] for i, p in enumerate(prefixes)
+                    if matched[i]}
+        finally:
+            self.lib.ii2_prefix_out_free(C.byref(out))
+
+    def prefix_search(self, segs: list[FlatSegment], prefixes: list[bytes]
+                      ) -> dict[bytes, np.ndarray]:
+        """found[prefix] for every prefix with at least one matching term, over host views."""
+        arr = views_array(segs)
+        blob, off = self._prefix_args(prefixes)
+        out = A.PrefixOut()
+        self._check(self.lib.ii2_prefix_search(arr, len(segs), A.np_ptr(blob, A.u8p),
+                                               A.np_ptr(off, A.u32p), len(prefixes),
+                                               C.byref(out)), "prefix_search")
+        return self._prefix_result(prefixes, out)
+
+    def prefix_search_dev(self, segs: list[DeviceSegment], prefixes: list[bytes]
+                          ) -> dict[bytes, np.ndarray]:
+        blob, off = self._prefix_args(prefixes)
+        out = A.PrefixOut()
+        self._check(self.lib.ii2_prefix_search_dev(self._handles(segs), len(segs),
+                                                   A.np_ptr(blob, A.u8p), A.np_ptr(off, A.u32p),
+                                                   len(prefixes), C.byref(out)),
+                    "prefix_search_dev")
+        return self._prefix_result(prefixes, out)
+
     # ---- codec -----------------------------------------------------------------------
     def intcomp_encode_batch(self, post: np.ndarray, post_off: np.ndarray):
         post = np.ascontiguousarray(post, dtype=np.uint32)

@@ -32,6 +32,9 @@ class Backend(Protocol):
     def read_range(self, segs: list[FlatSegment], min_term: bytes | None,
                    max_term: bytes | None) -> ReadResult: ...
 
+    # optional: found[prefix] (sorted-unique values) for every prefix with a matching term
+    # def prefix_search(self, segs: list[FlatSegment], prefixes: list[bytes]) -> dict: ...
+
 
 _key_lock = threading.Lock()
 _last_key = 0
@@ -289,11 +292,14 @@ class InvertedIndex:
         return gen()
 
     def prefix_search(self, prefixes: list[bytes]) -> dict[bytes, list[int]]:
-        """InvertedIndex.PrefixSearch, inverted_index.go:192-295."""
+        """InvertedIndex.PrefixSearch, inverted_index.go:192-295.  Shard selection by min/max
+        as the reference does it (:211-236); the scan of the selected shards (:239-285) and the
+        final sort + compact (:289-292) are ONE C-ABI call (ii2_prefix_search) over the
+        segments of all selected shards when the backend offers it."""
         prefixes = sorted(prefixes)
-        found: dict[bytes, list[int]] = {}
         with self.m:
             shards = list(self.shards)
+        picked: list[tuple[Shard, list[bytes]]] = []
         for shard in shards:
             lo, hi = shard.min_max()
             if lo is None:
@@ -307,8 +313,22 @@ class InvertedIndex:
                 if p[:l] > hi[:l]:
                     continue
                 mine.append(p)
-            if not mine:
-                continue
+            if mine:
+                picked.append((shard, mine))
+        if not picked:
+            return {}
+        if hasattr(self.backend, "prefix_search"):
+            wanted = sorted({p for _, mine in picked for p in mine})
+            locked = [(shard, shard.segments.read_lock_all()) for shard, _ in picked]
+            try:
+                segs = [s.data for _, ss in locked for s in ss]
+                res = self.backend.prefix_search(segs, wanted)
+            finally:
+                for shard, ss in locked:
+                    shard.segments.read_release(ss)
+            return {k: [int(x) for x in v] for k, v in res.items()}
+        found: dict[bytes, list[int]] = {}
+        for shard, mine in picked:  # backend without the fused call: scan through Shard.Read
             greatest = mine[-1]
             for term, values in shard.read(mine[0], None):
                 if greatest < term[:min(len(term), len(greatest))]:

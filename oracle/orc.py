@@ -174,6 +174,25 @@ def read_range(segs: list[FlatSegment], min_term: bytes | None = None,
         lib().orc_read_out_free(C.byref(out))
 
 
+def prefix_search(segs: list[FlatSegment], prefixes: list[bytes]) -> dict[bytes, list[int]]:
+    """The per-shard scan of InvertedIndex.PrefixSearch restated literally
+    (inverted_index.go:196 sort; :251 Read(prefixes[0], nil); :266-271 stop past the greatest
+    prefix; :274-279 HasPrefix test of every prefix, append; :289-292 sort + compact), over one
+    shard's segments.  Pure-Python loop over the oracle's read: small cases only."""
+    if not prefixes:
+        return {}
+    prefixes = sorted(prefixes)
+    greatest = prefixes[-1]
+    found: dict[bytes, list[int]] = {}
+    for term, values in read_range(segs, prefixes[0], None).items():
+        if greatest < term[:min(len(term), len(greatest))]:
+            break
+        for p in prefixes:
+            if term.startswith(p):
+                found.setdefault(p, []).extend(values)
+    return {k: sorted(set(v)) for k, v in found.items()}
+
+
 def shard_key(term: bytes) -> int:
     p, n, keep = _bytes_arg(term)
     return int(lib().orc_shard_key(p, n))

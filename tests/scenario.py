@@ -34,6 +34,9 @@ class OracleBackend:
     def read_range(self, segs, min_term, max_term):
         return self.orc.read_range(segs, min_term, max_term)
 
+    def prefix_search(self, segs, prefixes):
+        return self.orc.prefix_search(segs, prefixes)
+
 
 def run_steps(target, steps, is_index: bool):
     for cmd, arg in steps:

@@ -305,6 +305,49 @@ def test_read_keeps_empty_lists(engine, orc):
     assert_read_equal(got, orc.read_range([seg]))
 
 
+# ---------------------------------------------------------------- PrefixSearch vs oracle
+def _assert_prefix_equal(got, exp):
+    assert sorted(got) == sorted(exp)
+    for k in exp:
+        assert [int(x) for x in got[k]] == list(exp[k]), k
+
+
+def test_prefix_search_matches_oracle(engine, orc):
+    """ii2_prefix_search against the literal scan of inverted_index.go:239-292: prefixes of
+    every length (empty = everything, one byte, a whole term, longer than any term), absent
+    prefixes (omitted from the map), duplicates, unsorted input order."""
+    w = synth.make_workload(6000, 7, 90000, universe=1 << 16, seed=77)
+    t = lambda i: synth.term_at(w.term_bytes, w.term_off, i)
+    prefixes = [b"", b"a", b"Z", b"ab", t(10), t(10)[:5], t(4000)[:3], t(5999), t(0) + b"x",
+                b"zzzzzz", b"\x00", t(123)[:2], t(123)[:2], b"q", t(77) + b"~" * 40]
+    got = engine.prefix_search(w.segments, prefixes)
+    exp = orc.prefix_search(w.segments, prefixes)
+    assert b"" in exp and b"zzzzzz" not in exp
+    _assert_prefix_equal(got, exp)
+    # resident segments, one prefix per call
+    dsegs = [engine.upload(s) for s in w.segments]
+    for p in (b"", b"b", t(2000)[:4]):
+        _assert_prefix_equal(engine.prefix_search_dev(dsegs, [p]), orc.prefix_search(w.segments, [p]))
+
+
+def test_prefix_search_edge_cases(engine, orc):
+    """One segment with unsorted and duplicated values (the final sort + compact applies even
+    to a single source, unlike the merge's pass-through); a matching term with an empty list
+    still creates the key; no segments / no prefixes; values at the u32 limits."""
+    seg = FlatSegment.from_items([(b"aa", [9, 3, 3, 7]), (b"ab", []), (b"b", [0xFFFFFFFF, 0, 5]),
+                                  (b"ba", [5, 5, 1])])
+    for prefixes in ([b"a"], [b"ab"], [b"b", b"a", b"c"], [b"", b"ba"], []):
+        got = engine.prefix_search([seg], prefixes)
+        exp = orc.prefix_search([seg], prefixes)
+        _assert_prefix_equal(got, exp)
+    assert engine.prefix_search([seg], [b"ab"]) .keys() == {b"ab"}
+    assert engine.prefix_search([], [b"a"]) == {}
+    # a union far beyond one 4096-value sort tile (global bitonic stages)
+    w = synth.make_workload(3000, 5, 400000, universe=1 << 20, seed=5)
+    _assert_prefix_equal(engine.prefix_search(w.segments, [b""]),
+                         orc.prefix_search(w.segments, [b""]))
+
+
 # ---------------------------------------------------------------- device-resident API
 def test_resident_pipeline_and_multipass(engine, orc):
     """Resident segments; a result adopted as a segment and merged again equals the one-pass
