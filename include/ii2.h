@@ -262,6 +262,40 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
 int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, uint32_t** vals,
                     uint64_t* n);
 
+/* ---- <key>_fst term dictionaries: blevesearch/vellum v1 FST files ----------
+ * Host-side (no device work, usable without a GPU).  Replaces vellum.Open +
+ * fst.Iterator(min, nil) + the manual inclusive max bound of the reader
+ * (file/reader.go:139-155, :48-58) and vellum.New / Insert / Close of the writer
+ * (file/writer.go:35,43,62,104-129).  Format restated from the vellum module,
+ * which is not in the reference tree: bytes unverified against Go (see
+ * csrc/fst_v1.cpp). */
+typedef struct ii2_fst_terms {
+  uint64_t n_terms;    /* keys in [min,max]                                   */
+  uint8_t* term_bytes; /* ascending bytes.Compare order, 32 readable pad bytes */
+  uint32_t* term_off;  /* n_terms + 1                                          */
+  uint64_t* values;    /* FST outputs: `_val` byte offsets, or the posting itself
+                        * in direct mode (file/writer.go:35,43)                 */
+  uint64_t fst_len;    /* keys in the whole FST (its footer)                   */
+  void* _owner;
+} ii2_fst_terms;
+
+/* All keys k with min <= k <= max (NULL = open), with their outputs: what the
+ * reader's FST iterator yields.  The result plugs into ii2_seg_view as
+ * term_bytes / term_off / val_off (modes II2_SEG_VAL and II2_SEG_DIRECT). */
+int ii2_fst_read(const uint8_t* fst, uint64_t nbytes, const uint8_t* min, size_t minlen,
+                 const uint8_t* max, size_t maxlen, ii2_fst_terms* out);
+void ii2_fst_terms_free(ii2_fst_terms* out);
+/* fst.Get: *found = 0 if the key is absent. */
+int ii2_fst_get(const uint8_t* fst, uint64_t nbytes, const uint8_t* key, size_t keylen,
+                uint64_t* value, int* found);
+int ii2_fst_len(const uint8_t* fst, uint64_t nbytes, uint64_t* n_terms);
+/* vellum.New(w, nil) + Insert(term i, values[i]) for ascending, distinct terms
+ * + Close: the bytes of a `<key>_fst` file.  II2_ERR_INVALID if the terms are
+ * not strictly ascending (vellum.ErrOutOfOrder).  Free with ii2_fst_free. */
+int ii2_fst_build(const uint8_t* term_bytes, const uint32_t* term_off, const uint64_t* values,
+                  uint64_t n_terms, uint8_t** fst, uint64_t* nbytes);
+void ii2_fst_free(void* fst);
+
 /* ---- partitioning rule: shardKey (shard.go:362-378) ---------------------- */
 /* Returns the numeric shard key 0..1023 ((t[0]<<8 | t[1]) >> 6; 0 for terms
  * shorter than 2 bytes). Host-side helper, no device work. */

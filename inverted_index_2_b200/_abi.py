@@ -89,6 +89,17 @@ class PrefixOut(C.Structure):
     ]
 
 
+class FstTerms(C.Structure):
+    _fields_ = [
+        ("n_terms", C.c_uint64),
+        ("term_bytes", u8p),
+        ("term_off", u32p),
+        ("values", u64p),
+        ("fst_len", C.c_uint64),
+        ("_owner", C.c_void_p),
+    ]
+
+
 class ResultInfo(C.Structure):
     _fields_ = [
         ("terms_count", C.c_uint64),
@@ -159,6 +170,15 @@ PROTOTYPES = {
                                   C.POINTER(C.c_uint64)]),
     "ii2_bitmask_get": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(u32p),
                                   C.POINTER(C.c_uint64)]),
+    "ii2_fst_read": (C.c_int, [u8p, C.c_uint64, u8p, C.c_size_t, u8p, C.c_size_t,
+                               C.POINTER(FstTerms)]),
+    "ii2_fst_terms_free": (None, [C.POINTER(FstTerms)]),
+    "ii2_fst_get": (C.c_int, [u8p, C.c_uint64, u8p, C.c_size_t, C.POINTER(C.c_uint64),
+                              C.POINTER(C.c_int)]),
+    "ii2_fst_len": (C.c_int, [u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "ii2_fst_build": (C.c_int, [u8p, u32p, u64p, C.c_uint64, C.POINTER(u8p),
+                                C.POINTER(C.c_uint64)]),
+    "ii2_fst_free": (None, [C.c_void_p]),
     "ii2_shard_key": (C.c_uint32, [u8p, C.c_size_t]),
 }
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libii2.so")
 SOURCES = ["runtime.cu", "k3a_intcomp.cu", "k1_plan.cu", "k12_union.cu", "k6_emit.cu",
-           "k5_prefix.cu", "k3b_bitmask.cu", "api.cu"]
+           "k5_prefix.cu", "k3b_bitmask.cu", "api.cu", "fst_v1.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.splitext(os.path.basename(src))[0] + ".o")
         if force or _newer([src] + hdrs, obj):
             cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
             if verbose:

@@ -16,6 +16,7 @@ GPU.  There is no built-in CPU path.
 from __future__ import annotations
 
 import bisect
+import os
 import threading
 import time
 from typing import Iterator, Protocol
@@ -135,11 +136,35 @@ class Segments:
 class Shard:
     """shard.go: one term-prefix shard = a set of immutable segments + removed list."""
 
-    def __init__(self, key: str, backend: Backend):
+    def __init__(self, key: str, backend: Backend, basedir: str | None = None):
+        """basedir: the shard's directory of `<key>_fst` / `<key>_val` files (NewShard,
+        shard.go:300-358); existing segments are loaded, new ones are written there.  None keeps
+        the shard in memory only.  (removed.list persistence is gob, Go-side: out of scope.)"""
         self.key = key
         self.backend = backend
+        self.basedir = basedir
         self.segments = Segments()
         self.removed_list = RemovedLists()
+        if basedir is not None:
+            from . import files
+            os.makedirs(basedir, exist_ok=True)
+            for k in files.list_segments(basedir):  # shard.go:307-331
+                data = files.open_segment(basedir, k)
+                if data is None:
+                    continue
+                terms = data.terms()
+                self.segments.add(Segment(int(k), len(terms), terms[0], terms[-1], data))
+
+    def _persist(self, seg: "Segment") -> None:
+        if self.basedir is not None:
+            from . import files
+            files.write_segment(self.basedir, str(seg.key), seg.data)
+
+    def _unlink(self, segs: list["Segment"]) -> None:
+        if self.basedir is not None:
+            from . import files
+            for s in segs:
+                files.remove_segment(self.basedir, str(s.key))
 
     def get_key(self) -> str:
         return self.key
@@ -148,8 +173,10 @@ class Shard:
         """Shard.Put, shard.go:33-67: one direct-mode segment per ingested document."""
         terms = sorted(terms)
         data = FlatSegment.direct(terms, val)
-        self.segments.add(Segment(_unix_nano_key(), len(terms), terms[0] if terms else None,
-                                  terms[-1] if terms else None, data))
+        seg = Segment(_unix_nano_key(), len(terms), terms[0] if terms else None,
+                      terms[-1] if terms else None, data)
+        self._persist(seg)
+        self.segments.add(seg)
 
     def read(self, min_term: bytes | None = None, max_term: bytes | None = None
              ) -> Iterator[tuple[bytes, list[int]]]:
@@ -190,9 +217,12 @@ class Shard:
         removed = self.removed_list.values()
         res = self.backend.merge([s.data for s in chosen], removed)
         if res.terms_count > 0:  # lazy writer: nothing is written for an empty result
-            self.segments.add(Segment(_unix_nano_key(), res.terms_count, res.min_term,
-                                      res.max_term, res.to_segment()))
+            seg = Segment(_unix_nano_key(), res.terms_count, res.min_term, res.max_term,
+                          res.to_segment())
+            self._persist(seg)
+            self.segments.add(seg)
         self.segments.detach(chosen)
+        self._unlink(chosen)  # removeSegments, shard.go:232-242
         return len(chosen)
 
     def min_max(self) -> list[bytes | None]:
@@ -213,13 +243,21 @@ class Shard:
 class InvertedIndex:
     """inverted_index.go: router over term-prefix shards."""
 
-    def __init__(self, backend: Backend | None = None):
+    def __init__(self, backend: Backend | None = None, basedir: str | None = None):
+        """basedir: one sub-directory per shard key, each holding that shard's segment files
+        (NewInvertedIndex, inverted_index.go:342-378); existing shards are loaded."""
         if backend is None:
             from .engine import Engine  # the CUDA engine; raises if unavailable
             backend = Engine.default()
         self.backend = backend
+        self.basedir = basedir
         self.shards: list[Shard] = []  # sorted by key
         self.m = threading.RLock()
+        if basedir is not None:
+            os.makedirs(basedir, exist_ok=True)
+            for name in sorted(os.listdir(basedir)):
+                if os.path.isdir(os.path.join(basedir, name)):
+                    self.shards.append(Shard(name, backend, os.path.join(basedir, name)))
 
     def _find_shard(self, key: str) -> Shard | None:
         with self.m:
@@ -233,7 +271,8 @@ class InvertedIndex:
             i = bisect.bisect_left(keys, key)
             if i < len(keys) and keys[i] == key:
                 return self.shards[i]
-            sh = Shard(key, self.backend)
+            sh = Shard(key, self.backend,
+                       os.path.join(self.basedir, key) if self.basedir is not None else None)
             self.shards.insert(i, sh)
             return sh
 
