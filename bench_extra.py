@@ -2,6 +2,7 @@
 """bench_extra.py — the other BASELINE.json configurations, one JSON line each:
   C3  term-range read union across 256 segments with 5 % removed_list filtering (µs per call)
   C4  file/bitmask + intcomp encode/decode sweep, posting-list lengths 16 .. 16M
+  prefix  PrefixSearch batches over 64 resident segments (µs per call)
 bench.py stays the headline (C2 compaction); these lines are evidence for SURVEY §8 rows."""
 from __future__ import annotations
 
@@ -60,6 +61,31 @@ def c3(eng, a):
                     "postings_in_per_s": int(info.postings_in) / float(np.median(lat))})
     print(json.dumps({"config": "C3 range read, 256 segments, 5% removed (read + merge-style filter)",
                       "terms": a.terms, "postings": w.postings_in, "results": out}))
+
+
+def prefix(eng, a):
+    """PrefixSearch (inverted_index.go:192-295) as one ii2_prefix_search_dev call over resident
+    segments: batches of 16 prefixes of 3, 2 and 1 bytes, and the empty prefix (everything)."""
+    w = synth.make_workload(a.terms, 64, a.postings, seed=0xC2)
+    dsegs = [eng.upload(s) for s in w.segments]
+    n = len(w.term_off) - 1
+    rng = np.random.default_rng(6)
+    out = []
+    for plen, count in ((3, 16), (2, 16), (1, 16), (0, 1)):
+        picks = sorted({synth.term_at(w.term_bytes, w.term_off, int(i))[:plen]
+                        for i in rng.integers(0, n, size=count)})
+        res = None
+
+        def call():
+            nonlocal res
+            res = eng.prefix_search_dev(dsegs, picks)
+        med, worst = timed(call, 3)
+        out.append({"prefix_len": plen, "prefixes": len(picks),
+                    "values_out": int(sum(len(v) for v in res.values())),
+                    "median_us": 1e6 * med, "max_us": 1e6 * worst})
+    print(json.dumps({"config": "PrefixSearch over 64 resident segments (one C-ABI call per batch, "
+                                "results downloaded)", "terms": a.terms, "postings": w.postings_in,
+                      "results": out}))
 
 
 def c4(eng, a):
@@ -125,6 +151,8 @@ def main():
         c3(eng, a)
     if "c4" in a.which:
         c4(eng, a)
+    if "prefix" in a.which:
+        prefix(eng, a)
 
 
 if __name__ == "__main__":

@@ -34,6 +34,7 @@ constexpr int K1B_WARPS = K1B_THREADS / 32;
 constexpr uint32_t CAP_I = 1024;   // instances per sub-tile
 constexpr uint32_t K1B_HT = 2048;  // hash slots
 constexpr uint32_t REG_CAP = 256;  // values a warp sorts in registers
+constexpr uint32_t K1B_STAGE_CAP = CAP_I * 6;  // postings of a tile assembled in the 24 KB of key windows
 constexpr uint32_t K1B_SMALL_D = 64;  // distinct terms ranked by counting instead of sorting
 constexpr uint32_t K1B_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t K12_PENDING = 0xFFFFFFFFu;
@@ -94,6 +95,21 @@ __host__ __device__ inline size_t k1b_smem_bytes(int k) {
 #ifndef K1B_MIN_CTAS
 #define K1B_MIN_CTAS 4
 #endif
+// -DK1B_TIMING: warp 0 of every CTA adds the clock ticks it spent in each phase of a tile to
+// g_k1b_clk (read back with ii2_debug_k1b_clocks); profiling builds only.
+#ifdef K1B_TIMING
+__device__ unsigned long long g_k1b_clk[10];
+#define K1B_TICK(slot)                                        \
+  do {                                                        \
+    if (tid == 0) {                                           \
+      const long long now_ = clock64();                       \
+      atomicAdd(&g_k1b_clk[slot], (unsigned long long)(now_ - tick_)); \
+      tick_ = now_;                                           \
+    }                                                         \
+  } while (0)
+#else
+#define K1B_TICK(slot) do { } while (0)
+#endif
 __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(const K1bArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t s_ws64[K1B_WARPS + 2];
@@ -128,6 +144,9 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
 
   const uint32_t tid = threadIdx.x;
   const unsigned lane = lane_id(), warp = warp_id();
+#ifdef K1B_TIMING
+  long long tick_ = clock64();
+#endif
   const uint32_t b = a.bucket0 + blockIdx.x;
   uint32_t W = (uint32_t)(a.bk_pos[b + 1] - a.bk_pos[b]);
   if (W == 0) {
@@ -149,6 +168,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
   uint32_t pcount = 0;   // postings of light terms so far
   uint32_t ecount = 0;   // staging words so far
   __syncthreads();
+  K1B_TICK(0);  // bucket header: part rows, prefix loads
 
   while (W > 0) {
     // ---------------- choose the sub-tile [cur, mmp) ----------------
@@ -196,6 +216,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
       __syncthreads();
     }
 
+    K1B_TICK(1);  // tile choice (bisection of oversized buckets)
     // ---------------- (1) run starts; reset of the tile state ----------------
     if (k <= 128) {  // every warp scans for itself (identical values): no warp waits for another
       uint32_t v[4], sum = 0;
@@ -233,6 +254,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     if (tid == 0) s_nreps = 0;
     __syncthreads();
 
+    K1B_TICK(2);  // run starts, resets
     // bytes past the 24-byte window, only needed for terms longer than cpl+24
     auto tail_compare = [&](uint32_t x, uint32_t y) -> int {
       const uint32_t skip = cpl + 24;
@@ -293,6 +315,9 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
           p1[j] = __ldg(sd.poff + ix[j] + 1);
         }
       }
+      // (requesting the words of all four key windows before using any was measured slower,
+      // 1.61 vs 1.43 ms, like batching the source copies below: the phase is bound by the
+      // L1's handling of these 64-way scattered small reads, not by their latency)
 #pragma unroll
       for (int j = 0; j < PER; j++) {
         if (sg[j] >= 0) {
@@ -314,6 +339,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     // a thread's keys are visible to the block before it enters the hash table: whoever finds
     // its slot taken reads the owner's keys after the CAS
     __threadfence_block();
+    K1B_TICK(3);  // run search, offset loads, key windows (warp 0's own share)
 
     // ---------------- (3) group equal terms (hash table of representatives) ----------------
 #pragma unroll
@@ -358,7 +384,9 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
       og[j] = (rep << 20) |
               (atomicAdd(&cg[rep], (1u << 20) | (pl[j] > REG_CAP ? REG_CAP + 1 : pl[j])) & 0xFFFFFu);
     }
+    K1B_TICK(4);  // hash grouping (warp 0's own share)
     __syncthreads();
+    K1B_TICK(5);  // waiting for the other warps' keys + grouping
     const uint32_t D = s_nreps;
 
     // ---------------- (4) order the distinct terms; one record per term ----------------
@@ -449,12 +477,45 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
       }
     }
     __syncthreads();
+    K1B_TICK(6);  // ranking + records
 
     // ---------------- (5) sources of every term ---------------------------------------------
     // light terms: the postings themselves, copied into the term's slot (any order: the union
-    // sorts; a single-source term is one copy, order kept); heavy terms: (pointer, length)
+    // sorts; a single-source term is one copy, order kept); heavy terms: (pointer, length).
+    // A source lands in the middle of its term's slot, so stored straight to global memory the
+    // lanes of a warp hit 32 different lines per store (ncu: the LSU data pipe is the busiest
+    // unit of this kernel, 60 % of its wavefront peak, a third of it these stores).  The slots of
+    // one tile are contiguous in the bucket's gather region: the tile is assembled in shared
+    // memory (the key windows are dead by now) and written out as one coalesced stream.
     // (requesting the first values of all four sources before storing any was measured
-    // slower: 1.59 vs 1.44 ms — more loads in flight only thrash the L1)
+    // slower: 1.59 vs 1.44 ms)
+    const uint32_t tile_p = s_tot[0];
+#ifdef K1B_NO_STAGE
+    const bool staged = false;
+#else
+    const bool staged = tile_p <= K1B_STAGE_CAP;
+#endif
+    uint32_t* const stage = reinterpret_cast<uint32_t*>(key_hi);  // key_hi | key_lo | key_x
+    auto copy_source = [](const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n) {
+      uint32_t t = 0;
+#pragma unroll 1
+      for (; t + 4 <= n; t += 4) {  // loads first: four in flight per thread
+        const uint32_t x0 = __ldg(src + t), x1 = __ldg(src + t + 1), x2 = __ldg(src + t + 2),
+                       x3 = __ldg(src + t + 3);
+        dst[t] = x0;
+        dst[t + 1] = x1;
+        dst[t + 2] = x2;
+        dst[t + 3] = x3;
+      }
+      if (t < n) {
+        const uint32_t x0 = __ldg(src + t);
+        const uint32_t x1 = t + 1 < n ? __ldg(src + t + 1) : 0u;
+        const uint32_t x2 = t + 2 < n ? __ldg(src + t + 2) : 0u;
+        dst[t] = x0;
+        if (t + 1 < n) dst[t + 1] = x1;
+        if (t + 2 < n) dst[t + 2] = x2;
+      }
+    };
 #pragma unroll
     for (int j = 0; j < PER; j++) {
       const uint32_t i = tid + j * K1B_THREADS;
@@ -462,27 +523,12 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
         const uint32_t g = og[j] >> 20;
         const uint32_t pb = pbase[g];
         if (pb != K1B_HEAVY) {
-          const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(pp[j]);
-          uint32_t* __restrict__ dst = gath + pb + (og[j] & 0xFFFFFu);
-          const uint32_t n = pl[j];
-          uint32_t t = 0;
-#pragma unroll 1
-          for (; t + 4 <= n; t += 4) {  // loads first: four in flight per thread
-            const uint32_t x0 = __ldg(src + t), x1 = __ldg(src + t + 1), x2 = __ldg(src + t + 2),
-                           x3 = __ldg(src + t + 3);
-            dst[t] = x0;
-            dst[t + 1] = x1;
-            dst[t + 2] = x2;
-            dst[t + 3] = x3;
-          }
-          if (t < n) {
-            const uint32_t x0 = __ldg(src + t);
-            const uint32_t x1 = t + 1 < n ? __ldg(src + t + 1) : 0u;
-            const uint32_t x2 = t + 2 < n ? __ldg(src + t + 2) : 0u;
-            dst[t] = x0;
-            if (t + 1 < n) dst[t + 1] = x1;
-            if (t + 2 < n) dst[t + 2] = x2;
-          }
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(pp[j]);
+          const uint32_t at = pb + (og[j] & 0xFFFFFu);
+          if (staged)
+            copy_source(src, stage + (at - pcount), pl[j]);
+          else
+            copy_source(src, gath + at, pl[j]);
         } else {
           const uint32_t at = sbase[g] + ((atomicSub(&cg[g], 1u << 20) >> 20) - 1u);
           a.src_ptr[at] = pp[j];
@@ -490,6 +536,24 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
         }
       }
     }
+    K1B_TICK(7);  // source copies (warp 0's own share)
+    if (staged) {
+      __syncthreads();
+      K1B_TICK(8);  // waiting for the other warps' copies
+      uint32_t* const out = gath + pcount;
+      // head up to the first 16-byte boundary of the destination, then 128-bit stores
+      const uint32_t head = min(tile_p, (uint32_t)((16u - ((uintptr_t)out & 15u)) & 15u) >> 2);
+      if (tid < head) out[tid] = stage[tid];
+      const uint32_t nvec = (tile_p - head) >> 2;
+      for (uint32_t v = tid; v < nvec; v += K1B_THREADS) {
+        const uint32_t e = head + 4 * v;
+        *reinterpret_cast<uint4*>(out + e) =
+            make_uint4(stage[e], stage[e + 1], stage[e + 2], stage[e + 3]);
+      }
+      const uint32_t tail0 = head + 4 * nvec;
+      if (tail0 + tid < tile_p) out[tail0 + tid] = stage[tail0 + tid];
+    }
+    K1B_TICK(9);  // coalesced write-out of the tile
     dcount += D;
     icount += size;
     pcount += s_tot[0];
@@ -1206,6 +1270,18 @@ int k2_large_run(LargeArgs la, uint32_t h_nl, DevBuf<uint32_t>& large_tmp,
   II2_CUDA_TRY(cudaStreamSynchronize(s));  // keeps `offs` alive until its copy is done
   return II2_OK;
 }
+
+#ifdef K1B_TIMING
+extern "C" int ii2_debug_k1b_clocks(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_k1b_clk, sizeof(g_k1b_clk));
+  if (reset) {
+    unsigned long long z[10] = {0};
+    cudaMemcpyToSymbol(g_k1b_clk, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // ---------------------------------------------------------------- host driver
 int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool want_enc,
