@@ -80,9 +80,13 @@ def prefix(eng, a):
             nonlocal res
             res = eng.prefix_search_dev(dsegs, picks)
         med, worst = timed(call, 3)
+        eng.prof_enable(True)
+        call()
+        phases = {p["name"]: round(1e3 * p["ms"] / max(1, p["count"]), 1) for p in eng.prof_read()}
+        eng.prof_enable(False)
         out.append({"prefix_len": plen, "prefixes": len(picks),
                     "values_out": int(sum(len(v) for v in res.values())),
-                    "median_us": 1e6 * med, "max_us": 1e6 * worst})
+                    "median_us": 1e6 * med, "max_us": 1e6 * worst, "phase_us": phases})
     print(json.dumps({"config": "PrefixSearch over 64 resident segments (one C-ABI call per batch, "
                                 "results downloaded)", "terms": a.terms, "postings": w.postings_in,
                       "results": out}))

@@ -1026,11 +1026,20 @@ __global__ void __launch_bounds__(256) k2_large_len(const LargeArgs a, uint32_t 
   if (lane_id() == 0) a.len[g] = L;
 }
 
+__global__ void __launch_bounds__(256)
+k2_large_counts(const LargeArgs a, uint32_t n, uint32_t* __restrict__ c) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) c[g] = a.gin[a.rec[g]].c;
+}
+
 // gather: grid (x = CTAs per group, y = group)
-__global__ void __launch_bounds__(256) k2_large_gather(const LargeArgs a) {
+// bitmap != null: instead of copying, set the bit of every value (bitmap path of group g0)
+__global__ void __launch_bounds__(256)
+k2_large_gather(const LargeArgs a, uint32_t* __restrict__ bitmap, uint32_t g0) {
   __shared__ uint64_t s_moff[kMaxSegs + 1];
   __shared__ uint64_t s_ws[256 / 32 + 2];
-  const uint32_t g = blockIdx.y;
+  const uint32_t g = bitmap ? g0 : blockIdx.y;
+  if (!bitmap && a.presorted && a.presorted[g]) return;  // set straight from the sources
   const uint32_t c = a.gin[a.rec[g]].c, beg = a.gin[a.rec[g]].src;
   uint64_t run = 0;
   for (uint32_t base = 0; base < c; base += 256) {
@@ -1055,7 +1064,11 @@ __global__ void __launch_bounds__(256) k2_large_gather(const LargeArgs a) {
         hi = mid;
     }
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src_ptr[beg + lo]);
-    dst[e] = __ldg(src + (e - s_moff[lo]));
+    const uint32_t x = __ldg(src + (e - s_moff[lo]));
+    if (bitmap)
+      atomicOr(&bitmap[x >> 5], 1u << (x & 31u));
+    else
+      dst[e] = x;
   }
 }
 
@@ -1065,6 +1078,7 @@ constexpr uint32_t LG_TILE = 4096;
 __global__ void __launch_bounds__(512) k2_large_tile_sort(const LargeArgs a) {
   __shared__ uint32_t tile[LG_TILE];
   if (a.gin[a.rec[blockIdx.y]].c == 1 && !a.always_sort) return;  // single source: passes through unsorted (Q4)
+  if (a.presorted && a.presorted[blockIdx.y]) return;
   const uint64_t n = a.len[blockIdx.y];
   uint32_t* base = a.tmp + a.off[blockIdx.y];
   for (uint64_t t0 = (uint64_t)blockIdx.x * LG_TILE; t0 < n; t0 += (uint64_t)gridDim.x * LG_TILE) {
@@ -1083,6 +1097,7 @@ __global__ void __launch_bounds__(512) k2_large_tile_sort(const LargeArgs a) {
 __global__ void __launch_bounds__(256) k2_large_stage(const LargeArgs a, uint64_t kk, uint64_t j) {
   const uint64_t n = a.len[blockIdx.y];
   if ((kk >> 1) >= n || (a.gin[a.rec[blockIdx.y]].c == 1 && !a.always_sort)) return;  // sorted / pass-through
+  if (a.presorted && a.presorted[blockIdx.y]) return;
   uint32_t* v = a.tmp + a.off[blockIdx.y];
   const uint64_t half = j ? j : (kk >> 1);
   const uint64_t limit = (n + 1) / 2 + half;
@@ -1111,6 +1126,7 @@ __global__ void __launch_bounds__(512) k2_large_tile_merge(const LargeArgs a, ui
   __shared__ uint32_t tile[LG_TILE];
   const uint64_t n = a.len[blockIdx.y];
   if ((kk >> 1) >= n || (a.gin[a.rec[blockIdx.y]].c == 1 && !a.always_sort)) return;
+  if (a.presorted && a.presorted[blockIdx.y]) return;
   uint32_t* base = a.tmp + a.off[blockIdx.y];
   for (uint64_t t0 = (uint64_t)blockIdx.x * LG_TILE; t0 < n; t0 += (uint64_t)gridDim.x * LG_TILE) {
     const uint32_t m = (uint32_t)((n - t0) < LG_TILE ? (n - t0) : LG_TILE);
@@ -1135,6 +1151,68 @@ __global__ void __launch_bounds__(512) k2_large_tile_merge(const LargeArgs a, ui
   }
 }
 
+// ---- very long unions over a dense id range: bitmap instead of a sort ------------------------
+// A union of n values whose largest id is M costs O(n log^2 n) on the bitonic path; when M is
+// not much larger than n (a stop-word term, a short prefix: most ids of the universe are hit)
+// setting one bit per value in an M-bit map (L2-resident up to a few hundred MB... 2 MiB for a
+// 2^24 universe) and reading the map back in order is the sorted-unique union in O(n + M/32).
+constexpr uint64_t BM_MIN_VALUES = 1ull << 16;  // shorter unions stay on the sort path
+constexpr uint32_t BM_CHUNK_WORDS = 32;         // one warp expands 1024 bits
+
+__global__ void __launch_bounds__(256)
+k2_bm_max(const LargeArgs a, uint32_t g, uint32_t* __restrict__ out) {
+  const GroupIn gi = a.gin[a.rec[g]];
+  uint32_t m = 0;
+  // one warp per source at a time; the sources of a group are few and long here
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + warp_id(); j < gi.c; j += warps) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src_ptr[gi.src + j]);
+    const uint32_t n = a.src_len[gi.src + j];
+    for (uint32_t e = lane_id(); e < n; e += 32) m = max(m, __ldg(src + e));
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if (lane_id() == 0 && m) atomicMax(out, m);
+}
+
+// counts[c] = set bits of chunk c (32 words); counts[n_chunks] = 0 for the scan
+// (the removed filter is applied here, on whole words, when the removed set has its own bitmap)
+__global__ void __launch_bounds__(256)
+k2_bm_count(uint32_t* __restrict__ bitmap, uint64_t words, uint64_t n_chunks,
+            uint64_t* __restrict__ counts, const RemovedSet rem) {
+  const uint64_t c = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (c > n_chunks) return;
+  const uint64_t w = c * BM_CHUNK_WORDS + lane_id();
+  uint32_t x = (c < n_chunks && w < words) ? bitmap[w] : 0u;
+  if (x && rem.bitmap && (w << 5) < rem.bitmap_bits) {  // bitmap_bits is a multiple of 32
+    x &= ~__ldg(rem.bitmap + w);
+    bitmap[w] = x;
+  }
+  const uint32_t tot = __reduce_add_sync(0xffffffffu, __popc(x));
+  if (lane_id() == 0) counts[c] = tot;
+}
+
+// the set bits of chunk c, ascending, to out[pos[c] ...); the last warp records the total
+__global__ void __launch_bounds__(256)
+k2_bm_expand(const uint32_t* __restrict__ bitmap, uint64_t words, uint64_t n_chunks,
+             const uint64_t* __restrict__ pos, uint32_t* __restrict__ out,
+             uint64_t* __restrict__ len_out) {
+  const uint64_t c = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (c >= n_chunks) return;
+  const unsigned lane = lane_id();
+  const uint64_t w = c * BM_CHUNK_WORDS + lane;
+  uint32_t x = w < words ? bitmap[w] : 0u;
+  const uint32_t cnt = __popc(x);
+  const uint32_t inc = warp_inclusive_scan(cnt);
+  uint32_t* dst = out + pos[c] + (inc - cnt);
+  const uint32_t base = (uint32_t)(w << 5);
+  while (x) {
+    const uint32_t b = __ffs(x) - 1;
+    x &= x - 1;
+    *dst++ = base + b;
+  }
+  if (c + 1 == n_chunks && lane == 31) *len_out = pos[c] + inc;
+}
+
 // one CTA per heavy group: in-place dedup + filter, encode, record, bucket totals
 __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
   __shared__ uint64_t s_ws[1024 / 32 + 2];
@@ -1145,7 +1223,10 @@ __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
   const bool single = a.gin[a.rec[g]].c == 1 && !a.always_sort;  // pass-through: duplicates stay
   uint32_t* v = a.tmp + a.off[g];
   uint64_t outn = 0;
-  for (uint64_t e0 = 0; e0 < n; e0 += 1024) {
+  // bitmap path: already sorted, deduped and (when the removed set has a bitmap) filtered
+  const bool done = a.presorted && a.presorted[g] && (a.rem.n == 0 || a.rem.bitmap != nullptr);
+  if (done) outn = n;
+  for (uint64_t e0 = 0; e0 < n && !done; e0 += 1024) {
     const uint64_t e = e0 + threadIdx.x;
     const bool valid = e < n;
     const uint32_t x = valid ? v[e] : 0u;
@@ -1237,6 +1318,52 @@ int k2_large_run(LargeArgs la, uint32_t h_nl, DevBuf<uint32_t>& large_tmp,
   if (want_enc) II2_TRY(large_enc.alloc_scratch(etotal, s));
   la.tmp = large_tmp.p;
   la.enc = large_enc.p;
+  // which groups take the bitmap path: long, sortable, and dense enough (map words <= 4 n)
+  std::vector<uint8_t> h_pre(h_nl, 0);
+  std::vector<uint32_t> h_max(h_nl, 0);
+  DevBuf<uint8_t> d_pre;
+  DevBuf<uint32_t> d_max, bm_words;
+  DevBuf<uint64_t> bm_counts;
+  la.presorted = nullptr;
+  {
+    std::vector<uint32_t> cand;
+    for (uint32_t i = 0; i < h_nl; i++)
+      if (lens[i] >= BM_MIN_VALUES) cand.push_back(i);
+    if (!cand.empty()) {
+      std::vector<uint32_t> h_c(h_nl);
+      II2_TRY(d_max.alloc_scratch(h_nl, s));
+      II2_CUDA_TRY(cudaMemsetAsync(d_max.p, 0, (size_t)h_nl * 4, s));
+      for (uint32_t i : cand) {
+        k2_bm_max<<<148, 256, 0, s>>>(la, i, d_max.p + i);
+        II2_LAUNCHED();
+      }
+      II2_CUDA_TRY(cudaMemcpyAsync(h_max.data(), d_max.p, (size_t)h_nl * 4, cudaMemcpyDeviceToHost, s));
+      // single-source groups pass through unsorted unless always_sort: read their source counts
+      DevBuf<uint32_t> d_c;
+      II2_TRY(d_c.alloc_scratch(h_nl, s));
+      k2_large_counts<<<div_up(h_nl, 256), 256, 0, s>>>(la, h_nl, d_c.p);
+      II2_LAUNCHED();
+      II2_CUDA_TRY(cudaMemcpyAsync(h_c.data(), d_c.p, (size_t)h_nl * 4, cudaMemcpyDeviceToHost, s));
+      II2_CUDA_TRY(cudaStreamSynchronize(s));
+      uint64_t max_words = 0;
+      bool any = false;
+      for (uint32_t i : cand) {
+        const uint64_t words = ((uint64_t)h_max[i] >> 5) + 1;
+        if ((h_c[i] > 1 || la.always_sort) && words <= 4 * lens[i]) {
+          h_pre[i] = 1;
+          any = true;
+          max_words = std::max(max_words, words);
+        }
+      }
+      if (any) {
+        II2_TRY(d_pre.alloc_scratch(h_nl, s));
+        II2_CUDA_TRY(cudaMemcpyAsync(d_pre.p, h_pre.data(), h_nl, cudaMemcpyHostToDevice, s));
+        II2_TRY(bm_words.alloc_scratch(max_words + BM_CHUNK_WORDS, s));
+        II2_TRY(bm_counts.alloc_scratch((max_words + BM_CHUNK_WORDS - 1) / BM_CHUNK_WORDS + 2, s));
+        la.presorted = d_pre.p;
+      }
+    }
+  }
   II2_CUDA_TRY(cudaMemcpyAsync(d_off.p, offs.data(), 2 * (size_t)h_nl * 8, cudaMemcpyHostToDevice, s));
   for (uint32_t y0 = 0; y0 < h_nl; y0 += 32768) {  // grid.y limit
     const uint32_t ny = std::min<uint32_t>(32768, h_nl - y0);
@@ -1244,14 +1371,39 @@ int k2_large_run(LargeArgs la, uint32_t h_nl, DevBuf<uint32_t>& large_tmp,
     for (uint32_t i = 0; i < ny; i++) maxL = std::max(maxL, lens[y0 + i]);
     LargeArgs b2 = la;
     b2.rec += y0;
+    if (b2.presorted) b2.presorted += y0;
     if (b2.bucket) b2.bucket += y0;
     b2.len += y0;
     b2.off += y0;
     b2.eoff += y0;
     const unsigned gx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((maxL + 4095) / 4096, 2048));
     dim3 grid(gx, ny);
-    k2_large_gather<<<grid, 256, 0, s>>>(b2);
+    k2_large_gather<<<grid, 256, 0, s>>>(b2, nullptr, 0);
     II2_LAUNCHED();
+    // dense long unions: bitmap path, one group after the other (they are few)
+    uint64_t maxS = 0;  // longest union left to the sort path
+    for (uint32_t i = 0; i < ny; i++) {
+      const uint32_t g = y0 + i;
+      if (!h_pre[g]) {
+        maxS = std::max(maxS, lens[g]);
+        continue;
+      }
+      const uint64_t words = ((uint64_t)h_max[g] >> 5) + 1;
+      const uint64_t n_chunks = (words + BM_CHUNK_WORDS - 1) / BM_CHUNK_WORDS;
+      II2_CUDA_TRY(cudaMemsetAsync(bm_words.p, 0, words * 4, s));
+      k2_large_gather<<<(unsigned)std::min<uint64_t>((lens[g] + 255) / 256, 148 * 16), 256, 0, s>>>(
+          b2, bm_words.p, i);
+      II2_LAUNCHED();
+      k2_bm_count<<<div_up((n_chunks + 1) * 32, 256), 256, 0, s>>>(bm_words.p, words, n_chunks,
+                                                                   bm_counts.p, la.rem);
+      II2_LAUNCHED();
+      II2_TRY(exclusive_scan_u64(bm_counts.p, n_chunks + 1, nullptr, s));
+      k2_bm_expand<<<div_up(n_chunks * 32, 256), 256, 0, s>>>(bm_words.p, words, n_chunks,
+                                                              bm_counts.p, la.tmp + offs[g],
+                                                              d_len.p + g);
+      II2_LAUNCHED();
+    }
+    maxL = maxS;
     k2_large_tile_sort<<<grid, 512, 0, s>>>(b2);
     II2_LAUNCHED();
     for (uint64_t kk = 2ull * LG_TILE; (kk >> 1) < maxL; kk <<= 1) {
@@ -1396,6 +1548,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     la.want_enc = want_enc ? 1 : 0;
     la.keep_empty = keep_empty ? 1 : 0;
     la.always_sort = 0;
+    la.presorted = nullptr;
     la.bk_raw = u.bk_raw.p;
     la.nb1 = B + 1;
     II2_TRY(k2_large_run(la, h_nl, u.large_tmp, u.large_enc, s));

@@ -173,6 +173,7 @@ int k5_prefix_search(const SegDesc* d_segs, int k, const uint8_t* d_pbytes, cons
   la.want_enc = 0;
   la.keep_empty = 1;
   la.always_sort = 1;
+  la.presorted = nullptr;
   la.bk_raw = nullptr;
   la.nb1 = 0;
   DevBuf<uint32_t> tmp, enc;

@@ -44,6 +44,7 @@ struct LargeArgs {
   RemovedSet rem;
   int want_enc, keep_empty;
   int always_sort;         // sort + dedup single-source groups too (prefix search)
+  const uint8_t* presorted;  // [n] groups already sorted + deduped by the bitmap path, or null
   uint64_t* bk_raw;        // per-bucket totals to add to, or null
   uint32_t nb1;
 };

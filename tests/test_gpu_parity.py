@@ -187,7 +187,8 @@ def test_merge_long_and_similar_terms(engine, orc):
 
 def test_heavy_terms_multi_cta_union(engine, orc):
     """Lists far larger than one CTA's shared memory (survey §7 hard part 2): the global
-    bitonic path; also a heavy single-source list."""
+    bitonic path, the bitmap path of long dense unions ("heavy": 350k values below 2^20), heavy
+    single-source lists (pass-through, survey Q4) and a long sparse union."""
     rng = np.random.default_rng(9)
     segs = []
     for s in range(6):
@@ -196,6 +197,10 @@ def test_heavy_terms_multi_cta_union(engine, orc):
                  (b"small%d" % s, [s, s + 1])]
         if s == 0:
             items.append((b"solo_heavy", rng.integers(0, 1 << 20, size=50000).tolist()))
+        if s == 1:  # long, dense, ONE source: passes through unsorted, never the bitmap path
+            items.append((b"solo_dense", rng.integers(0, 1 << 18, size=70000).tolist()))
+        if s >= 4:  # long but sparse over the whole u32 range: stays on the sort path
+            items.append((b"sparse", rng.integers(0, 1 << 32, size=40000, dtype=np.uint64).tolist()))
         segs.append(FlatSegment.from_items(sorted(items)))
     removed = np.unique(rng.integers(0, 1 << 20, size=50000)).astype(np.uint32)
     assert_merge_equal(engine.merge(segs, removed, decoded=True),
