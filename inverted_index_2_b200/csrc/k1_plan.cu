@@ -228,6 +228,174 @@ k1_partition_chunks(const SegDesc* __restrict__ segs, int k, const uint32_t* __r
   }
 }
 
+// crank[c] = splitters <= the term just before chunk c (0 for the first chunk of a segment):
+// chunk c then owns the splitters [crank[c], crank[c+1]) (all the rest for a segment's last
+// chunk).  One thread per chunk: 16 dependent probes each, all chunks in parallel — inside the
+// partition kernel the same two searches kept a whole CTA waiting at its barrier.
+__global__ void __launch_bounds__(256)
+k1_chunk_ranks(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ cbase,
+               uint32_t n_chunks, uint32_t S, SampleArrays sp, uint32_t* __restrict__ crank) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  int lo = 0, hi = k;  // segment of chunk c: last s with cbase[s] <= c
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cbase[mid + 1] <= c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const SegDesc sd = segs[lo];
+  const uint32_t ci = c - cbase[lo];
+  uint32_t r = 0;
+  if (ci != 0 && sd.hi > sd.lo) {
+    const KeyedTerm t = keyed_term(sd, sd.lo + ci * K1_CHUNK - 1);
+    uint32_t a = 0, b = S;  // first splitter > t
+    while (a < b) {
+      const uint32_t mid = (a + b) >> 1;
+      if (keyed_compare(sample_term(sp, mid), t) <= 0)
+        a = mid + 1;
+      else
+        b = mid;
+    }
+    r = a;
+  }
+  crank[c] = r;
+}
+
+// The same partition with the chunk staged RAW: the chunk's offsets and term bytes are two
+// contiguous pieces of the segment, copied into shared memory with coalesced word loads (every
+// byte of the dictionary still read exactly once, but by ~38 independent coalesced loads per
+// thread instead of 16 offset loads + 40 scattered key-window loads), and only the few splitters
+// that fall inside the chunk build key windows — from shared memory, during their search.
+constexpr uint32_t K1_RAW_BYTES = 38 * 1024;  // term bytes of a chunk (avg 14.5 B x 2048 = 30 KB)
+
+__device__ __forceinline__ void smem_key16(const uint32_t* __restrict__ raw, uint32_t a, uint32_t len,
+                                           uint64_t& hi, uint64_t& lo) {
+  // raw = words of the staged bytes, a = byte offset of the term inside them (window at byte 0)
+  if (len == 0) {
+    hi = lo = 0;
+    return;
+  }
+  const uint32_t* wp = raw + (a >> 2);
+  const uint32_t sh = (a & 3u) * 8u;
+  const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+  const uint32_t x0 = __byte_perm(__funnelshift_r(w0, w1, sh), 0, 0x0123);
+  const uint32_t x1 = __byte_perm(__funnelshift_r(w1, w2, sh), 0, 0x0123);
+  const uint32_t x2 = __byte_perm(__funnelshift_r(w2, w3, sh), 0, 0x0123);
+  const uint32_t x3 = __byte_perm(__funnelshift_r(w3, w4, sh), 0, 0x0123);
+  hi = ((uint64_t)x0 << 32) | x1;
+  lo = ((uint64_t)x2 << 32) | x3;
+  if (len < 16) {
+    if (len <= 8) {
+      lo = 0;
+      if (len < 8) hi &= ~0ull << (8 * (8 - len));
+    } else {
+      lo &= ~0ull << (8 * (16 - len));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ cbase,
+                        uint32_t S, SampleArrays sp, const uint32_t* __restrict__ crank,
+                        uint32_t* __restrict__ part) {
+  extern __shared__ __align__(16) uint32_t k1_smem[];
+  uint32_t* s_off = k1_smem;                  // [K1_CHUNK + 1] term offsets of the chunk
+  uint32_t* s_raw = k1_smem + K1_CHUNK + 4;   // staged term bytes (+ 8 words of slack)
+  __shared__ uint32_t s_range[2];
+  const uint32_t c = blockIdx.x;
+  int lo = 0, hi = k;  // segment of chunk c: last s with cbase[s] <= c
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cbase[mid + 1] <= c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const int s = lo;
+  const SegDesc sd = segs[s];
+  const uint32_t nchunks = cbase[s + 1] - cbase[s], ci = c - cbase[s];
+  const uint32_t i0 = sd.lo + ci * K1_CHUNK;
+  const uint32_t i1 = (ci + 1 == nchunks) ? sd.hi : i0 + K1_CHUNK;
+  const uint32_t n = i1 - i0;
+  // start of the staged bytes: 16-byte aligned ADDRESS when the buffer allows it (128-bit loads)
+  const uint32_t t0 = __ldg(sd.toff + i0), b1 = __ldg(sd.toff + i1);
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(sd.tb + t0) & 15u);
+  const bool wide = mis <= t0;
+  const uint32_t b0 = wide ? t0 - mis : (t0 & ~3u);
+  const uint32_t words = (b1 - b0 + 3u) >> 2;
+  const bool staged = words * 4u + 16u <= K1_RAW_BYTES;
+  {
+    constexpr int PER = K1_CHUNK / 256;
+    uint32_t o[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const uint32_t t = threadIdx.x + j * 256;
+      o[j] = t <= n ? __ldg(sd.toff + i0 + t) : 0u;
+    }
+    if (threadIdx.x == 0) s_off[n] = b1;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const uint32_t t = threadIdx.x + j * 256;
+      if (t < n) s_off[t] = o[j];
+    }
+  }
+  if (staged) {
+    if (wide) {
+      const uint4* src = reinterpret_cast<const uint4*>(sd.tb + b0);
+      uint4* dst = reinterpret_cast<uint4*>(s_raw);
+      const uint32_t quads = (words + 3u) >> 2;
+#pragma unroll 4
+      for (uint32_t q = threadIdx.x; q < quads; q += 256) dst[q] = __ldg(src + q);
+    } else {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(sd.tb + b0);
+#pragma unroll 8
+      for (uint32_t q = threadIdx.x; q < words; q += 256) s_raw[q] = __ldg(src + q);
+    }
+  }
+  if (threadIdx.x < 2 && ci == 0) {
+    const bool first = threadIdx.x == 0;
+    part[(uint64_t)(first ? 0 : S + 1) * k + s] = first ? sd.lo : sd.hi;
+  }
+  if (threadIdx.x == 0) {
+    s_range[0] = crank[c];
+    s_range[1] = ci + 1 == nchunks ? S : crank[c + 1];
+  }
+  __syncthreads();
+  const uint32_t ra = s_range[0], rb = s_range[1];
+  for (uint32_t r = ra + threadIdx.x; r < rb; r += 256) {
+    const KeyedTerm x = sample_term(sp, r);
+    uint32_t a = 0, b = n;  // first term of the chunk >= x
+    while (a < b) {
+      const uint32_t mid = (a + b) >> 1;
+      KeyedTerm t;
+      const uint32_t o = s_off[mid];
+      t.len = s_off[mid + 1] - o;
+      if (staged)
+        smem_key16(s_raw, o - b0, t.len, t.hi, t.lo);
+      else
+        load_key16(sd.tb, o, t.len, 0, t.hi, t.lo);
+      int cmp;
+      if (t.hi != x.hi) {
+        cmp = t.hi < x.hi ? -1 : 1;
+      } else if (t.lo != x.lo) {
+        cmp = t.lo < x.lo ? -1 : 1;
+      } else if (t.len > 16 && x.len > 16) {
+        t.p = sd.tb + o;
+        cmp = term_compare(t.p + 16, t.len - 16, x.p + 16, x.len - 16);
+      } else {
+        cmp = t.len < x.len ? -1 : (t.len > x.len ? 1 : 0);
+      }
+      if (cmp < 0)
+        a = mid + 1;
+      else
+        b = mid;
+    }
+    part[(uint64_t)(r + 1) * k + s] = i0 + a;
+  }
+}
+
 // One warp per bucket.  raw[0][b] = instances, raw[1][b] = input postings, raw[2][b] = staging
 // words (upper bound).
 __global__ void __launch_bounds__(256)
@@ -336,7 +504,26 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     k1_rank_samples<<<div_up((uint64_t)S * 32, 256), 256, 0, s>>>(k, d_sbase, S, sa, sp);
     II2_LAUNCHED();
   }
-  k1_partition_chunks<<<n_chunks, 256, 0, s>>>(plan.segs, k, d_cbase, S, sp, plan.part.p);
+  // II2_PARTITION_KEYS=1: the first version of the kernel (key windows of every term staged)
+  static const bool old_partition = getenv("II2_PARTITION_KEYS") != nullptr;
+  if (old_partition) {
+    k1_partition_chunks<<<n_chunks, 256, 0, s>>>(plan.segs, k, d_cbase, S, sp, plan.part.p);
+  } else {
+    constexpr size_t smem = (K1_CHUNK + 4 + 8) * 4 + K1_RAW_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+      II2_CUDA_TRY(cudaFuncSetAttribute(k1_partition_chunks_raw,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    DevBuf<uint32_t> crank;
+    II2_TRY(crank.alloc_scratch((size_t)n_chunks + 1, s));
+    k1_chunk_ranks<<<div_up(n_chunks, 256), 256, 0, s>>>(plan.segs, k, d_cbase, n_chunks, S, sp,
+                                                          crank.p);
+    II2_LAUNCHED();
+    k1_partition_chunks_raw<<<n_chunks, 256, smem, s>>>(plan.segs, k, d_cbase, S, sp, crank.p,
+                                                        plan.part.p);
+  }
   II2_LAUNCHED();
   k1_bucket_stats<<<div_up((uint64_t)(B + 1) * 32, 256), 256, 0, s>>>(
       plan.segs, k, S, sp, plan.part.p, plan.bk_WP.p, plan.bk_cpl.p);
