@@ -280,19 +280,26 @@ def run_ours(a):
     t_in = w.term_instances
     t_in_bytes = int(sum(int(s.term_off[-1]) for s in w.segments))
     n_groups = int(prof_terms) if (prof_terms := stats[2]) else 0  # distinct terms ~ terms out
-    k1b_bytes = (t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 12 * t_in
-                 + 32 * n_groups)
-    k2b_bytes = 32 * n_groups + 12 * t_in + 4 * n_in + 4 * len(w.removed) + 32 * n_groups + val_size
+    # K1b (grouping): term bytes, term and posting offsets and the postings themselves in (the
+    # sources of every term are copied into its gather slot), gather slots + a 32 B record per
+    # distinct term out
+    k1b_bytes = (t_in_bytes + 4 * (t_in + a.segments) + 8 * (t_in + a.segments) + 4 * n_in
+                 + 4 * n_in + 32 * n_groups)
+    # K2b (union + dedup + filter + encode): records + gather slots + the removed bitmap in,
+    # records + the `_val` staging stream out
+    k2b_bytes = 32 * n_groups + 4 * n_in + len(w.removed) // 8 + 32 * n_groups + val_size
     alg = {
-        # K1b (grouping: term bytes + term/posting offsets in; a 12 B source entry per instance
-        # and a 32 B record per distinct term out) and K2b (records + source entries + postings
-        # in; records + the `_val` stream out) run as one two-stream pipeline over bucket chunks
-        "k12_group_union": k1b_bytes + k2b_bytes,
         "k1b_group": k1b_bytes,
         "k2b_union": k2b_bytes,
         # K6: records + staged `_val` words + surviving term bytes in; the new segment out
         "k6_emit": 32 * n_groups + val_size + t_out_bytes + val_size + t_out_bytes + 12 * t_out,
     }
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture
+    # of this command (profiles/r01b_ncu_full_metrics.csv); only valid for the default workload
+    ncu_traffic = {"k1b_group": 1273.5e6 + 447.8e6, "k2b_union": 493.8e6 + 306.3e6,
+                   "k6_emit": 516.8e6 + 271.9e6}
+    default_workload = (a.terms, a.segments, a.postings, a.removed_frac) == \
+        (1_000_000, 64, 100_000_000, 0.05) and world == 1
     peak, peak_src = peaks()
     roof = None
     if prof:
@@ -302,7 +309,10 @@ def run_ours(a):
         if b is not None and per_launch_ms > 0:
             ach = b / (per_launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_traffic.get(top["name"]) if default_workload else None,
+                    "traffic_source": "ncu --set full, profiles/r01b_ncu_full_metrics.csv",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms}
     pipeline_bytes = synth.algorithmic_bytes(n_in, n_out, t_in, t_in_bytes, a.segments, t_out,
                                              t_out_bytes, len(w.removed))

@@ -127,7 +127,7 @@ k1_rank_samples(int k, const uint32_t* __restrict__ sbase, uint32_t S, SampleArr
 // searches over the sorted splitter array, and each of them is located in the staged keys.
 // part row r+1 = lower_bound of splitter r in every segment; row 0 / S+1 = window starts / ends.
 #ifndef K1_CHUNK_TERMS
-#define K1_CHUNK_TERMS 2048
+#define K1_CHUNK_TERMS 1024
 #endif
 constexpr uint32_t K1_CHUNK = K1_CHUNK_TERMS;
 
@@ -268,7 +268,7 @@ k1_chunk_ranks(const SegDesc* __restrict__ segs, int k, const uint32_t* __restri
 // byte of the dictionary still read exactly once, but by ~38 independent coalesced loads per
 // thread instead of 16 offset loads + 40 scattered key-window loads), and only the few splitters
 // that fall inside the chunk build key windows — from shared memory, during their search.
-constexpr uint32_t K1_RAW_BYTES = 38 * 1024;  // term bytes of a chunk (avg 14.5 B x 2048 = 30 KB)
+constexpr uint32_t K1_RAW_BYTES = K1_CHUNK * 19;  // term bytes of a chunk (14.5 B per term on average in C2)
 
 __device__ __forceinline__ void smem_key16(const uint32_t* __restrict__ raw, uint32_t a, uint32_t len,
                                            uint64_t& hi, uint64_t& lo) {

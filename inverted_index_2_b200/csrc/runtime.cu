@@ -360,24 +360,41 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(uint64_t* __restric
   }
 }
 
-// m arrays of length n laid out back to back, each scanned independently by its own CTA:
-// every thread owns a contiguous chunk (sum, block scan of the sums, second pass writes).
+// m arrays of length n laid out back to back, each scanned independently by its own CTA.
+// Every WARP owns a contiguous 1/32 of the array and walks it 32 elements at a time (coalesced
+// loads, four tiles requested ahead, shuffle scan, running total in a register — no block
+// barrier inside the loops); the 32 warp totals are scanned once, then each warp adds its base.
+// (The first version gave every thread a contiguous chunk: 2 x 41 strided dependent loads per
+// thread, 48 us per launch at n = 41 k.)
 __global__ void __launch_bounds__(1024) k_scan_multi(const uint64_t* a, uint64_t* out, uint64_t n,
                                                      uint64_t* __restrict__ totals) {
   __shared__ uint64_t ws[1024 / 32 + 2];
   const uint64_t* arr = a + (uint64_t)blockIdx.x * n;
   uint64_t* dst = out + (uint64_t)blockIdx.x * n;
-  const uint64_t chunk = (n + 1023) / 1024;
-  const uint64_t lo = threadIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
-  uint64_t sum = 0;
-  for (uint64_t i = lo; i < hi; i++) sum += arr[i];
-  uint64_t total;
-  uint64_t ex = block_exclusive_scan(sum, ws, total);
-  for (uint64_t i = lo; i < hi; i++) {
-    const uint64_t v = arr[i];
-    dst[i] = ex;
-    ex += v;
+  const unsigned lane = lane_id(), w = warp_id();
+  const uint64_t per_warp = ((n + 31) / 32 + 31) & ~31ull;  // multiple of 32: aligned tiles
+  const uint64_t lo = w * per_warp, hi = lo + per_warp < n ? lo + per_warp : n;
+  uint64_t run = 0;
+  for (uint64_t base = lo; base < hi; base += 128) {
+    uint64_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint64_t i = base + 32 * q + lane;
+      v[q] = i < hi ? arr[i] : 0ull;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint64_t inc = warp_inclusive_scan(v[q]);
+      const uint64_t i = base + 32 * q + lane;
+      if (i < hi) dst[i] = run + inc - v[q];
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
   }
+  uint64_t total;
+  const uint64_t wbase = block_exclusive_scan<uint64_t>(lane == 0 ? run : (uint64_t)0, ws, total);
+  const uint64_t add = __shfl_sync(0xffffffffu, wbase, 0);
+  if (add)
+    for (uint64_t i = lo + lane; i < hi; i += 32) dst[i] += add;
   if (threadIdx.x == 0 && totals) totals[blockIdx.x] = total;
 }
 
