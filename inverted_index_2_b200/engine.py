@@ -314,15 +314,21 @@ class Engine:
         return blob, off
 
     def _prefix_result(self, prefixes: list[bytes], out: A.PrefixOut) -> dict[bytes, np.ndarray]:
-        try:
-            n = int(out.n_prefixes)
-            off = A.from_ptr(out.value_off, n + 1, np.uint64)
-            vals = A.from_ptr(out.values, int(off[-1]) if n else 0, np.uint32)
-            matched = A.from_ptr(out.matched, n, np.uint8)
-            return {p: vals[int(off[i]):int(off[i + 1])] for i, p in enumerate(prefixes)
-                    if matched[i]}
-        finally:
-            self.lib.ii2_prefix_out_free(C.byref(out))
+        """Zero-copy: the returned arrays are views of the library's pinned result buffer, which
+        is released (ii2_prefix_out_free) when the last view is garbage collected."""
+        import weakref
+        n = int(out.n_prefixes)
+        off = A.from_ptr(out.value_off, n + 1, np.uint64)
+        matched = A.from_ptr(out.matched, n, np.uint8)
+        total = int(off[-1]) if n else 0
+        lib = self.lib
+        if total == 0:
+            lib.ii2_prefix_out_free(C.byref(out))
+            empty = np.zeros(0, dtype=np.uint32)
+            return {p: empty for i, p in enumerate(prefixes) if matched[i]}
+        vals = np.ctypeslib.as_array(out.values, shape=(total,))
+        weakref.finalize(vals, lambda o=out: lib.ii2_prefix_out_free(C.byref(o)))
+        return {p: vals[int(off[i]):int(off[i + 1])] for i, p in enumerate(prefixes) if matched[i]}
 
     def prefix_search(self, segs: list[FlatSegment], prefixes: list[bytes]
                       ) -> dict[bytes, np.ndarray]:
