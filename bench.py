@@ -434,6 +434,20 @@ def run_ours(a):
 
 def main():
     a = parse()
+    # exactly ONE line on stdout: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there when NCCL_DEBUG is set) are pointed at stderr for the duration of the
+    # run; the JSON line goes to the real stdout
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    global print
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001 - only the JSON lines are printed in this module
+        kw.setdefault("file", out)
+        _print(*args, **kw)
+        out.flush()
     if a.impl == "reference":
         run_reference(a)
     else:
