@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """bench_extra.py — the other BASELINE.json configurations, one JSON line each:
+  C1  4 x Put(all terms) + Merge as one ii2_ingest call (device sort of every document)
   C3  term-range read union across 256 segments with 5 % removed_list filtering (µs per call)
   C4  file/bitmask + intcomp encode/decode sweep, posting-list lengths 16 .. 16M
   prefix  PrefixSearch batches over 64 resident segments (µs per call)
@@ -92,6 +93,40 @@ def prefix(eng, a):
                       "results": out}))
 
 
+def c1(eng, a):
+    """BASELINE configs[0] shape through ii2_ingest: 4 x Put(all terms, val = 1..4) + Merge as
+    ONE call — every document's terms are handed over SHUFFLED (Put sorts them, shard.go:34)."""
+    tb, off = synth.make_terms(a.terms)
+    raw = tb.tobytes()
+    terms = [raw[int(off[i]):int(off[i + 1])] for i in range(a.terms)]
+    rng = np.random.default_rng(1)
+    docs = []
+    for val in (1, 2, 3, 4):
+        perm = rng.permutation(a.terms)
+        docs.append(([terms[int(i)] for i in perm], val))
+    res = None
+
+    def call():
+        nonlocal res
+        res = eng.ingest(docs, None, decoded=True)
+    t0 = time.perf_counter()
+    call()
+    first = time.perf_counter() - t0
+    eng.prof_enable(True)
+    t0 = time.perf_counter()
+    call()
+    second = time.perf_counter() - t0
+    phases = {p["name"]: round(p["ms"] / max(1, p["count"]), 2) for p in eng.prof_read()}
+    eng.prof_enable(False)
+    ok = (res.terms_count == a.terms and np.array_equal(res.term_bytes, tb)
+          and np.array_equal(res.post, np.tile(np.array([1, 2, 3, 4], dtype=np.uint32), a.terms)))
+    print(json.dumps({"config": "C1 ingest: 4 documents x all terms (shuffled), one ii2_ingest call "
+                                "(ctypes marshalling of 4 x %d Python terms included)" % a.terms,
+                      "terms": a.terms, "postings": 4 * a.terms, "first_call_ms": 1e3 * first,
+                      "call_ms": 1e3 * second, "device_phase_ms": phases,
+                      "result_is_every_term_to_1234": bool(ok)}))
+
+
 def c4(eng, a):
     from oracle import orc  # checker only
     rows = []
@@ -151,6 +186,8 @@ def main():
     a = ap.parse_args()
     from inverted_index_2_b200.engine import Engine
     eng = Engine(0)
+    if "c1" in a.which:
+        c1(eng, a)
     if "c3" in a.which:
         c3(eng, a)
     if "c4" in a.which:

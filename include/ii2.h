@@ -146,6 +146,23 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
               uint64_t nrem, uint32_t flags, ii2_merge_out* out);
 void ii2_merge_out_free(ii2_merge_out* out);
 
+/* ---- ingest batching: replaces D calls of Shard.Put (shard.go:33-67) and the
+ *      Shard.Merge that later folds their segments ---------------------------- */
+typedef struct ii2_doc_view {
+  uint64_t n_terms;
+  const uint8_t* term_bytes; /* the document's terms in ANY order: Put sorts them (shard.go:34) */
+  const uint32_t* term_off;  /* n_terms + 1 */
+  uint32_t value;            /* every term of the document maps to [value] (shard.go:47)     */
+} ii2_doc_view;
+
+/* The segment that Put(docs[0]) .. Put(docs[n-1]) followed by one Merge of the
+ * resulting direct-mode segments produces: terms sorted on the device (one
+ * segmented sort over all documents), a term repeated inside a document kept
+ * once, then the same pipeline as ii2_merge (union per term, removed filter,
+ * intcomp `_val` stream, FST outputs).  At most 1024 documents per call. */
+int ii2_ingest(const ii2_doc_view* docs, int ndocs, const uint32_t* removed_sorted,
+               uint64_t nrem, uint32_t flags, ii2_merge_out* out);
+
 /* ---- term-range read: replaces shard.go:253-278 + the iterator pulls ----- */
 typedef struct ii2_read_out {
   uint64_t n_terms;

@@ -79,6 +79,15 @@ class ReadOut(C.Structure):
     ]
 
 
+class DocView(C.Structure):
+    _fields_ = [
+        ("n_terms", C.c_uint64),
+        ("term_bytes", u8p),
+        ("term_off", u32p),
+        ("value", C.c_uint32),
+    ]
+
+
 class PrefixOut(C.Structure):
     _fields_ = [
         ("n_prefixes", C.c_uint64),
@@ -137,6 +146,8 @@ PROTOTYPES = {
     "ii2_merge": (C.c_int, [C.POINTER(SegView), C.c_int, u32p, C.c_uint64, C.c_uint32,
                             C.POINTER(MergeOut)]),
     "ii2_merge_out_free": (None, [C.POINTER(MergeOut)]),
+    "ii2_ingest": (C.c_int, [C.POINTER(DocView), C.c_int, u32p, C.c_uint64, C.c_uint32,
+                             C.POINTER(MergeOut)]),
     "ii2_read_range": (C.c_int, [C.POINTER(SegView), C.c_int, u8p, C.c_size_t, u8p, C.c_size_t,
                                  u32p, C.c_uint64, C.POINTER(ReadOut)]),
     "ii2_read_out_free": (None, [C.POINTER(ReadOut)]),

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "codec.cuh"
+#include "ingest.cuh"
 #include "prefix.cuh"
 #include "union.cuh"
 
@@ -771,6 +772,122 @@ void ii2_prefix_out_free(ii2_prefix_out* o) {
   if (!o) return;
   delete static_cast<HostOwner*>(o->_owner);
   memset(o, 0, sizeof(*o));
+}
+
+// ------------------------------------------------------------------ ingest batching
+static int ingest_impl(const ii2_doc_view* docs, int ndocs, const uint32_t* removed_sorted,
+                       uint64_t nrem, uint32_t flags, ii2_merge_out* out, cudaStream_t s) {
+  if (ndocs > kMaxSegs) {
+    set_last_error("%d documents in one call (max %d per pass)", ndocs, kMaxSegs);
+    return II2_ERR_UNSUPPORTED;
+  }
+  uint64_t N = 0, TB = 0;
+  for (int d = 0; d < ndocs; d++) {
+    const ii2_doc_view& v = docs[d];
+    if (v.n_terms && (!v.term_off || !v.term_bytes)) return II2_ERR_INVALID;
+    N += v.n_terms;
+    if (v.n_terms) {
+      if (v.term_off[v.n_terms] < v.term_off[0]) return II2_ERR_INVALID;
+      TB += v.term_off[v.n_terms] - v.term_off[0];
+    }
+  }
+  if (N >= (1ull << 32) || TB >= (1ull << 32)) {
+    set_last_error("ingest batch of %llu terms / %llu term bytes (max 2^32-1)",
+                   (unsigned long long)N, (unsigned long long)TB);
+    return II2_ERR_UNSUPPORTED;
+  }
+  // offsets rebased to one concatenated buffer, document starts and values: one pinned block
+  const size_t off_bytes = ((size_t)N + 1) * 4, doff_bytes = ((size_t)ndocs + 1) * 8;
+  const size_t stage_bytes = off_bytes + 8 + doff_bytes + (size_t)ndocs * 4 + 64;
+  struct PinnedBlock {
+    void* p = nullptr;
+    ~PinnedBlock() { pinned_free(p); }
+  } stage;
+  stage.p = pinned_alloc(stage_bytes);
+  if (!stage.p) return II2_ERR_NOMEM;
+  uint64_t* h_doff = static_cast<uint64_t*>(stage.p);
+  uint32_t* h_vals = reinterpret_cast<uint32_t*>(h_doff + ndocs + 1);
+  uint32_t* h_off = h_vals + ndocs + (ndocs & 1);
+  DevBuf<uint8_t> d_tb;
+  II2_TRY(d_tb.alloc_scratch((size_t)TB, s, 32));
+  uint64_t n = 0, b = 0;
+  for (int d = 0; d < ndocs; d++) {
+    const ii2_doc_view& v = docs[d];
+    h_doff[d] = n;
+    h_vals[d] = v.value;
+    if (!v.n_terms) continue;
+    const uint32_t first = v.term_off[0];
+    uint32_t max_len = 0;
+    for (uint64_t i = 0; i < v.n_terms; i++) {
+      if (v.term_off[i + 1] < v.term_off[i]) return II2_ERR_INVALID;
+      max_len = std::max(max_len, v.term_off[i + 1] - v.term_off[i]);
+      h_off[n + i] = (uint32_t)(b + (v.term_off[i] - first));
+    }
+    if (max_len > 65535) {
+      set_last_error("term of %u bytes (max 65535)", max_len);
+      return II2_ERR_UNSUPPORTED;
+    }
+    const uint64_t nb = v.term_off[v.n_terms] - first;
+    if (nb)
+      II2_CUDA_TRY(cudaMemcpyAsync(d_tb.p + b, v.term_bytes + first, nb, cudaMemcpyHostToDevice, s));
+    n += v.n_terms;
+    b += nb;
+  }
+  h_doff[ndocs] = n;
+  h_off[N] = (uint32_t)TB;
+  II2_CUDA_TRY(cudaMemsetAsync(d_tb.p + TB, 0, 32, s));
+  DevBuf<uint8_t> d_stage;
+  II2_TRY(d_stage.alloc_scratch(stage_bytes, s, 32));
+  II2_CUDA_TRY(cudaMemcpyAsync(d_stage.p, stage.p, stage_bytes, cudaMemcpyHostToDevice, s));
+  const uint64_t* d_doff = reinterpret_cast<const uint64_t*>(d_stage.p);
+  const uint32_t* d_vals = reinterpret_cast<const uint32_t*>(d_doff + ndocs + 1);
+  const uint32_t* d_off = d_vals + ndocs + (ndocs & 1);
+  IngestOut io;
+  II2_TRY(k7_ingest_sort(d_tb.p, d_off, d_doff, h_doff, d_vals, ndocs, N, TB, io, s));
+  // the documents as resident direct-mode segments: views into the shared buffers
+  std::vector<std::unique_ptr<ii2_seg>> owned;
+  std::vector<ii2_seg*> list;
+  auto view = [](auto& buf, auto* p, size_t cnt) {
+    buf.p = p;
+    buf.n = cnt;
+    buf.scratch = true;  // not owned: never freed through this handle
+  };
+  for (int d = 0; d < ndocs; d++) {
+    const uint64_t f = io.first[d], nt = io.first[d + 1] - f;
+    std::unique_ptr<ii2_seg> g(new ii2_seg());
+    g->n_terms = (uint32_t)nt;
+    g->n_post = nt;
+    g->term_bytes_len = io.n_bytes;
+    view(g->tb, io.tb.p, (size_t)io.n_bytes);
+    view(g->toff, io.toff.p + f, (size_t)nt + 1);
+    view(g->post, io.post.p, (size_t)io.n_terms);
+    view(g->poff, io.poff.p + f, (size_t)nt + 1);
+    list.push_back(g.get());
+    owned.push_back(std::move(g));
+  }
+  ii2_removed* rem = nullptr;
+  if (nrem) II2_TRY(ii2_removed_upload(removed_sorted, nrem, &rem));
+  std::unique_ptr<ii2_removed> rem_guard(rem);
+  ii2_result* res = nullptr;
+  II2_TRY(run_pipeline_impl(list.data(), ndocs, nullptr, 0, false, nullptr, 0, false, rem,
+                            (flags & II2_MERGE_WANT_DECODED) != 0, true, true, false, &res, s));
+  std::unique_ptr<ii2_result> res_guard(res);
+  return ii2_result_download_merge(res, flags, out);
+}
+
+int ii2_ingest(const ii2_doc_view* docs, int ndocs, const uint32_t* removed_sorted, uint64_t nrem,
+               uint32_t flags, ii2_merge_out* out) {
+  if (!out || ndocs < 0 || (ndocs && !docs) || (nrem && !removed_sorted)) return II2_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  II2_TRY(ctx_require());
+  cudaStream_t s = cur_stream();
+  const int rc = ingest_impl(docs, ndocs, removed_sorted, nrem, flags, out, s);
+  if (rc != II2_OK) {
+    cudaStreamSynchronize(s);
+    memset(out, 0, sizeof(*out));
+  }
+  arena_reset(s);
+  return rc;
 }
 
 void ii2_merge_out_free(ii2_merge_out* o) {

@@ -304,6 +304,33 @@ class Engine:
                     "read_range_dev")
         return DeviceResult(self, h.value)
 
+    # ---- ingest batching (Shard.Put x D + Shard.Merge as one call) ----------------------------
+    def ingest(self, docs: list[tuple[list[bytes], int]], removed=None, decoded: bool = False
+               ) -> MergeResult:
+        """docs: (terms in any order, value) per document; returns the merged segment."""
+        arr = (A.DocView * max(1, len(docs)))()
+        keep = []
+        for i, (terms, val) in enumerate(docs):
+            off = np.zeros(len(terms) + 1, dtype=np.uint32)
+            if terms:
+                off[1:] = np.cumsum([len(t) for t in terms])
+            blob = np.frombuffer(b"".join(terms) + b"\0", dtype=np.uint8).copy()
+            keep.append((off, blob))
+            arr[i].n_terms = len(terms)
+            arr[i].term_bytes = A.np_ptr(blob, A.u8p)
+            arr[i].term_off = A.np_ptr(off, A.u32p)
+            arr[i].value = int(val)
+        r = np.ascontiguousarray(removed if removed is not None else [], dtype=np.uint32)
+        out = A.MergeOut()
+        self._check(self.lib.ii2_ingest(arr, len(docs),
+                                        A.np_ptr(r, A.u32p) if len(r) else C.cast(None, A.u32p),
+                                        len(r), A.II2_MERGE_WANT_DECODED if decoded else 0,
+                                        C.byref(out)), "ingest")
+        try:
+            return MergeResult.from_c(out, decoded)
+        finally:
+            self.lib.ii2_merge_out_free(C.byref(out))
+
     # ---- PrefixSearch (inverted_index.go:192-295) ----------------------------------------
     @staticmethod
     def _prefix_args(prefixes: list[bytes]):

@@ -178,6 +178,20 @@ class Shard:
         self._persist(seg)
         self.segments.add(seg)
 
+    def put_batch(self, docs: list[tuple[list[bytes], int]]) -> None:
+        """Extension: Put for every document of the batch followed by one
+        Merge of exactly those documents, as ONE C-ABI call (ii2_ingest) that leaves one full
+        segment instead of len(docs) direct-mode ones.  Needs a backend with `ingest`."""
+        docs = [(list(t), int(v)) for t, v in docs if len(t)]
+        for i in range(0, len(docs), 1024):
+            chunk = docs[i:i + 1024]
+            res = self.backend.ingest(chunk, self.removed_list.values())
+            if res.terms_count > 0:
+                seg = Segment(_unix_nano_key(), res.terms_count, res.min_term, res.max_term,
+                              res.to_segment())
+                self._persist(seg)
+                self.segments.add(seg)
+
     def read(self, min_term: bytes | None = None, max_term: bytes | None = None
              ) -> Iterator[tuple[bytes, list[int]]]:
         """Shard.Read, shard.go:72-75: union over ALL segments, [min,max] inclusive.
@@ -284,6 +298,19 @@ class InvertedIndex:
         for key in sorted(groups):
             shard = self._find_shard(key) or self._new_shard(key)
             shard.put(groups[key], val)
+
+    def put_batch(self, docs: list[tuple[list[bytes], int]]) -> None:
+        """Extension: a batch of documents routed by shard key, one ii2_ingest per shard."""
+        per_shard: dict[str, list[tuple[list[bytes], int]]] = {}
+        for terms, val in docs:
+            groups: dict[str, list[bytes]] = {}
+            for t in terms:
+                groups.setdefault(shard_key(t), []).append(t)
+            for key, ts in groups.items():
+                per_shard.setdefault(key, []).append((ts, val))
+        for key in sorted(per_shard):
+            shard = self._find_shard(key) or self._new_shard(key)
+            shard.put_batch(per_shard[key])
 
     def put_removed(self, values) -> None:
         """InvertedIndex.PutRemoved, inverted_index.go:41-55: every shard gets the batch."""

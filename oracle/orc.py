@@ -174,6 +174,14 @@ def read_range(segs: list[FlatSegment], min_term: bytes | None = None,
         lib().orc_read_out_free(C.byref(out))
 
 
+def ingest(docs: list[tuple[list[bytes], int]], removed=None, decoded: bool = True) -> MergeResult:
+    """Shard.Put for every document (shard.go:33-67: terms sorted, one direct-mode segment whose
+    every term carries the document's value; a term repeated inside a document is one FST key)
+    followed by ONE Shard.Merge of those segments (shard.go:158-212)."""
+    segs = [FlatSegment.direct(sorted(set(terms)), val) for terms, val in docs]
+    return merge(segs, removed, decoded)
+
+
 def prefix_search(segs: list[FlatSegment], prefixes: list[bytes]) -> dict[bytes, list[int]]:
     """The per-shard scan of InvertedIndex.PrefixSearch restated literally
     (inverted_index.go:196 sort; :251 Read(prefixes[0], nil); :266-271 stop past the greatest

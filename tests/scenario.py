@@ -37,6 +37,9 @@ class OracleBackend:
     def prefix_search(self, segs, prefixes):
         return self.orc.prefix_search(segs, prefixes)
 
+    def ingest(self, docs, removed):
+        return self.orc.ingest(docs, removed=np.asarray(removed, dtype=np.uint32), decoded=False)
+
 
 def run_steps(target, steps, is_index: bool):
     for cmd, arg in steps:

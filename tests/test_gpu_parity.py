@@ -390,6 +390,56 @@ def test_index_on_disk_with_engine(engine, tmp_path):
     assert list(again.read(None, None)) == [(b"aaaa", [2])]  # inverted_index_test.go:59-82
 
 
+# ---------------------------------------------------------------- ingest batching
+def _random_docs(rng, n_docs, vocab, lo, hi):
+    docs = []
+    for d in range(n_docs):
+        n = int(rng.integers(lo, hi + 1))
+        pick = rng.integers(0, len(vocab), size=n)
+        docs.append(([vocab[int(i)] for i in pick], int(rng.integers(0, 1 << 20))))
+    return docs
+
+
+def test_ingest_matches_put_then_merge(engine, orc):
+    """ii2_ingest = Put x D + one Merge (oracle chain): unsorted terms, terms repeated inside a
+    document, documents sharing terms and values, an empty document, terms that agree on their
+    first 16 / 32 bytes, a document far larger than one 2048-record sort tile, removed filter."""
+    rng = np.random.default_rng(17)
+    tb, off = synth.make_terms(3000, seed=5)
+    base = [synth.term_at(tb, off, i) for i in range(3000)]
+    long_ = [b"shared-prefix-of-sixteen+" + b"x" * int(k % 23) + bytes([65 + k % 7]) for k in range(200)]
+    vocab = base + long_ + [b"", b"a", b"ab", b"abc"]
+    docs = _random_docs(rng, 40, vocab, 0, 300)
+    docs.append(([], 7))
+    docs.append((list(vocab) + list(reversed(vocab)), 99))       # every term twice, 6400+ records
+    docs.append(([b"zz", b"zz", b"zz"], 5))
+    removed = np.unique(rng.integers(0, 1 << 20, size=2000)).astype(np.uint32)
+    for rem in (None, removed):
+        got = engine.ingest(docs, rem, decoded=True)
+        exp = orc.ingest(docs, rem, decoded=True)
+        assert_merge_equal(got, exp)
+    # a value removed everywhere: nothing left
+    only = [([b"t1", b"t0"], 3), ([b"t1"], 3)]
+    assert engine.ingest(only, np.array([3], dtype=np.uint32)).terms_count == 0
+    assert engine.ingest([], None).terms_count == 0
+    assert engine.ingest(only, None, decoded=True).as_dict() == {b"t0": [3], b"t1": [3]}
+
+
+def test_put_batch_on_host_mirror(engine, orc):
+    from inverted_index_2_b200.host import InvertedIndex
+    from scenario import OracleBackend
+    rng = np.random.default_rng(23)
+    tb, off = synth.make_terms(500, seed=9)
+    vocab = [synth.term_at(tb, off, i) for i in range(500)]
+    docs = [(t, v) for t, v in _random_docs(rng, 30, vocab, 1, 60)]
+    a, b, c = InvertedIndex(engine), InvertedIndex(OracleBackend(orc)), InvertedIndex(engine)
+    a.put_batch(docs)
+    b.put_batch(docs)
+    for terms, val in docs:
+        c.put(terms, val)
+    assert list(a.read(None, None)) == list(b.read(None, None)) == list(c.read(None, None))
+
+
 # ---------------------------------------------------------------- device-resident API
 def test_resident_pipeline_and_multipass(engine, orc):
     """Resident segments; a result adopted as a segment and merged again equals the one-pass
