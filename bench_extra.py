@@ -56,7 +56,13 @@ def c3(eng, a):
                 r.release()
             med, _ = timed(call, 3)
             lat.append(med)
-        out.append({"range_frac": frac, "terms": int(info.terms_count),
+        eng.prof_enable(True)
+        call()
+        phases = {p["name"]: round(1e3 * p["ms"] / max(1, p["count"]), 1) for p in eng.prof_read()}
+        host = {p["name"]: round(1e3 * p["host_ms"] / max(1, p["count"]), 1) for p in eng.prof_read()}
+        eng.prof_enable(False)
+        out.append({"range_frac": frac, "terms": int(info.terms_count), "phase_us": phases,
+                    "host_us": host,
                     "postings_in": int(info.postings_in), "postings_out": int(info.postings_out),
                     "median_us": 1e6 * float(np.median(lat)), "p99_us": 1e6 * float(np.max(lat)),
                     "postings_in_per_s": int(info.postings_in) / float(np.median(lat))})

@@ -29,7 +29,10 @@
 
 namespace ii2 {
 
-constexpr int K1B_THREADS = 256;
+#ifndef K1B_THREADS_N
+#define K1B_THREADS_N 256
+#endif
+constexpr int K1B_THREADS = K1B_THREADS_N;  // a tile holds CAP_I instances: CAP_I / K1B_THREADS per thread
 constexpr int K1B_WARPS = K1B_THREADS / 32;
 constexpr uint32_t CAP_I = 1024;   // instances per sub-tile
 constexpr uint32_t K1B_HT = 2048;  // hash slots
@@ -246,9 +249,8 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
       }
       for (uint32_t s2 = k + tid; s2 <= kp2; s2 += K1B_THREADS) rstart[s2] = size;
     }
-    static_assert(K1B_HT * 4 == K1B_THREADS * 32, "two 16-byte stores per thread reset the table");
-    reinterpret_cast<uint4*>(table)[tid] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    reinterpret_cast<uint4*>(table)[tid + K1B_THREADS] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (uint32_t i = tid; i < K1B_HT / 4; i += K1B_THREADS)
+      reinterpret_cast<uint4*>(table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     for (uint32_t i = 4 * tid; i < CAP_I; i += 4 * K1B_THREADS)
       *reinterpret_cast<uint4*>(cg + i) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_nreps = 0;
@@ -858,7 +860,10 @@ __device__ __forceinline__ uint32_t encode_shared_warp(const uint32_t* v, uint32
 }
 
 // ---------------------------------------------------------------- K2b: two terms per warp
-constexpr int K2B_THREADS = 128;
+#ifndef K2B_THREADS_N
+#define K2B_THREADS_N 128
+#endif
+constexpr int K2B_THREADS = K2B_THREADS_N;
 constexpr int K2B_WARPS = K2B_THREADS / 32;
 constexpr uint32_t K2B_HALF = 128;  // a 16-lane group handles terms of fewer values than this
 constexpr uint32_t K2B_ENC_WORDS = 3 + 2 * 129 + 1 + (5 * 127 + 3) / 4 + 1;  // enc_bound(255)
