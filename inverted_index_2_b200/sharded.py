@@ -98,6 +98,11 @@ class ShardedIndex:
         if mine:
             self.local.put(mine, val)
 
+    def put_batch(self, docs: list[tuple[list[bytes], int]]) -> None:
+        """Batched ingest (ii2_ingest per shard): every rank keeps the terms of its own shards."""
+        mine = [([t for t in terms if self._mine(t)], val) for terms, val in docs]
+        self.local.put_batch([(t, v) for t, v in mine if t])
+
     def put_removed(self, values) -> None:
         self.local.put_removed(values)  # tombstones go to every shard (inverted_index.go:41-55)
 

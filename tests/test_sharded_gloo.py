@@ -57,8 +57,11 @@ def _worker(rank, world, port, q):
     lo, hi = vocab[50], vocab[300]
     part = idx.read(lo, hi)
     pref = idx.prefix_search([b"a", b"te", b"Zz"])
+    batched = sharded.ShardedIndex(OracleBackend(orc), bounds, rank)
+    batched.put_batch(docs)  # one ingest call per shard instead of one Put per document
+    full_b = batched.read(None, None)
     if rank == 0:
-        q.put((merged, full.items(), part.items(), pref, bounds.tolist()))
+        q.put((merged, full.items(), part.items(), pref, bounds.tolist(), full_b.items()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,7 +74,7 @@ def test_world2_matches_single_process(orc):
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    merged, full, part, pref, bounds = q.get(timeout=240)
+    merged, full, part, pref, bounds, full_b = q.get(timeout=240)
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert 0 < bounds[1] < sharded.N_SHARD_KEYS and merged > 0
@@ -85,6 +88,10 @@ def test_world2_matches_single_process(orc):
     assert full == list(single.read(None, None))
     assert part == list(single.read(vocab[50], vocab[300]))
     assert pref == single.prefix_search([b"a", b"te", b"Zz"])
+    plain = InvertedIndex(OracleBackend(orc))
+    for terms, val in docs:
+        plain.put(terms, val)
+    assert full_b == list(plain.read(None, None))
     # removed values are gone after the merge, and the order is the shard-key order
     assert all(3 not in v and 7 not in v for _, v in full)
     keys = [shard_key(t) for t, _ in full]
