@@ -313,6 +313,25 @@ int ii2_fst_build(const uint8_t* term_bytes, const uint32_t* term_off, const uin
                   uint64_t n_terms, uint8_t** fst, uint64_t* nbytes);
 void ii2_fst_free(void* fst);
 
+/* ---- removed.list: the gob stream of RemovedLists (removed_list.go:26-33,73-80;
+ *      read/written next to the segment files, shard.go:340-358) -------------
+ * Host-side.  lists[timestamps[k]] = values[off[k] .. off[k+1]).  Wire format
+ * restated from the encoding/gob documentation, unverified against Go (see
+ * csrc/removed_gob.cpp). */
+typedef struct ii2_removed_lists {
+  uint64_t n_lists;
+  int64_t* timestamps; /* n_lists           */
+  uint64_t* off;       /* n_lists + 1       */
+  uint32_t* values;    /* off[n_lists]      */
+  void* _owner;
+} ii2_removed_lists;
+/* RemovedLists.Serialize.  Free the bytes with ii2_fst_free. */
+int ii2_removed_list_encode(const int64_t* timestamps, const uint64_t* off, const uint32_t* values,
+                            uint64_t n_lists, uint8_t** bytes, uint64_t* nbytes);
+/* UnserializeRemovedList. */
+int ii2_removed_list_decode(const uint8_t* bytes, uint64_t nbytes, ii2_removed_lists* out);
+void ii2_removed_lists_free(ii2_removed_lists* lists);
+
 /* ---- partitioning rule: shardKey (shard.go:362-378) ---------------------- */
 /* Returns the numeric shard key 0..1023 ((t[0]<<8 | t[1]) >> 6; 0 for terms
  * shorter than 2 bytes). Host-side helper, no device work. */

@@ -109,6 +109,16 @@ class FstTerms(C.Structure):
     ]
 
 
+class RemovedLists(C.Structure):
+    _fields_ = [
+        ("n_lists", C.c_uint64),
+        ("timestamps", C.POINTER(C.c_int64)),
+        ("off", u64p),
+        ("values", u32p),
+        ("_owner", C.c_void_p),
+    ]
+
+
 class ResultInfo(C.Structure):
     _fields_ = [
         ("terms_count", C.c_uint64),
@@ -190,6 +200,10 @@ PROTOTYPES = {
     "ii2_fst_build": (C.c_int, [u8p, u32p, u64p, C.c_uint64, C.POINTER(u8p),
                                 C.POINTER(C.c_uint64)]),
     "ii2_fst_free": (None, [C.c_void_p]),
+    "ii2_removed_list_encode": (C.c_int, [C.POINTER(C.c_int64), u64p, u32p, C.c_uint64,
+                                          C.POINTER(u8p), C.POINTER(C.c_uint64)]),
+    "ii2_removed_list_decode": (C.c_int, [u8p, C.c_uint64, C.POINTER(RemovedLists)]),
+    "ii2_removed_lists_free": (None, [C.POINTER(RemovedLists)]),
     "ii2_shard_key": (C.c_uint32, [u8p, C.c_size_t]),
 }
 

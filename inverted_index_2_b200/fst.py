@@ -106,3 +106,43 @@ def fst_len(data: bytes) -> int:
     if rc != A.II2_OK:
         raise FstError(rc, "len")
     return int(v.value)
+
+
+# ---- removed.list (gob stream of map[int64][]uint32, removed_list.go:26-33,73-80) -------------
+def removed_list_encode(lists: dict[int, np.ndarray]) -> bytes:
+    """RemovedLists.Serialize."""
+    ts = np.array(sorted(lists), dtype=np.int64)
+    parts = [np.ascontiguousarray(lists[int(t)], dtype=np.uint32) for t in ts]
+    off = np.zeros(len(ts) + 1, dtype=np.uint64)
+    if parts:
+        off[1:] = np.cumsum([len(p) for p in parts])
+    vals = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
+    if len(vals) == 0:
+        vals = np.zeros(1, dtype=np.uint32)
+    out, nb = A.u8p(), C.c_uint64()
+    rc = _lib().ii2_removed_list_encode(
+        ts.ctypes.data_as(C.POINTER(C.c_int64)) if len(ts) else C.cast(None, C.POINTER(C.c_int64)),
+        A.np_ptr(off, A.u64p), A.np_ptr(vals, A.u32p), len(ts), C.byref(out), C.byref(nb))
+    if rc != A.II2_OK:
+        raise FstError(rc, "removed_list_encode")
+    try:
+        return C.string_at(out, nb.value)
+    finally:
+        _lib().ii2_fst_free(out)
+
+
+def removed_list_decode(data: bytes) -> dict[int, np.ndarray]:
+    """UnserializeRemovedList."""
+    p, n, keep = _buf(data)
+    out = A.RemovedLists()
+    rc = _lib().ii2_removed_list_decode(p, n, C.byref(out))
+    if rc != A.II2_OK:
+        raise FstError(rc, "removed_list_decode")
+    try:
+        k = int(out.n_lists)
+        ts = A.from_ptr(out.timestamps, k, np.int64)
+        off = A.from_ptr(out.off, k + 1, np.uint64)
+        vals = A.from_ptr(out.values, int(off[-1]) if k else 0, np.uint32)
+        return {int(ts[i]): vals[int(off[i]):int(off[i + 1])].copy() for i in range(k)}
+    finally:
+        _lib().ii2_removed_lists_free(C.byref(out))

@@ -85,6 +85,20 @@ class RemovedLists:
             for t in [t for t in self.lists if t < oldest]:
                 del self.lists[t]
 
+    def serialize(self) -> bytes:
+        """RemovedLists.Serialize, removed_list.go:73-80 (gob; csrc/removed_gob.cpp)."""
+        from . import fst
+        with self.m:
+            return fst.removed_list_encode(self.lists)
+
+    @classmethod
+    def unserialize(cls, data: bytes) -> "RemovedLists":
+        """UnserializeRemovedList, removed_list.go:26-33."""
+        from . import fst
+        rl = cls()
+        rl.lists = fst.removed_list_decode(data)
+        return rl
+
 
 class Segment:
     """segments.go:16-23."""
@@ -137,9 +151,9 @@ class Shard:
     """shard.go: one term-prefix shard = a set of immutable segments + removed list."""
 
     def __init__(self, key: str, backend: Backend, basedir: str | None = None):
-        """basedir: the shard's directory of `<key>_fst` / `<key>_val` files (NewShard,
-        shard.go:300-358); existing segments are loaded, new ones are written there.  None keeps
-        the shard in memory only.  (removed.list persistence is gob, Go-side: out of scope.)"""
+        """basedir: the shard's directory of `<key>_fst` / `<key>_val` files and `removed.list`
+        (NewShard, shard.go:300-358); existing segments and the removed list are loaded, new
+        ones are written there.  None keeps the shard in memory only."""
         self.key = key
         self.backend = backend
         self.basedir = basedir
@@ -154,6 +168,18 @@ class Shard:
                     continue
                 terms = data.terms()
                 self.segments.add(Segment(int(k), len(terms), terms[0], terms[-1], data))
+            rl = os.path.join(basedir, "removed.list")  # shard.go:340-352
+            if os.path.exists(rl):
+                with open(rl, "rb") as f:
+                    self.removed_list = RemovedLists.unserialize(f.read())
+
+    def _persist_removed(self) -> None:
+        """The removed list is flushed with every change (Shard.Remove, shard.go:95-104)."""
+        if self.basedir is not None:
+            tmp = os.path.join(self.basedir, "removed.list.tmp")
+            with open(tmp, "wb") as f:
+                f.write(self.removed_list.serialize())
+            os.rename(tmp, os.path.join(self.basedir, "removed.list"))
 
     def _persist(self, seg: "Segment") -> None:
         if self.basedir is not None:
@@ -213,6 +239,7 @@ class Shard:
             stamps = [now] + [s.key for s in self.segments.list]
         self.removed_list.sync(stamps)
         self.removed_list.put(_unix_nano_key(), values)
+        self._persist_removed()
 
     def merge(self, req_count: int, m_count: int) -> int:
         """Shard.Merge, shard.go:127-245; returns how many segments were merged."""

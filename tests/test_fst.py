@@ -167,3 +167,64 @@ def test_index_directory_reopen(tmp_path, orc):
     third = InvertedIndex(OracleBackend(orc), basedir=d)
     assert list(third.read(None, None)) == exp
     assert third.prefix_search([b"ab", b"zz"]) == {b"ab": [1, 2]}
+
+
+# ---------------------------------------------------------------- removed.list (gob)
+def test_gob_removed_list_roundtrip_and_known_bytes():
+    """removed_list_test.go:9-18 through the gob stream; the byte layout is checked against the
+    encodings the encoding/gob documentation fixes (uint / int forms, message framing, the
+    singleton zero byte), not against a file written by Go."""
+    lists = {1: np.array([1, 5, 10], dtype=np.uint32), 2: np.array([2, 20, 30], dtype=np.uint32)}
+    data = fst.removed_list_encode(lists)
+    back = fst.removed_list_decode(data)
+    assert sorted(back) == [1, 2] and all(np.array_equal(back[k], lists[k]) for k in lists)
+    # message 1: type -66 = map{Id 66, Key int(2), Elem 65}; message 2: type -65 = slice{Id 65,
+    # Elem uint(3)}; message 3: value of type 66: 0 (singleton), 2 entries
+    m1 = bytes([0xFF, 0x83, 0x04, 0x01, 0x02, 0xFF, 0x84, 0x00, 0x01, 0x04, 0x01, 0xFF, 0x82, 0x00, 0x00])
+    m2 = bytes([0xFF, 0x81, 0x02, 0x01, 0x02, 0xFF, 0x82, 0x00, 0x01, 0x06, 0x00, 0x00])
+    m3 = bytes([0xFF, 0x84, 0x00, 0x02, 0x02, 0x03, 0x01, 0x05, 0x0A, 0x04, 0x03, 0x02, 0x14, 0x1E])
+    assert data == bytes([len(m1)]) + m1 + bytes([len(m2)]) + m2 + bytes([len(m3)]) + m3
+    # wide values: unix-nano timestamps (9 bytes on the wire), negative keys, values >= 2^31
+    big = {1_700_000_000_123_456_789: np.array([0, 127, 128, 0xFFFFFFFF], dtype=np.uint32),
+           -5: np.zeros(0, dtype=np.uint32), 0: np.arange(300, dtype=np.uint32)}
+    back = fst.removed_list_decode(fst.removed_list_encode(big))
+    assert sorted(back) == sorted(big) and all(np.array_equal(back[k], big[k]) for k in big)
+    assert fst.removed_list_decode(fst.removed_list_encode({})) == {}
+
+
+def test_gob_decoder_accepts_named_types_and_other_ids():
+    """A stream as another gob encoder may write it: type names present, different type ids,
+    the slice described before the map."""
+    def msg(body):
+        assert len(body) < 128
+        return bytes([len(body)]) + bytes(body)
+    name_s, name_m = b"[]uint32", b"map[int64][]uint32"
+    # ids 70 (slice) and 71 (map): int(-70) = 139, int(70) = 140, int(-71) = 141, int(71) = 142
+    slice_def = [0xFF, 139, 0x02, 0x01, 0x01, len(name_s), *name_s, 0x01, 0xFF, 140, 0x00,
+                 0x01, 0x06, 0x00, 0x00]
+    map_def = [0xFF, 141, 0x04, 0x01, 0x01, len(name_m), *name_m, 0x01, 0xFF, 142, 0x00,
+               0x01, 0x04, 0x01, 0xFF, 140, 0x00, 0x00]
+    value = [0xFF, 142, 0x00, 0x01, 0x0E, 0x02, 0x09, 0xFE, 0x01, 0x00]  # {7: [9, 256]}
+    got = fst.removed_list_decode(msg(slice_def) + msg(map_def) + msg(value))
+    assert list(got) == [7] and got[7].tolist() == [9, 256]
+    with pytest.raises(fst.FstError):
+        fst.removed_list_decode(msg(slice_def) + msg(map_def) + msg(value)[:-2])
+    with pytest.raises(fst.FstError):
+        fst.removed_list_decode(msg(value))  # value of an undescribed type
+
+
+def test_removed_list_persists_with_the_shard(tmp_path, orc):
+    from inverted_index_2_b200.host import InvertedIndex
+    from scenario import OracleBackend
+    d = str(tmp_path)
+    idx = InvertedIndex(OracleBackend(orc), basedir=d)
+    idx.put([b"aaaa", b"bbbb"], 1)
+    idx.put([b"aaaa", b"bbbb"], 1)
+    idx.put([b"aaaa"], 2)
+    idx.put_removed([1])
+    shard_dir = os.path.join(d, sorted(os.listdir(d))[0])
+    assert "removed.list" in os.listdir(shard_dir)
+    again = InvertedIndex(OracleBackend(orc), basedir=d)  # removed list reloaded from disk
+    assert again.shards[0].removed_list.values().tolist() == [1]
+    assert again.merge(2, 3, 2) > 0
+    assert list(again.read(None, None)) == [(b"aaaa", [2])]  # inverted_index_test.go:59-82
