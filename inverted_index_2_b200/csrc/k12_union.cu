@@ -92,6 +92,9 @@ __host__ __device__ inline size_t k1b_smem_bytes(int k) {
          + (size_t)CAP_I * 4 * 3                 // inst, count|length, pbase
          + (size_t)(4 * k) * 4 + (size_t)(2 * k + 2) * 4   // cur, mm, hi, endr; rstart (padded to 2^n + 1)
          + (size_t)CAP_I * 2 * 2                 // tlen, reps
+#ifndef K1B_SEG_GLOBAL
+         + (size_t)k * 40 + 16                   // tb, toff, poff, post pointers; base - lo
+#endif
          + (size_t)K1B_HT * 4 + 64;
 }
 
@@ -140,6 +143,16 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
   uint32_t* endr = reinterpret_cast<uint32_t*>(sp); sp += k * 4;
   // run starts inside the tile, padded with `size` up to kp2 = the power of two >= k
   uint32_t* rstart = reinterpret_cast<uint32_t*>(sp);
+#ifndef K1B_SEG_GLOBAL
+  // the segment descriptors of the call, one field per array: phase (2) indexes them by run
+  sp += (2 * k + 2) * 4;
+  sp += (8 - (reinterpret_cast<uintptr_t>(sp) & 7)) & 7;
+  const uint8_t** sg_tb = reinterpret_cast<const uint8_t**>(sp); sp += k * 8;
+  const uint32_t** sg_toff = reinterpret_cast<const uint32_t**>(sp); sp += k * 8;
+  const uint64_t** sg_poff = reinterpret_cast<const uint64_t**>(sp); sp += k * 8;
+  const uint32_t** sg_post = reinterpret_cast<const uint32_t**>(sp); sp += k * 8;
+  uint32_t* sg_bl = reinterpret_cast<uint32_t*>(sp);  // base - lo
+#endif
   // alias, valid once the hash table is done: first source slot by representative
   uint32_t* sbase = table;
   uint32_t kp2 = 1;
@@ -161,6 +174,14 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     for (int s = tid; s < k; s += K1B_THREADS) {
       cur[s] = a.part[(uint64_t)r0 * k + s];
       endr[s] = a.part[(uint64_t)r1 * k + s];
+#ifndef K1B_SEG_GLOBAL
+      const SegDesc sd = a.segs[s];
+      sg_tb[s] = sd.tb;
+      sg_toff[s] = sd.toff;
+      sg_poff[s] = sd.poff;
+      sg_post[s] = sd.post;
+      sg_bl[s] = sd.base - sd.lo;
+#endif
     }
   }
   const uint64_t rec_base = a.bk_pos[b];
@@ -310,11 +331,18 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
 #pragma unroll
       for (int j = 0; j < PER; j++) {
         if (sg[j] >= 0) {
+#ifndef K1B_SEG_GLOBAL
+          const uint32_t* const toff_s = sg_toff[sg[j]];
+          const uint64_t* const poff_s = sg_poff[sg[j]];
+#else
           const SegDesc& sd = a.segs[sg[j]];
-          to[j] = __ldg(sd.toff + ix[j]);
-          tn[j] = __ldg(sd.toff + ix[j] + 1);
-          pp[j] = __ldg(sd.poff + ix[j]);
-          p1[j] = __ldg(sd.poff + ix[j] + 1);
+          const uint32_t* const toff_s = sd.toff;
+          const uint64_t* const poff_s = sd.poff;
+#endif
+          to[j] = __ldg(toff_s + ix[j]);
+          tn[j] = __ldg(toff_s + ix[j] + 1);
+          pp[j] = __ldg(poff_s + ix[j]);
+          p1[j] = __ldg(poff_s + ix[j] + 1);
         }
       }
       // (requesting the words of all four key windows before using any was measured slower,
@@ -326,15 +354,28 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
           const uint32_t i = tid + j * K1B_THREADS;
           const uint32_t n = tn[j] - to[j];
           uint64_t kh, kl;
-          load_key16(a.segs[sg[j]].tb, to[j], n, cpl, kh, kl);
+#ifndef K1B_SEG_GLOBAL
+          const uint8_t* const tb_s = sg_tb[sg[j]];
+          const uint32_t* const post_s = sg_post[sg[j]];
+          const uint32_t inst_s = sg_bl[sg[j]] + ix[j];
+#else
+          const SegDesc& sd = a.segs[sg[j]];
+          const uint8_t* const tb_s = sd.tb;
+          const uint32_t* const post_s = sd.post;
+          const uint32_t inst_s = sd.base + (ix[j] - sd.lo);
+#endif
+          load_key16(tb_s, to[j], n, cpl, kh, kl);
           key_hi[i] = kh;
           key_lo[i] = kl;
-          key_x[i] = load_key_x(a.segs[sg[j]].tb, to[j], n, cpl);
+          key_x[i] = load_key_x(tb_s, to[j], n, cpl);
           tlen[i] = (uint16_t)n;
-          const SegDesc& sd = a.segs[sg[j]];
-          inst_a[i] = sd.base + (ix[j] - sd.lo);
+          inst_a[i] = inst_s;
           pl[j] = (p1[j] - pp[j]) > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)(p1[j] - pp[j]);
-          pp[j] = reinterpret_cast<uint64_t>(sd.post + pp[j]);
+          pp[j] = reinterpret_cast<uint64_t>(post_s + pp[j]);
+#ifndef K1B_NO_PREFETCH_POST
+          // the copy of phase (5) is ~15 k clocks away: ask the L2 for the line now
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp[j]));
+#endif
         }
       }
     }

@@ -54,7 +54,10 @@ constexpr uint32_t K6_MAX_GROUP = 32;  // buckets per CTA
 // bucket, form one flat sequence (buckets are in merged order and bk_out is the exclusive
 // prefix over buckets, so the running output positions simply continue across the buckets of
 // the group).  About 256 records per CTA: one set of block scans per 256 terms.
-__global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a, uint32_t group,
+#ifndef K6_MIN_CTAS
+#define K6_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(K6_THREADS, K6_MIN_CTAS) k6_emit_kernel(const K6Args a, uint32_t group,
                                                              uint32_t n_buckets) {
   __shared__ K6Work s_work[K6_THREADS];
   __shared__ uint64_t s_ws64[K6_WARPS + 2];
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a, uin
       if (a.want_enc) a.o_val_off[t] = 4ull * w.enc_dst;
     }
     __syncthreads();
+#ifdef K6_SERIAL_COPY
     for (uint32_t h = warp_id(); h < n_surv; h += K6_WARPS) {
       const K6Work w = s_work[h];
       const unsigned lane = lane_id();
@@ -130,6 +134,60 @@ __global__ void __launch_bounds__(K6_THREADS) k6_emit_kernel(const K6Args a, uin
       if (a.want_enc)
         for (uint32_t i = lane; i < w.enc; i += 32) a.o_val_words[w.enc_dst + i] = w.esrc[i];
     }
+#else
+    // A term is ~15 bytes + ~100 words: with one load per lane in flight the warp pays a full
+    // memory round trip per 32 words (source and destination may alias as far as the compiler
+    // knows, so it keeps load -> store -> load in order).  The first 128 words of both streams
+    // and the first 32 term bytes are requested before anything is stored.
+    for (uint32_t h = warp_id(); h < n_surv; h += K6_WARPS) {
+      const K6Work w = s_work[h];
+      const unsigned lane = lane_id();
+      uint8_t tb0 = 0;
+      uint32_t ev[4], dv[4];
+      if (lane < w.tlen) tb0 = __ldg(w.tsrc + lane);
+      if (a.want_enc) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u * 32 + lane < w.enc) ev[u] = __ldg(w.esrc + u * 32 + lane);
+      }
+      if (a.want_dec) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u * 32 + lane < w.cnt) dv[u] = __ldg(w.dsrc + u * 32 + lane);
+      }
+      if (lane < w.tlen) a.o_term_bytes[w.tdst + lane] = tb0;
+      if (a.want_enc) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u * 32 + lane < w.enc) a.o_val_words[w.enc_dst + u * 32 + lane] = ev[u];
+      }
+      if (a.want_dec) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u * 32 + lane < w.cnt) a.o_post[w.post_dst + u * 32 + lane] = dv[u];
+      }
+      // the rest of a long term / a heavy term's streams, four requests at a time
+      for (uint32_t i = 32 + lane; i < w.tlen; i += 32) a.o_term_bytes[w.tdst + i] = __ldg(w.tsrc + i);
+      if (a.want_enc)
+        for (uint32_t base = 128; base < w.enc; base += 128) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (base + u * 32 + lane < w.enc) ev[u] = __ldg(w.esrc + base + u * 32 + lane);
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (base + u * 32 + lane < w.enc) a.o_val_words[w.enc_dst + base + u * 32 + lane] = ev[u];
+        }
+      if (a.want_dec)
+        for (uint32_t base = 128; base < w.cnt; base += 128) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (base + u * 32 + lane < w.cnt) dv[u] = __ldg(w.dsrc + base + u * 32 + lane);
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (base + u * 32 + lane < w.cnt) a.o_post[w.post_dst + base + u * 32 + lane] = dv[u];
+        }
+    }
+#endif
     run_t += n_surv;
     run_tb += tot_a >> 32;
     run_p += tot_p;
