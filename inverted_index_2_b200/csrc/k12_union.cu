@@ -181,6 +181,12 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
       sg_poff[s] = sd.poff;
       sg_post[s] = sd.post;
       sg_bl[s] = sd.base - sd.lo;
+#ifndef K1B_NO_PREFETCH_OFFS
+      // the offsets of the run are read in phase (2), a few thousand clocks from here
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.toff + cur[s]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.poff + cur[s]));
+      if (endr[s] - cur[s] > 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.poff + endr[s]));
+#endif
 #endif
     }
   }
@@ -345,6 +351,11 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
           p1[j] = __ldg(poff_s + ix[j] + 1);
         }
       }
+#if !defined(K1B_NO_PREFETCH_TB) && !defined(K1B_SEG_GLOBAL)
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (sg[j] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sg_tb[sg[j]] + to[j] + cpl));
+#endif
       // (requesting the words of all four key windows before using any was measured slower,
       // 1.61 vs 1.43 ms, like batching the source copies below: the phase is bound by the
       // L1's handling of these 64-way scattered small reads, not by their latency)
@@ -960,6 +971,7 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
       g_next = g_none;
       if (rn < D) g_next = a.gin[rec_base + rn];
     }
+
     const bool heavy = has && g.L > REG_CAP;
     const bool wide = has && !heavy && g.L >= K2B_HALF;
     if (heavy && hl == 0) {  // the multi-CTA path works from the source list
@@ -982,6 +994,12 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
       uint32_t* const buf = s_buf[warp] + half * K2B_HALF;
       uint32_t* const ebuf = s_enc[warp] + half * (K2B_EBUF / 2);
       const uint32_t outn = union_blocked<16>(slot, buf, L, g.c > 1, a.rem);
+#ifdef K2B_PREFETCH_SLOT
+      // the record of the next round has arrived by now: its gathered values start moving
+      // towards the L2 while this round encodes and writes out
+      if (hl * 32 < g_next.L && hl < 8)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gath + g_next.pst + hl * 32));
+#endif
       if (a.want_dec)
         for (uint32_t e = hl; e < outn; e += 16) slot[e] = buf[e];
       uint32_t enc = 0;
