@@ -162,8 +162,43 @@ class ClockSampler:
 
     def __init__(self, dev: int):
         self.dev, self.proc, self.lines = dev, None, []
+        self.nv, self.nv_samples, self.nv_stop = None, [], threading.Event()
+
+    def _nvml_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x.strip() for x in vis.split(",") if x.strip()]
+        if ids and all(x.isdigit() for x in ids) and self.dev < len(ids):
+            return int(ids[self.dev])
+        return self.dev
+
+    def _nvml_loop(self, h):
+        import pynvml as nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.nv_stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.nv_samples.append((float(sm), float(mx), [k for k, b in bits.items() if r & b]))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        # the timed region of the default run is ~30 ms: an in-process NVML poll every 2 ms sees
+        # it (the library calls release the GIL); nvidia-smi -lms 100 stays as the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.nv = threading.Thread(target=self._nvml_loop, args=(h,), daemon=True)
+            self.nv.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -178,6 +213,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.nv_stop.set()
+            self.nv.join(timeout=2)
+            if self.nv_samples:
+                sm = [x[0] for x in self.nv_samples]
+                return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(x[1] for x in self.nv_samples),
+                        "reasons": sorted({r for x in self.nv_samples for r in x[2]}),
+                        "samples": len(sm), "source": "NVML, 2 ms poll over the timed region"}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML sample"], "samples": 0}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

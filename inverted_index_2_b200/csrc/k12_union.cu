@@ -248,6 +248,11 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
 
     K1B_TICK(1);  // tile choice (bisection of oversized buckets)
     // ---------------- (1) run starts; reset of the tile state ----------------
+#ifndef K1B_RSTART_ALL
+    if (k <= 128 && warp != 0) {
+      // warp 0 scans; the barrier after the resets below publishes the run starts
+    } else
+#endif
     if (k <= 128) {  // every warp scans for itself (identical values): no warp waits for another
       uint32_t v[4], sum = 0;
 #pragma unroll
@@ -444,6 +449,64 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
     const uint32_t D = s_nreps;
 
     // ---------------- (4) order the distinct terms; one record per term ----------------
+#ifndef K1B_RANK_WARP
+    if (D <= K1B_SMALL_D) {  // rank by counting: EIGHT lanes per term, four terms per warp
+      // (a warp per term leaves most lanes idle at ~24 distinct terms per bucket and takes
+      // three rounds: 1.26 -> 1.23 ms; a thread per term issues a ninth of the instructions
+      // and was measured SLOWER, 1.37 vs 1.29 ms: the serial loop sits on the tile's critical
+      // path while seven warps wait at the barrier)
+      const unsigned sub = lane & 7u;
+#pragma unroll 1
+      for (uint32_t t0 = warp * 4; t0 < D; t0 += K1B_WARPS * 4) {
+        const uint32_t t = t0 + (lane >> 3);
+        const bool valid = t < D;
+        const uint32_t me = valid ? reps[t] : 0u;
+        uint32_t rank = 0, ib = 0, pst = 0, est = 0;
+        if (valid) {
+          const uint64_t mh = key_hi[me], ml = key_lo[me], mx = key_x[me];
+#pragma unroll 1
+          for (uint32_t j = sub; j < D; j += 8) {
+            const uint32_t o = reps[j];
+            const uint64_t oh = key_hi[o];
+            bool lt = oh < mh;
+            if (oh == mh && o != me) {  // rare: the first eight bytes past the prefix agree
+              const uint64_t ol = key_lo[o], ox = key_x[o];
+              lt = ol != ml ? ol < ml : (ox != mx ? ox < mx : tail_compare(o, me) < 0);
+            }
+            const uint32_t c = cg[o];
+            const uint32_t len = c & 0xFFFFFu;
+            const bool lg = lt && len <= REG_CAP;
+            rank += lt ? 1u : 0u;
+            ib += lt ? c >> 20 : 0u;
+            pst += lg ? len : 0u;
+            est += lg ? enc_slot_words(len) : 0u;
+          }
+        }
+#pragma unroll
+        for (int d = 4; d > 0; d >>= 1) {
+          rank += __shfl_xor_sync(0xffffffffu, rank, d);
+          ib += __shfl_xor_sync(0xffffffffu, ib, d);
+          pst += __shfl_xor_sync(0xffffffffu, pst, d);
+          est += __shfl_xor_sync(0xffffffffu, est, d);
+        }
+        if (valid && sub == 0) {
+          const uint32_t cme = cg[me];
+          const uint32_t len = cme & 0xFFFFFu;
+          const bool light = len <= REG_CAP;
+          const uint32_t src = (uint32_t)rec_base + icount + ib;
+          uint4* rec = reinterpret_cast<uint4*>(a.gin + rec_base + dcount + rank);
+          rec[0] = make_uint4(inst_a[me], tlen[me], src, cme >> 20);
+          rec[1] = make_uint4(len, pcount + pst, ecount + est, 0u);
+          sbase[me] = src;
+          pbase[me] = light ? pcount + pst : K1B_HEAVY;
+          if (rank == D - 1) {
+            s_tot[0] = pst + (light ? len : 0u);
+            s_tot[1] = est + (light ? enc_slot_words(len) : 0u);
+          }
+        }
+      }
+    } else
+#endif
     if (D <= K1B_SMALL_D) {  // rank by counting: one warp per term, lanes over the others
 #pragma unroll 1
       for (uint32_t t = warp; t < D; t += K1B_WARPS) {
