@@ -38,9 +38,9 @@ constexpr int K1B_WARPS = K1B_THREADS / 32;
 #define K1B_CAP_N 1024  // 512 needs k <= 512 (a tile holds at least one instance of every segment)
 #endif
 constexpr uint32_t CAP_I = K1B_CAP_N;   // instances per sub-tile
-constexpr uint32_t K1B_HT = 2 * CAP_I;  // hash slots
-static_assert(CAP_I % K1B_THREADS == 0 && CAP_I <= 1024 && (CAP_I & (CAP_I - 1)) == 0,
-              "tile = a power of two, a whole number of instances per thread, 10-bit tile indexes");
+constexpr uint32_t K1B_HT = CAP_I > 512 ? 2048 : 1024;  // hash slots (a power of two >= 2 * CAP_I)
+static_assert(CAP_I % K1B_THREADS == 0 && CAP_I <= 1024 && CAP_I % 4 == 0,
+              "tile = a whole number of instances per thread, 10-bit tile indexes");
 constexpr uint32_t REG_CAP = 256;  // values a warp sorts in registers
 constexpr uint32_t K1B_STAGE_CAP = CAP_I * 6;  // postings of a tile assembled in the 24 KB of key windows
 constexpr uint32_t K1B_SMALL_D = 64;  // distinct terms ranked by counting instead of sorting

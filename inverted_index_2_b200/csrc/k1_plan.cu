@@ -449,6 +449,20 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     return (v >= 32 && v <= 1024) ? (uint32_t)v : kInstancesPerBucket;
   }();
   uint64_t want = N / per_bucket;
+  // a small call (a narrow range read) is latency-bound: smaller buckets spread it over the SMs
+  // (II2_SMALL_BUCKET=<min instances per bucket>, 0 = off)
+  static const uint32_t small_bucket = [] {
+    const char* e = getenv("II2_SMALL_BUCKET");
+    const long v = e ? atol(e) : 128;
+    return (v >= 0 && v <= 1024) ? (uint32_t)v : 128u;
+  }();
+  static const uint32_t small_want = [] {  // II2_SMALL_WANT=<buckets a small call is cut into>
+    const char* e = getenv("II2_SMALL_WANT");
+    const long v = e ? atol(e) : 592;
+    return (v >= 1 && v <= 65536) ? (uint32_t)v : 592u;
+  }();
+  if (small_bucket && want < small_want && N / small_bucket > want)
+    want = std::min<uint64_t>(small_want, N / small_bucket);
   if (want > kMaxBuckets - 1) want = kMaxBuckets - 1;
   uint32_t* cbase = sbase + (k + 1);
   sbase[0] = 0;

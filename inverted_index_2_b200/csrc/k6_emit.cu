@@ -238,8 +238,11 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   ProfScope scope("k6_emit", s);
   // buckets per CTA: about one CTA-width of records
   const uint64_t tm = u.terms_merged ? u.terms_merged : 1;
-  const uint32_t group = (uint32_t)std::min<uint64_t>(
+  uint32_t group = (uint32_t)std::min<uint64_t>(
       K6_MAX_GROUP, std::max<uint64_t>(1, (uint64_t)K6_THREADS * plan.n_buckets / tm));
+  // a small result (a narrow range read) must not end up on a handful of CTAs whose warps walk
+  // dozens of terms one after the other: at least ~two CTAs per SM while the buckets last
+  group = (uint32_t)std::min<uint64_t>(group, std::max<uint64_t>(1, plan.n_buckets / 296));
   k6_emit_kernel<<<div_up(plan.n_buckets, group), K6_THREADS, 0, s>>>(a, group, plan.n_buckets);
   II2_LAUNCHED();
   return II2_OK;
