@@ -339,9 +339,9 @@ def run_ours(a):
         "k6_emit": 32 * n_groups + val_size + t_out_bytes + val_size + t_out_bytes + 12 * t_out,
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture
-    # of this command (profiles/r01b_ncu_full_metrics.csv); only valid for the default workload
-    ncu_traffic = {"k1b_group": 1273.5e6 + 447.8e6, "k2b_union": 493.8e6 + 306.3e6,
-                   "k6_emit": 516.8e6 + 271.9e6}
+    # of this command (profiles/r01c_ncu_full_metrics.csv); only valid for the default workload
+    ncu_traffic = {"k1b_group": 1279.3e6 + 457.9e6, "k2b_union": 494.1e6 + 308.3e6,
+                   "k6_emit": 521.3e6 + 298.3e6}
     default_workload = (a.terms, a.segments, a.postings, a.removed_frac) == \
         (1_000_000, 64, 100_000_000, 0.05) and world == 1
     peak, peak_src = peaks()
@@ -355,7 +355,7 @@ def run_ours(a):
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak,
                     "traffic": ncu_traffic.get(top["name"]) if default_workload else None,
-                    "traffic_source": "ncu --set full, profiles/r01b_ncu_full_metrics.csv",
+                    "traffic_source": "ncu --set full, profiles/r01c_ncu_full_metrics.csv",
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms}
     pipeline_bytes = synth.algorithmic_bytes(n_in, n_out, t_in, t_in_bytes, a.segments, t_out,
