@@ -172,34 +172,9 @@ k_bitmap_set(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t* __restri
 
 // Range windows (K4): lo = first term >= min (vellum Iterator(min) seek, file/reader.go:147),
 // hi = first term > max (inclusive right bound, :54-58 and :151-155); then bases.
-// One WARP per segment searches 32 ways at a time: the lanes probe 32 evenly spaced terms of the
-// current interval, a ballot narrows it 33-fold (4 rounds for 500 k terms instead of the 19
-// dependent probes of a binary search — a small read spent 50 of its 270 us there).  The last
-// CTA to finish turns the window widths into instance bases.
-template <bool UPPER>
-__device__ __forceinline__ uint32_t warp_seg_bound(const SegDesc& sd, uint32_t lo, uint32_t hi,
-                                                   const uint8_t* t, uint32_t nt) {
-  const unsigned lane = lane_id();
-  while (lo < hi) {  // uniform inside the warp
-    const uint32_t width = hi - lo;
-    const bool narrow = width <= 32;
-    const uint32_t probe = narrow ? lo + lane : lo + (uint32_t)(((uint64_t)(lane + 1) * width) / 33);
-    bool before = false;
-    if (!narrow || lane < width) {
-      const uint32_t o = __ldg(sd.toff + probe), n = __ldg(sd.toff + probe + 1) - o;
-      const int c = term_compare(sd.tb + o, n, t, nt);
-      before = UPPER ? c <= 0 : c < 0;
-    }
-    const uint32_t c = __popc(__ballot_sync(0xffffffffu, before));  // sorted: lanes 0 .. c-1
-    if (narrow) return lo + c;
-    const uint32_t first_not = lo + (uint32_t)(((uint64_t)(c + 1) * width) / 33);  // probe of lane c
-    const uint32_t last_before = lo + (uint32_t)(((uint64_t)c * width) / 33);     // probe of lane c-1
-    if (c < 32) hi = first_not;
-    if (c > 0) lo = last_before + 1;
-  }
-  return lo;
-}
-
+// One WARP per segment searches 32 ways at a time (warp_partition_point: 4 rounds for 500 k
+// terms instead of the 19 dependent probes of a binary search — a small read spent 50 of its
+// 270 us there).  The last CTA to finish turns the window widths into instance bases.
 __global__ void __launch_bounds__(256)
 k4_windows(SegDesc* segs, int k, const uint8_t* __restrict__ bounds, uint32_t minlen,
            int has_min, uint32_t maxlen, int has_max, uint32_t* n_total) {
@@ -209,8 +184,14 @@ k4_windows(SegDesc* segs, int k, const uint8_t* __restrict__ bounds, uint32_t mi
   const int s = blockIdx.x * 8 + warp_id();
   if (s < k) {
     const SegDesc sd = segs[s];
-    const uint32_t lo = has_min ? warp_seg_bound<false>(sd, 0, sd.n, bounds, minlen) : 0u;
-    const uint32_t hi = has_max ? warp_seg_bound<true>(sd, lo, sd.n, bounds + minlen, maxlen) : sd.n;
+    auto term_vs = [&](uint32_t i, const uint8_t* t, uint32_t nt) {
+      const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
+      return term_compare(sd.tb + o, n, t, nt);
+    };
+    const uint32_t lo = has_min ? warp_partition_point(0u, sd.n, [&](uint32_t i) {
+      return term_vs(i, bounds, minlen) < 0; }) : 0u;
+    const uint32_t hi = has_max ? warp_partition_point(lo, sd.n, [&](uint32_t i) {
+      return term_vs(i, bounds + minlen, maxlen) <= 0; }) : sd.n;
     if (lane_id() == 0) {
       segs[s].lo = lo;
       segs[s].hi = hi;

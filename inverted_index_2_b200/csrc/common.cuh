@@ -165,6 +165,29 @@ __device__ __forceinline__ uint32_t seg_upper_bound(const SegDesc& s, uint32_t l
   return lo;
 }
 
+// First index in [lo,hi) for which pred is false, pred being true on a prefix of the range
+// (a partition point), found by a whole warp: the lanes probe 32 evenly spaced indexes, a
+// ballot narrows the interval 33-fold — 4 rounds of dependent loads for 500 k terms instead of
+// the 19 of a binary search.  Every lane must call with the same lo / hi; returns the same value
+// in every lane.
+template <class Pred>
+__device__ __forceinline__ uint32_t warp_partition_point(uint32_t lo, uint32_t hi, Pred pred) {
+  const unsigned lane = lane_id();
+  while (lo < hi) {  // uniform inside the warp
+    const uint32_t width = hi - lo;
+    const bool narrow = width <= 32;
+    const uint32_t probe = narrow ? lo + lane : lo + (uint32_t)(((uint64_t)(lane + 1) * width) / 33);
+    const bool t = (!narrow || lane < width) ? pred(probe) : false;
+    const uint32_t c = __popc(__ballot_sync(0xffffffffu, t));  // monotone: lanes 0 .. c-1
+    if (narrow) return lo + c;
+    const uint32_t first_false = lo + (uint32_t)(((uint64_t)(c + 1) * width) / 33);  // lane c's probe
+    const uint32_t last_true = lo + (uint32_t)(((uint64_t)c * width) / 33);          // lane c-1's
+    if (c < 32) hi = first_false;
+    if (c > 0) lo = last_true + 1;
+  }
+  return lo;
+}
+
 // slices.BinarySearch(removedValues, v) membership (shard.go:183), answered from the bitmap
 // when one covers v.
 __device__ __forceinline__ bool is_removed(const RemovedSet& r, uint32_t v) {

@@ -47,28 +47,26 @@ struct K5Args {
   uint32_t* flags;     // [0] = a slice longer than 2^32-1 postings
 };
 
-// One thread per (prefix, segment): lo = first term >= p (every term with prefix p is >= p),
+// One WARP per (prefix, segment): lo = first term >= p (every term with prefix p is >= p),
 // hi = first term at or after lo that does not start with p (terms with a common prefix are
-// contiguous in bytes.Compare order).
+// contiguous in bytes.Compare order); both are 32-way searches (warp_partition_point).
 __global__ void __launch_bounds__(256) k5_windows(const K5Args a) {
-  const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= (uint64_t)a.np * a.k) return;
+  const uint64_t id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (id >= (uint64_t)a.np * a.k) return;  // whole warps leave together
   const uint32_t p = (uint32_t)(id / a.k);
   const int s = (int)(id % a.k);
   const SegDesc sd = a.segs[s];
   const uint8_t* pb = a.pbytes + a.poff[p];
   const uint32_t pn = a.poff[p + 1] - a.poff[p];
-  const uint32_t lo = seg_lower_bound(sd, 0, sd.n, pb, pn);
-  uint32_t x = lo, y = sd.n;
-  while (x < y) {
-    const uint32_t mid = x + ((y - x) >> 1);
-    const uint32_t o = sd.toff[mid], n = sd.toff[mid + 1] - o;
-    if (has_prefix(sd.tb + o, n, pb, pn))
-      x = mid + 1;
-    else
-      y = mid;
-  }
-  const uint32_t hi = x;
+  const uint32_t lo = warp_partition_point(0u, sd.n, [&](uint32_t i) {
+    const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
+    return term_compare(sd.tb + o, n, pb, pn) < 0;
+  });
+  const uint32_t hi = warp_partition_point(lo, sd.n, [&](uint32_t i) {
+    const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
+    return has_prefix(sd.tb + o, n, pb, pn);
+  });
+  if (lane_id() != 0) return;
   const uint64_t p0 = sd.poff[lo], p1 = sd.poff[hi];
   uint64_t len = p1 - p0;
   if (len > 0xFFFFFFFFull) {
@@ -156,7 +154,7 @@ int k5_prefix_search(const SegDesc* d_segs, int k, const uint8_t* d_pbytes, cons
   a.flags = flags.p;
   {
     ProfScope scope("k5_windows", s);
-    k5_windows<<<div_up(pairs, 256), 256, 0, s>>>(a);
+    k5_windows<<<div_up(pairs, 8), 256, 0, s>>>(a);  // a warp per pair
     II2_LAUNCHED();
   }
   LargeArgs la;
