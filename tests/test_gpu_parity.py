@@ -303,6 +303,35 @@ def test_read_range_matches_oracle(engine, orc):
                           orc.read_range(w.segments, lo, hi, removed=w.removed))
 
 
+def test_window_search_boundaries(engine, orc):
+    """The 32-way warp search of the range windows (K4) and of the prefix windows (K5): segment
+    sizes around the lane count and its powers (0, 1, 31..34, 1088..1090 = 33^2 +- 1, 36000 >
+    33^3), bounds on every kind of position — a member, between members, before the first,
+    after the last, equal min and max, min > max."""
+    rng = np.random.default_rng(1234)
+    tb, off = synth.make_terms(40000, 0x1EE7)
+    sizes = [0, 1, 2, 31, 32, 33, 34, 65, 1088, 1089, 1090, 36000]
+    segs = []
+    for n in sizes:
+        ids = np.sort(rng.choice(40000, size=n, replace=False))
+        stb, stoff = synth.gather_terms(tb, off, ids)
+        post = rng.integers(0, 1 << 20, size=n, dtype=np.int64).astype(np.uint32)
+        segs.append(FlatSegment(stb, stoff, A.II2_SEG_DECODED, post=post,
+                                post_off=np.arange(n + 1, dtype=np.uint64)))
+    t = lambda i: synth.term_at(tb, off, i)
+    picks = [0, 1, 2, 30, 31, 32, 33, 34, 1000, 1088, 1089, 20000, 39998, 39999]
+    bounds = [(None, None), (b"", None), (None, b""), (b"\x00", b"\x01"), (b"zzzz", None), (None, b"zzzz")]
+    for i in picks:
+        bounds += [(t(i), t(i)), (t(i), None), (None, t(i)), (t(i) + b"\x00", None), (None, t(i)[:-1]),
+                   (t(i), t(min(39999, i + 40))), (t(i)[:-1], t(min(39999, i + 33)) + b"~")]
+    bounds.append((t(500), t(400)))
+    for lo, hi in bounds:
+        assert_read_equal(engine.read_range(segs, lo, hi), orc.read_range(segs, lo, hi))
+    prefixes = [b"", t(0), t(39999), t(1089)[:4], t(20000)[:3], t(33)[:2], t(32)[:1], b"zzzz", b"\x00",
+                t(31) + b"x"]
+    _assert_prefix_equal(engine.prefix_search(segs, prefixes), orc.prefix_search(segs, prefixes))
+
+
 def test_read_keeps_empty_lists(engine, orc):
     seg = FlatSegment.from_items([(b"t1", [10, 500, 300]), (b"t2", []), (b"t3", [66, 5513])])
     got = engine.read_range([seg])
