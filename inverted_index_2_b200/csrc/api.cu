@@ -112,28 +112,32 @@ k_slices_check(const SliceRef* __restrict__ sl, uint32_t* __restrict__ stats) {
 // Staging kernel of the pipelined ii2_merge: gathers many host arrays (pinned, mapped into the
 // device address space by unified addressing) into device blocks with plain loads over the
 // bus.  One launch per term range replaces hundreds of copy-engine requests (measured ~7 us
-// of engine time each, more than the small slices take to transfer).  src and dst of a job
-// share their phase modulo 16 bytes, so the body moves as 16-byte vectors.
+// of engine time each, more than the small slices take to transfer).
+// Reads over the bus are fastest as whole aligned lines (scratch/h2d_micro.cu on B200: 51.5 GB/s
+// from a 512-byte aligned source, 46.9 .. 49.6 GB/s at other phases), and a slice starts anywhere
+// in its host array.  So a job is laid out over the 512-byte aligned ENVELOPE of its source
+// range: vector v of the job is the 16 bytes at (src rounded down to 512) + 16 v, a warp reads
+// one aligned 512-byte block, and dst shares the phase of src modulo 512 so the stores are whole
+// lines as well.  The vectors that straddle an end of the range (at most two per job) are copied
+// byte by byte by their lane, loads first.
 struct GatherJob {
   const uint8_t* src;  // host
-  uint8_t* dst;        // device
+  uint8_t* dst;        // device, dst = src (mod 512)
   uint64_t bytes;
-  uint64_t vec0;       // 16-byte vectors of the jobs before this one (exclusive prefix)
+  uint64_t vec0;       // envelope vectors of the jobs before this one (a multiple of 32)
 };
 constexpr int kGatherThreads = 256;
 constexpr int kGatherUnroll = 4;
+constexpr uint64_t kGatherAlign = 512;
+
+// envelope vectors of one job, rounded up to whole warps
+static inline uint64_t gather_job_vectors(const void* src, uint64_t bytes) {
+  const uint64_t lead = reinterpret_cast<uintptr_t>(src) & (kGatherAlign - 1);
+  return (((lead + bytes + 15) >> 4) + 31) & ~31ull;
+}
 
 __global__ void __launch_bounds__(kGatherThreads)
 k_gather_host(const GatherJob* __restrict__ jobs, uint32_t njobs, uint64_t nvec_total) {
-  // ragged ends (< 16 bytes at either side of every job): one thread per job
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < njobs; j += gridDim.x * blockDim.x) {
-    const GatherJob g = jobs[j];
-    const uint64_t ph = (16 - (reinterpret_cast<uintptr_t>(g.src) & 15)) & 15;
-    const uint64_t head = g.bytes < ph ? g.bytes : ph;
-    for (uint64_t i = 0; i < head; i++) g.dst[i] = g.src[i];
-    const uint64_t body = (g.bytes - head) & ~15ull;
-    for (uint64_t i = head + body; i < g.bytes; i++) g.dst[i] = g.src[i];
-  }
   const uint64_t tile = (uint64_t)kGatherThreads * kGatherUnroll;
   for (uint64_t v0 = (uint64_t)blockIdx.x * tile; v0 < nvec_total; v0 += (uint64_t)gridDim.x * tile) {
     uint4 x[kGatherUnroll];
@@ -143,7 +147,7 @@ k_gather_host(const GatherJob* __restrict__ jobs, uint32_t njobs, uint64_t nvec_
       const uint64_t v = v0 + (uint64_t)u * kGatherThreads + threadIdx.x;
       d[u] = nullptr;
       if (v < nvec_total) {
-        uint32_t lo = 0, hi = njobs;  // last job with vec0 <= v
+        uint32_t lo = 0, hi = njobs;  // last job with vec0 <= v (the same job for a whole warp)
         while (hi - lo > 1) {
           const uint32_t mid = (lo + hi) >> 1;
           if (jobs[mid].vec0 <= v)
@@ -152,10 +156,24 @@ k_gather_host(const GatherJob* __restrict__ jobs, uint32_t njobs, uint64_t nvec_
             hi = mid;
         }
         const GatherJob g = jobs[lo];
-        const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(g.src) & 15)) & 15;
-        const uint64_t at = head + (v - g.vec0) * 16;
-        x[u] = *reinterpret_cast<const uint4*>(g.src + at);
-        d[u] = reinterpret_cast<uint4*>(g.dst + at);
+        const int64_t lead = (int64_t)(reinterpret_cast<uintptr_t>(g.src) & (kGatherAlign - 1));
+        const int64_t pos = (int64_t)((v - g.vec0) << 4) - lead;  // of this vector, from src
+        if (pos >= 0 && pos + 16 <= (int64_t)g.bytes) {
+          x[u] = *reinterpret_cast<const uint4*>(g.src + pos);
+          d[u] = reinterpret_cast<uint4*>(g.dst + pos);
+        } else if (pos + 16 > 0 && pos < (int64_t)g.bytes) {  // straddles an end of the range
+          uint8_t b[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int64_t q = pos + i;
+            b[i] = (q >= 0 && q < (int64_t)g.bytes) ? g.src[q] : (uint8_t)0;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int64_t q = pos + i;
+            if (q >= 0 && q < (int64_t)g.bytes) g.dst[q] = b[i];
+          }
+        }
       }
     }
 #pragma unroll
@@ -1017,8 +1035,20 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     bounds[(size_t)P * nseg + i] = segs[i].n_terms;
     inst_total += segs[i].n_terms;
   }
+  // The ranges are equal except the last two: what follows the last upload (its merge and the
+  // download of its result) is the only part of the call the bus does not cover, so the last
+  // range is small; 0.65 and 0.4 of a full range keep every range's merge + download shorter
+  // than the next range's upload.  II2_MERGE_TAPER=0 turns it off (tuning).
+  std::vector<double> cum(P + 1, 0.0);
+  {
+    const char* env_taper = getenv("II2_MERGE_TAPER");
+    const bool taper = P >= 4 && segs[big].n_terms >= 64ull * P && !(env_taper && atoi(env_taper) == 0);
+    for (int p = 0; p < P; p++)
+      cum[p + 1] = cum[p] + (taper && p == P - 2 ? 0.65 : (taper && p == P - 1 ? 0.4 : 1.0));
+  }
   for (int p = 1; p < P; p++) {
-    const uint64_t at = segs[big].n_terms * (uint64_t)p / P;
+    const uint64_t at = std::min<uint64_t>(
+        segs[big].n_terms - 1, (uint64_t)((double)segs[big].n_terms * (cum[p] / cum[P])));
     const uint32_t o = segs[big].term_off[at], n = segs[big].term_off[at + 1] - o;
     for (int i = 0; i < nseg; i++)
       bounds[(size_t)p * nseg + i] =
@@ -1047,7 +1077,26 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     const uint8_t* poff;
   };
   std::vector<DevAlias> alias(nseg);
+  // II2_MERGE_UPLOAD picks how the slices cross the bus (tuning; results are the same):
+  //   gather  one kernel per range reads every slice from pinned host memory
+  //   dma<k>  every slice is a copy-engine request, round-robin over k streams (1..4) so the
+  //           fixed cost of a request overlaps the transfer of another
+  //   hybrid<k>  term bytes and postings (the large slices) by copy engine on k streams, the
+  //           offset arrays by the gather kernel, both at once
   bool gather = getenv("II2_MERGE_NO_GATHER") == nullptr;
+  int dma_streams = 0;       // 0: copies (if any) go to sA itself
+  bool dma_large = false;    // hybrid: copy engines for term bytes and postings only
+  if (const char* m = getenv("II2_MERGE_UPLOAD")) {
+    if (!strncmp(m, "dma", 3)) {
+      gather = false;
+      dma_streams = m[3] ? atoi(m + 3) : 0;
+    } else if (!strncmp(m, "hybrid", 6)) {
+      dma_large = true;
+      dma_streams = m[6] ? atoi(m + 6) : 1;
+    }
+    if (dma_streams < 0 || dma_streams > 4) dma_streams = 4;
+    if (dma_large && dma_streams < 1) dma_streams = 1;
+  }
   auto dev_alias = [&](const void* hp, size_t align, const uint8_t** out_p) {
     *out_p = nullptr;
     if (!hp) return;  // empty array: nothing to read
@@ -1073,10 +1122,19 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     dev_alias(segs[i].post_off, 8, &alias[i].poff);
   }
 
+  if (!gather) dma_large = false;  // hybrid needs the device aliases of the offset arrays
+  EventList fork_join;             // [0] = fork (allocations done), [1 + k] = join of copy stream k
+  if (dma_streams) {
+    for (int k = 0; k < 1 + dma_streams; k++) {
+      cudaEvent_t e;
+      II2_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      fork_join.v.push_back(e);
+    }
+  }
   // Stage the slices of range p: four allocations and one check launch for all segments (an
   // allocation + a kernel per slice would cost more host time than the copies take).  Offsets
   // stay absolute: the slice's base pointers are moved back by its first offset instead.  Every
-  // slice lands at the same phase modulo 16 bytes as its source (vector copies; the moved term
+  // slice lands at the same phase modulo 512 bytes as its source (vector copies; the moved term
   // pointer keeps the 4-byte alignment the key loads need).
   const size_t nx = (size_t)nseg;
   const size_t ref_bytes = (sizeof(SliceRef) * nx + 15) & ~(size_t)15;
@@ -1096,10 +1154,11 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     for (int i = 0; i < nseg; i++) {
       const ii2_seg_view& v = segs[i];
       const size_t n1 = (size_t)(hi[i] - lo[i]) + 1;
-      tb_bytes += (size_t)(v.term_off[hi[i]] - v.term_off[lo[i]]) + 64;  // phase + tail padding
-      toff_bytes += n1 * 4 + 32;
-      post_bytes += (size_t)(v.post_off[hi[i]] - v.post_off[lo[i]]) * 4 + 32;
-      poff_bytes += n1 * 8 + 32;
+      // every slice: up to 2 x 511 bytes of phase (placed at its source's phase modulo 512)
+      tb_bytes += (size_t)(v.term_off[hi[i]] - v.term_off[lo[i]]) + 2 * kGatherAlign + 64;  // + tail padding
+      toff_bytes += n1 * 4 + 2 * kGatherAlign;
+      post_bytes += (size_t)(v.post_off[hi[i]] - v.post_off[lo[i]]) * 4 + 2 * kGatherAlign;
+      poff_bytes += n1 * 8 + 2 * kGatherAlign;
     }
     II2_TRY(L.blk_tb.alloc(tb_bytes, sA, 64));
     II2_TRY(L.blk_toff.alloc(toff_bytes / 4, sA));
@@ -1107,6 +1166,12 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     II2_TRY(L.blk_poff.alloc(poff_bytes / 8, sA));
     II2_TRY(L.blk_ref.alloc(nx, sA));
     if (gather) II2_TRY(L.blk_job.alloc(4 * nx, sA));
+    if (dma_streams) {  // the blocks are stream-ordered allocations of sA
+      II2_CUDA_TRY(cudaEventRecord(fork_join.v[0], sA));
+      for (int k = 0; k < dma_streams; k++)
+        II2_CUDA_TRY(cudaStreamWaitEvent(copy_stream(k), fork_join.v[0], 0));
+    }
+    int rr = 0;
     SliceRef* refs = reinterpret_cast<SliceRef*>(h_tab + (ref_bytes + job_bytes) * p);
     GatherJob* jobs = reinterpret_cast<GatherJob*>(h_tab + (ref_bytes + job_bytes) * p + ref_bytes);
     uint32_t njobs = 0;
@@ -1115,23 +1180,25 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     uint32_t max_n = 0;
     // one array slice: place it at the phase of its source, queue its copy
     auto place = [&](uint8_t* blk, size_t& cursor, const void* hsrc, const uint8_t* dsrc,
-                     uint64_t bytes, uint8_t** dst_out) -> int {
-      const uint8_t* src = gather ? dsrc : static_cast<const uint8_t*>(hsrc);
-      cursor = ((cursor + 15) & ~(size_t)15) + (reinterpret_cast<uintptr_t>(src) & 15);
+                     uint64_t bytes, bool large, uint8_t** dst_out) -> int {
+      const bool by_kernel = gather && !(dma_large && large);
+      const uint8_t* src = by_kernel ? dsrc : static_cast<const uint8_t*>(hsrc);
+      cursor = ((cursor + kGatherAlign - 1) & ~(size_t)(kGatherAlign - 1)) +
+               (reinterpret_cast<uintptr_t>(src) & (kGatherAlign - 1));
       uint8_t* dst = blk + cursor;
       *dst_out = dst;
       cursor += bytes;
       if (!bytes) return II2_OK;
-      if (gather) {
+      if (by_kernel) {
         GatherJob& g = jobs[njobs++];
         g.src = src;
         g.dst = dst;
         g.bytes = bytes;
         g.vec0 = nvec;
-        const uint64_t head = std::min<uint64_t>(bytes, (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15);
-        nvec += (bytes - head) >> 4;
+        nvec += gather_job_vectors(src, bytes);
       } else {
-        II2_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sA));
+        cudaStream_t sc = dma_streams ? copy_stream(rr++ % dma_streams) : sA;
+        II2_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sc));
       }
       return II2_OK;
     };
@@ -1145,14 +1212,14 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
       if ((tlen && !v.term_bytes) || (plen && !v.post)) return II2_ERR_INVALID;
       uint8_t *d_tb, *d_toff, *d_post, *d_poff;
       II2_TRY(place(L.blk_tb.p, at_tb, v.term_bytes ? v.term_bytes + tfirst : nullptr,
-                    alias[i].tb ? alias[i].tb + tfirst : nullptr, tlen, &d_tb));
+                    alias[i].tb ? alias[i].tb + tfirst : nullptr, tlen, true, &d_tb));
       at_tb += 32;  // key loads read past the last term
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_toff.p), at_toff, v.term_off + lo[i],
-                    alias[i].toff + 4 * lo[i], (n + 1) * 4, &d_toff));
+                    alias[i].toff + 4 * lo[i], (n + 1) * 4, false, &d_toff));
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_post.p), at_post, v.post ? v.post + pfirst : nullptr,
-                    alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, &d_post));
+                    alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, true, &d_post));
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_poff.p), at_poff, v.post_off + lo[i],
-                    alias[i].poff + 8 * lo[i], (n + 1) * 8, &d_poff));
+                    alias[i].poff + 8 * lo[i], (n + 1) * 8, false, &d_poff));
       std::unique_ptr<ii2_seg> g(new ii2_seg());
       g->n_terms = (uint32_t)n;
       g->n_post = plen;
@@ -1176,10 +1243,17 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     II2_TRY(small_copy(L.blk_ref.p, refs, sizeof(SliceRef) * nx, sA));
     if (gather && njobs) {
       II2_TRY(small_copy(L.blk_job.p, jobs, sizeof(GatherJob) * njobs, sA));
+      // II2_GATHER_GRID=<n>: CTAs of the staging kernel (tuning; it shares the SMs with the merge)
+      const char* env_grid = getenv("II2_GATHER_GRID");
+      const uint64_t max_grid = env_grid && atoi(env_grid) > 0 ? (uint64_t)atoi(env_grid) : 64;
       const unsigned grid = (unsigned)std::min<uint64_t>(
-          64, std::max<uint64_t>(1, div_up(nvec, (uint64_t)kGatherThreads * kGatherUnroll)));
+          max_grid, std::max<uint64_t>(1, div_up(nvec, (uint64_t)kGatherThreads * kGatherUnroll)));
       k_gather_host<<<grid, kGatherThreads, 0, sA>>>(L.blk_job.p, njobs, nvec);
       II2_LAUNCHED();
+    }
+    for (int k = 0; k < dma_streams; k++) {  // join: the check and the merge read every slice
+      II2_CUDA_TRY(cudaEventRecord(fork_join.v[1 + k], copy_stream(k)));
+      II2_CUDA_TRY(cudaStreamWaitEvent(sA, fork_join.v[1 + k], 0));
     }
     if (max_n) {
       const dim3 grid(std::min<unsigned>(div_up(max_n, 256), 64u), (unsigned)nseg);
@@ -1248,8 +1322,8 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     return II2_OK;
   };
 
-  {
-    ProfScope sc("e2e_enqueue_upload", sA);
+  {  // range 0 crosses the bus alone; the later ranges share it with kernels and downloads
+    ProfScope sc("e2e_upload_first", sA);
     II2_TRY(enqueue_upload(0));
   }
   for (int p = 0; p < P; p++) {
@@ -1373,6 +1447,8 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
   if (rc != II2_OK) {
     cudaStreamSynchronize(cur_stream());
     cudaStreamSynchronize(aux_stream());
+    if (getenv("II2_MERGE_UPLOAD"))
+      for (int k = 0; k < 4; k++) cudaStreamSynchronize(copy_stream(k));
     memset(out, 0, sizeof(*out));
   }
   return rc;

@@ -47,6 +47,7 @@ int ctx_require() {
 struct ThreadStream {
   cudaStream_t own = nullptr;
   cudaStream_t aux = nullptr;
+  cudaStream_t copy[4] = {};
   cudaEvent_t ev[16] = {};
   cudaStream_t user = nullptr;
   bool use_user = false;
@@ -66,6 +67,11 @@ cudaStream_t cur_stream() {
 cudaStream_t aux_stream() {
   if (!t_stream.aux) cudaStreamCreateWithFlags(&t_stream.aux, cudaStreamNonBlocking);
   return t_stream.aux;
+}
+
+cudaStream_t copy_stream(int i) {
+  if (!t_stream.copy[i]) cudaStreamCreateWithFlags(&t_stream.copy[i], cudaStreamNonBlocking);
+  return t_stream.copy[i];
 }
 
 cudaEvent_t aux_event(int i) {

@@ -11,6 +11,7 @@ bool ctx_ready();
 int ctx_require();            // II2_OK or II2_ERR_NO_DEVICE (sets last error)
 cudaStream_t cur_stream();    // this thread's stream (caller-provided or library-owned)
 cudaStream_t aux_stream();    // a second library-owned stream of this thread (kernel overlap)
+cudaStream_t copy_stream(int i);  // copy-engine streams of this thread (staging of host slices), i < 4
 cudaEvent_t aux_event(int i);  // this thread's reusable timing-free events, i < 16
 
 // Per-thread scratch arena: one grow-only device block, bump-allocated during a pipeline call

@@ -240,6 +240,14 @@ def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
         monkeypatch.setenv("II2_MERGE_PARTS", parts)
         monkeypatch.delenv("II2_MERGE_SLACK", raising=False)
         assert_merge_equal(engine.merge(psegs, w.removed, decoded=True), exp)
+    # every staging mode moves the same bytes: copy engines on k streams, or copy engines for
+    # term bytes / postings next to the gather kernel for the offset arrays
+    monkeypatch.setenv("II2_MERGE_PARTS", "3")
+    for mode in ("gather", "dma", "dma2", "dma4", "hybrid", "hybrid2"):
+        monkeypatch.setenv("II2_MERGE_UPLOAD", mode)
+        assert_merge_equal(engine.merge(psegs, w.removed, decoded=True), exp)
+        assert_merge_equal(engine.merge(segs, w.removed, decoded=True), exp)  # pageable inputs
+    monkeypatch.delenv("II2_MERGE_UPLOAD", raising=False)
     # everything removed in the first ranges: min/max still come from the first / last range
     monkeypatch.setenv("II2_MERGE_PARTS", "4")
     monkeypatch.delenv("II2_MERGE_SLACK", raising=False)
