@@ -203,6 +203,37 @@ __device__ __forceinline__ void enc_block_emit_warp(const uint32_t* v, uint32_t 
   }
 }
 
+// The var-byte section of the `tail` (< 128) values after block nb of v, written at dst by one
+// warp; `my_stage` = kStageWords of shared memory private to the warp.
+__device__ __forceinline__ void enc_tail_warp(const uint32_t* v, uint32_t nb, uint32_t tail,
+                                              uint32_t* dst, uint32_t* my_stage) {
+  const unsigned lane = lane_id();
+  if (lane == 0) dst[0] = tail;
+  uint8_t* sb = reinterpret_cast<uint8_t*>(my_stage);
+  uint32_t bo = 0;
+  for (uint32_t t = 0; t < tail; t += 32) {
+    const uint32_t i = t + lane;
+    uint32_t z = 0, len = 0;
+    if (i < tail) {
+      const uint32_t idx = nb * 128 + i;
+      z = zigzag(v[idx], i ? v[idx - 1] : 0u);
+      len = vbyte_len(z);
+    }
+    const uint32_t inc = warp_inclusive_scan(len);
+    const uint32_t off = bo + inc - len;
+    for (uint32_t k = 0; k < len; k++) {
+      uint32_t byte = (z >> (7 * k)) & 0x7Fu;
+      if (k + 1 == len) byte |= 0x80u;
+      sb[off + k] = (uint8_t)byte;
+    }
+    bo += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  const uint32_t nwords = (bo + 3) / 4;
+  if (lane < nwords * 4 - bo) sb[bo + lane] = 0;
+  __syncwarp();
+  for (uint32_t j = lane; j < nwords; j += 32) dst[1 + j] = my_stage[j];
+}
+
 // Whole-CTA CompressUint32 of v[0..n) (global memory, n >= 128) to dst.  `table` = n/128 words
 // of global scratch (block sizes, then their exclusive prefix); `stage` = kStageWords of shared
 // memory per warp; `ws` = block-scan scratch (blockDim/32 + 2).  Every thread of the block
@@ -245,32 +276,7 @@ __device__ __forceinline__ uint32_t enc_emit_cta(const uint32_t* v, uint32_t n, 
     }
     bytes = warp_sum(bytes);
     tail_words = 1 + (bytes + 3) / 4;
-    if (warp == 0) {
-      if (lane == 0) dst[pos] = tail;
-      uint8_t* sb = reinterpret_cast<uint8_t*>(my_stage);
-      uint32_t bo = 0;
-      for (uint32_t t = 0; t < tail; t += 32) {
-        const uint32_t i = t + lane;
-        uint32_t z = 0, len = 0;
-        if (i < tail) {
-          const uint32_t idx = nb * 128 + i;
-          z = zigzag(v[idx], i ? v[idx - 1] : 0u);
-          len = vbyte_len(z);
-        }
-        const uint32_t inc = warp_inclusive_scan(len);
-        const uint32_t off = bo + inc - len;
-        for (uint32_t k = 0; k < len; k++) {
-          uint32_t byte = (z >> (7 * k)) & 0x7Fu;
-          if (k + 1 == len) byte |= 0x80u;
-          sb[off + k] = (uint8_t)byte;
-        }
-        bo += __shfl_sync(0xffffffffu, inc, 31);
-      }
-      const uint32_t nwords = (bo + 3) / 4;
-      if (lane < nwords * 4 - bo) sb[bo + lane] = 0;
-      __syncwarp();
-      for (uint32_t j = lane; j < nwords; j += 32) dst[pos + 1 + j] = my_stage[j];
-    }
+    if (warp == 0) enc_tail_warp(v, nb, tail, dst + pos, my_stage);
   }
   __syncthreads();
   return pos + tail_words;
@@ -358,6 +364,47 @@ __device__ __forceinline__ int dec_varbyte_thread(const uint32_t* w, uint64_t nw
     out[i] = prev;
   }
   return 0;
+}
+
+// One 128-value block by one warp.  p = its header word, end = end of the section, prev = the
+// value before the block.  EMIT: the values go to out[0..128) and the last one is returned;
+// else only the sum of the block's deltas (mod 2^32) is returned.  *bad is set when a width
+// or the section bound is violated.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t dec_block_warp(const uint32_t* w, uint64_t p, uint64_t end,
+                                                   uint32_t prev, uint32_t* out, bool* bad) {
+  const unsigned lane = lane_id();
+  const uint32_t h = w[p++];
+  uint32_t acc = 0;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const uint32_t f = (h >> (24 - 8 * g)) & 0xFFu;
+    const uint32_t wd = f & 0x7Fu, s = f >> 7;
+    if (wd > 32 || p + wd > end) {
+      *bad = true;
+      return 0;
+    }
+    uint32_t val = 0;
+    if (wd == 32) {
+      val = w[p + lane];
+    } else if (wd > 0) {
+      const uint32_t bit = lane * wd, wi = bit >> 5, sh = bit & 31u;
+      val = w[p + wi] >> sh;
+      if (sh + wd > 32u) val |= w[p + wi + 1] << (32u - sh);
+      val &= (1u << wd) - 1u;
+    }
+    const uint32_t d = s ? unzigzag(val) : val;
+    if (EMIT) {
+      const uint32_t value = prev + warp_inclusive_scan(d);
+      out[32 * g + lane] = value;
+      prev = __shfl_sync(0xffffffffu, value, 31);
+    } else {
+      acc += d;
+    }
+    p += wd;
+  }
+  if (EMIT) return prev;
+  return __reduce_add_sync(0xffffffffu, acc);
 }
 
 // Whole-stream decode by one warp (any length).  n = expected values (from dec_count).

@@ -16,9 +16,17 @@ namespace ii2 {
 constexpr int kCodecThreads = 256;
 
 // ---------------------------------------------------------------- decode
+// A list whose first bin-pack section holds at least kHugeValues values is decoded block-parallel
+// (below); n_work = {warp-per-list entries, huge lists, their blocks}.
+constexpr uint32_t kHugeValues = 128u * 64u;
+constexpr uint32_t kWalkThreads = 1024;
+constexpr uint32_t kWalkWindow = 6144;  // words staged per round (three 16-bit arrays of it in shared memory)
+
 __global__ void __launch_bounds__(kCodecThreads)
 k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff, uint64_t nlists,
-            uint64_t* __restrict__ counts, int* __restrict__ err) {
+            uint64_t* __restrict__ counts, uint32_t* __restrict__ n_work,
+            uint32_t* __restrict__ huge_list, uint32_t* __restrict__ huge_gstart,
+            int* __restrict__ err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = woff[i], b = woff[i + 1];
@@ -26,8 +34,156 @@ k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
   if (c < 0) {
     atomicExch(err, 1);
     c = 0;
+  } else if (b > a && words[a] >= kHugeValues) {
+    const uint32_t h = atomicAdd(&n_work[1], 1u);
+    huge_list[h] = (uint32_t)i;
+    huge_gstart[h] = atomicAdd(&n_work[2], words[a] >> 7);
   }
   counts[i] = (uint64_t)c;
+}
+
+// ---- long lists, block-parallel --------------------------------------------------------
+// dec_warp walks a list block by block: the place of a block is known only when the widths of
+// the block before it are, and its first value only when every delta before it is summed —
+// two dependent chains of global loads, ~3 us per 128 values, which is all there is to
+// overlap when a batch holds one 16 M-value list (C4).  Here the chains are cut:
+//   walk      one CTA per list stages a window of the stream in shared memory as
+//             "where the block would end if this word were a header" (all words in parallel);
+//             one thread then hops from header to header, two blocks per dependent
+//             shared-memory load, and the block's threads write the positions out
+//             (full pointer doubling was measured: faster only for 1-bit blocks, 2x slower
+//             for 13-bit ones — W log W shared-memory traffic against one load per block);
+//   sums      one warp per block: the sum of its deltas;  exclusive scan over all blocks;
+//   blocks    one warp per block decodes it from (first value + the deltas before it).
+// What follows the first section (the var-byte tail) goes through dec_warp.
+__global__ void __launch_bounds__(kWalkThreads)
+k_dec_walk(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+           const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_gstart,
+           uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist, int* __restrict__ err) {
+  constexpr uint32_t W = kWalkWindow, PER = W / kWalkThreads;
+  __shared__ uint16_t nxt[W];       // where the block ends if word i is a header (window-relative)
+  __shared__ uint16_t nxt2[W];      // the same two blocks ahead (or the exit from the window)
+  __shared__ uint16_t hdr[W];       // the headers found, in order (a block of zero widths is one word)
+  __shared__ uint32_t s_p, s_cnt;
+  const uint32_t L = blockIdx.x, tid = threadIdx.x;
+  const uint64_t a = woff[huge_list[L]];
+  const uint32_t* w = words + a;
+  const uint32_t nb = w[0] >> 7;
+  const uint64_t end = w[1];  // dec_count checked 3 <= len <= words of the list
+  const uint32_t gs = huge_gstart[L];
+  uint64_t wb = 3;
+  uint32_t b = 0;
+  while (b < nb && wb < end) {
+    const uint32_t wn = (uint32_t)min((uint64_t)W, end - wb);
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) {
+      const uint32_t i = tid + j * kWalkThreads;
+      if (i < wn) {
+        const uint32_t x = w[wb + i];
+        nxt[i] = (uint16_t)(i + 1 + ((x >> 24) & 0x7Fu) + ((x >> 16) & 0x7Fu) +
+                            ((x >> 8) & 0x7Fu) + (x & 0x7Fu));
+      }
+    }
+    // the next window starts 0 .. 508 words past this one: have the L2 fetch it during the walk
+    if (wb + wn < end) {
+      const uint64_t at = wb + wn + (uint64_t)tid * 32;
+      if (tid * 32 < W + 512 && at < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(w + at));
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) {
+      const uint32_t i = tid + j * kWalkThreads;
+      if (i < wn) {
+        const uint32_t n = nxt[i];
+        nxt2[i] = n < wn ? nxt[n] : (uint16_t)n;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // one thread hops from header to header, two blocks per dependent shared-memory load
+      const uint32_t room = nb - b;
+      uint32_t p = 0, cnt = 0;
+      while (p < wn && cnt < room) {
+        const uint32_t q = nxt[p];
+        hdr[cnt++] = (uint16_t)p;
+        if (q < wn && cnt < room) hdr[cnt++] = (uint16_t)q;
+        p = nxt2[p];
+      }
+      s_p = p;
+      s_cnt = cnt;
+    }
+    __syncthreads();
+    const uint32_t cnt = s_cnt;
+    for (uint32_t k = tid; k < cnt; k += kWalkThreads) {
+      bpos[gs + b + k] = a + wb + hdr[k];
+      blist[gs + b + k] = L;
+    }
+    wb += s_p;
+    b += cnt;
+    __syncthreads();
+  }
+  if (b < nb && tid == 0) {  // the section ends before its blocks do
+    atomicExch(err, 1);
+    for (; b < nb; b++) {
+      bpos[gs + b] = ~0ull;
+      blist[gs + b] = L;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kCodecThreads)
+k_dec_blocksum(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+               const uint32_t* __restrict__ huge_list, const uint64_t* __restrict__ bpos,
+               const uint32_t* __restrict__ blist, uint32_t nblocks, uint64_t* __restrict__ bsum,
+               int* __restrict__ err) {
+  const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blk > nblocks) return;
+  uint32_t sum = 0;
+  if (blk < nblocks && bpos[blk] != ~0ull) {
+    const uint64_t a = woff[huge_list[blist[blk]]];
+    bool bad = false;
+    sum = intcomp::dec_block_warp<false>(words, bpos[blk], a + words[a + 1], 0u, nullptr, &bad);
+    if (bad) {
+      if (lane_id() == 0) atomicExch(err, 1);
+      sum = 0;
+    }
+  }
+  if (lane_id() == 0) bsum[blk] = sum;  // [nblocks] = 0: room for the scan's total
+}
+
+__global__ void __launch_bounds__(kCodecThreads)
+k_dec_blocks(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+             const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_gstart,
+             const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ blist,
+             uint32_t nblocks, const uint64_t* __restrict__ bscan,
+             const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out) {
+  const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blk >= nblocks || bpos[blk] == ~0ull) return;
+  const uint32_t L = blist[blk], gs = huge_gstart[L], i = huge_list[L];
+  const uint64_t a = woff[i];
+  // sums are taken modulo 2^32 (unsorted lists have negative deltas): the low half of the
+  // 64-bit scan is the 32-bit sum
+  const uint32_t prev = words[a + 2] + (uint32_t)(bscan[blk] - bscan[gs]);
+  bool bad = false;
+  intcomp::dec_block_warp<true>(words, bpos[blk], a + words[a + 1], prev,
+                                out + out_off[i] + 128ull * (blk - gs), &bad);
+}
+
+// the sections after the first one of every long list (normally the var-byte tail)
+__global__ void __launch_bounds__(kCodecThreads)
+k_dec_huge_tail(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+                const uint32_t* __restrict__ huge_list, uint32_t n_huge,
+                const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out,
+                int* __restrict__ err) {
+  const uint32_t L = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (L >= n_huge) return;
+  const uint32_t i = huge_list[L];
+  const uint64_t a = woff[i], b = woff[i + 1];
+  const uint64_t c0 = words[a], len = words[a + 1];
+  if (a + len >= b) return;
+  const int rc = intcomp::dec_warp(words + a + len, b - a - len, out + out_off[i] + c0,
+                                   out_off[i + 1] - out_off[i] - c0);
+  if (rc && lane_id() == 0) atomicExch(err, 1);
 }
 
 // FST outputs (byte offsets) + file size -> word offsets [n+1] (file/reader.go:52,64)
@@ -50,6 +206,7 @@ k_dec_short(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
   if (i >= nlists) return;
   uint64_t a = woff[i], b = woff[i + 1];
   if (b <= a) return;  // empty run -> empty list (file/writer_test.go:15)
+  if (words[a] >= kHugeValues) return;  // block-parallel path
   if (words[a] >= 128) {
     worklist[atomicAdd(n_work, 1u)] = (uint32_t)i;
     return;
@@ -75,6 +232,7 @@ k_dec_long(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff
 int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t nlists,
                        DevBuf<uint32_t>& out, DevBuf<uint64_t>& out_off, uint64_t* total_out,
                        cudaStream_t s, bool scratch_out) {
+  ProfScope scope("k3a_decode", s);
   if (scratch_out) {
     II2_TRY(out_off.alloc_scratch(nlists + 1, s));
   } else {
@@ -85,18 +243,20 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
     return II2_ERR_UNSUPPORTED;
   }
   DevBuf<int> err;
-  DevBuf<uint32_t> n_work, worklist;
+  DevBuf<uint32_t> n_work, worklist, huge_list, huge_gstart;
   DevBuf<uint64_t> d_total;
   II2_TRY(err.alloc_scratch(1, s));
-  II2_TRY(n_work.alloc_scratch(1, s));
+  II2_TRY(n_work.alloc_scratch(4, s));
   II2_TRY(d_total.alloc_scratch(1, s));
   II2_TRY(worklist.alloc_scratch(nlists ? nlists : 1, s));
+  II2_TRY(huge_list.alloc_scratch(nlists ? nlists : 1, s));
+  II2_TRY(huge_gstart.alloc_scratch(nlists ? nlists : 1, s));
   II2_CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
-  II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, sizeof(uint32_t), s));
+  II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, 4 * sizeof(uint32_t), s));
   II2_CUDA_TRY(cudaMemsetAsync(out_off.p + nlists, 0, sizeof(uint64_t), s));
   if (nlists) {
-    k_dec_count<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(d_words, d_woff, nlists,
-                                                                        out_off.p, err.p);
+    k_dec_count<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
+        d_words, d_woff, nlists, out_off.p, n_work.p, huge_list.p, huge_gstart.p, err.p);
     II2_LAUNCHED();
   }
   II2_TRY(exclusive_scan_u64(out_off.p, nlists + 1, d_total.p, s));
@@ -104,9 +264,12 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
   int herr = 0;
   II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 20, d_total.p, sizeof(total), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 21, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 22, n_work.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
   total = pinned_scratch()[20];
   herr = *reinterpret_cast<const int*>(pinned_scratch() + 21);
+  const uint32_t n_huge = reinterpret_cast<const uint32_t*>(pinned_scratch() + 22)[1];
+  const uint32_t n_hblocks = reinterpret_cast<const uint32_t*>(pinned_scratch() + 22)[2];
   if (herr) {
     set_last_error("undecodable intcomp stream in batch");
     return II2_ERR_CORRUPT;
@@ -122,6 +285,27 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
     II2_LAUNCHED();
     k_dec_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_words, d_woff, out_off.p, out.p, worklist.p,
                                                      n_work.p, err.p);
+    II2_LAUNCHED();
+  }
+  if (n_huge) {
+    DevBuf<uint64_t> bpos, bsum;
+    DevBuf<uint32_t> blist;
+    II2_TRY(bpos.alloc_scratch(n_hblocks, s));
+    II2_TRY(blist.alloc_scratch(n_hblocks, s));
+    II2_TRY(bsum.alloc_scratch((size_t)n_hblocks + 1, s));
+    k_dec_walk<<<n_huge, kWalkThreads, 0, s>>>(d_words, d_woff, huge_list.p, huge_gstart.p, bpos.p,
+                                               blist.p, err.p);
+    II2_LAUNCHED();
+    k_dec_blocksum<<<div_up(((uint64_t)n_hblocks + 1) * 32, kCodecThreads), kCodecThreads, 0, s>>>(
+        d_words, d_woff, huge_list.p, bpos.p, blist.p, n_hblocks, bsum.p, err.p);
+    II2_LAUNCHED();
+    II2_TRY(exclusive_scan_u64(bsum.p, (uint64_t)n_hblocks + 1, nullptr, s));
+    k_dec_blocks<<<div_up((uint64_t)n_hblocks * 32, kCodecThreads), kCodecThreads, 0, s>>>(
+        d_words, d_woff, huge_list.p, huge_gstart.p, bpos.p, blist.p, n_hblocks, bsum.p, out_off.p,
+        out.p);
+    II2_LAUNCHED();
+    k_dec_huge_tail<<<div_up((uint64_t)n_huge * 32, kCodecThreads), kCodecThreads, 0, s>>>(
+        d_words, d_woff, huge_list.p, n_huge, out_off.p, out.p, err.p);
     II2_LAUNCHED();
   }
   II2_CUDA_TRY(cudaMemcpyAsync(&herr, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
@@ -176,48 +360,114 @@ k_enc_size_short(const uint32_t* __restrict__ in, const uint64_t* __restrict__ o
   sizes[i] = intcomp::enc_size_thread_small(in + a, (uint32_t)n);
 }
 
-// one CTA per huge list: Σ block sizes + tail
+// Huge lists (>= kHugeList values) are cut into slices of blocks, one CTA per slice (grid.y):
+// a 16 M-value list is 131 072 independent blocks, not one CTA's work (C4: 14 ms -> well under
+// one).  Size pass: block sizes into the list's table, one partial sum per slice; a warp per
+// list adds the partials and the tail.  Emit pass: a slice starts after the partials before it.
+constexpr uint32_t kSliceBlocks = 64;  // blocks a slice holds at least
+__device__ __forceinline__ uint32_t huge_slices(uint32_t nb, uint32_t ymax) {
+  const uint32_t y = nb / kSliceBlocks;
+  return y < 1 ? 1 : (y > ymax ? ymax : y);
+}
+
 __global__ void __launch_bounds__(1024)
 k_enc_size_huge(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
-                uint64_t* __restrict__ sizes, const uint32_t* __restrict__ worklist,
-                const uint32_t* __restrict__ n_work) {
+                uint32_t* __restrict__ tables, uint64_t* __restrict__ part, uint32_t ymax,
+                const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
   __shared__ uint64_t ws[1024 / 32 + 2];
   if (blockIdx.x >= n_work[1]) return;
   const uint32_t i = worklist[nlists - 1 - blockIdx.x];
   const uint32_t* v = in + off[i];
   const uint32_t n = (uint32_t)(off[i + 1] - off[i]);
-  const uint32_t nb = n >> 7, tail = n & 127u;
+  const uint32_t nb = n >> 7;
+  const uint32_t Y = huge_slices(nb, ymax), y = blockIdx.y;
+  if (y >= Y) return;
+  const uint32_t b0 = (uint32_t)((uint64_t)nb * y / Y), b1 = (uint32_t)((uint64_t)nb * (y + 1) / Y);
+  uint32_t* table = tables + ((off[i] - off[0]) >> 7);
   uint64_t acc = 0;
-  for (uint32_t b = warp_id(); b < nb; b += blockDim.x >> 5) {
+  for (uint32_t b = b0 + warp_id(); b < b1; b += blockDim.x >> 5) {
     const uint32_t w = intcomp::enc_block_size_warp(v, b);
-    if (lane_id() == 0) acc += w;
-  }
-  if (tail && threadIdx.x < 32) {
-    uint32_t bytes = 0;
-    for (uint32_t t = threadIdx.x; t < tail; t += 32) {
-      const uint32_t idx = nb * 128 + t;
-      bytes += intcomp::vbyte_len(intcomp::zigzag(v[idx], t ? v[idx - 1] : 0u));
+    if (lane_id() == 0) {
+      table[b] = w;
+      acc += w;
     }
-    bytes = warp_sum(bytes);
-    if (threadIdx.x == 0) acc += 1 + (bytes + 3) / 4;
   }
   uint64_t tot;
   block_exclusive_scan(acc, ws, tot);
-  if (threadIdx.x == 0) sizes[i] = 3 + tot;
+  if (threadIdx.x == 0) part[(uint64_t)blockIdx.x * ymax + y] = tot;
+}
+
+// one warp per huge list: 3 header words + the slices' partial sums + the var-byte tail
+__global__ void __launch_bounds__(kCodecThreads)
+k_enc_size_huge_fin(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off,
+                    uint64_t nlists, uint64_t* __restrict__ sizes,
+                    const uint64_t* __restrict__ part, uint32_t ymax,
+                    const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
+  const uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (h >= n_work[1]) return;
+  const uint32_t i = worklist[nlists - 1 - h];
+  const uint32_t* v = in + off[i];
+  const uint32_t n = (uint32_t)(off[i + 1] - off[i]);
+  const uint32_t nb = n >> 7, tail = n & 127u;
+  const uint32_t Y = huge_slices(nb, ymax);
+  uint64_t acc = 0;
+  for (uint32_t y = lane_id(); y < Y; y += 32) acc += part[(uint64_t)h * ymax + y];
+  uint32_t bytes = 0;
+  for (uint32_t t = lane_id(); t < tail; t += 32) {
+    const uint32_t idx = nb * 128 + t;
+    bytes += intcomp::vbyte_len(intcomp::zigzag(v[idx], t ? v[idx - 1] : 0u));
+  }
+  bytes = warp_sum(bytes);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane_id() == 0) sizes[i] = 3 + acc + (tail ? 1 + (bytes + 3) / 4 : 0);
 }
 
 __global__ void __launch_bounds__(1024)
 k_enc_emit_huge(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
                 const uint64_t* __restrict__ woff, uint32_t* __restrict__ words,
-                uint32_t* __restrict__ tables, const uint32_t* __restrict__ worklist,
-                const uint32_t* __restrict__ n_work) {
+                uint32_t* __restrict__ tables, const uint64_t* __restrict__ part, uint32_t ymax,
+                const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
   __shared__ uint64_t ws[1024 / 32 + 2];
   __shared__ uint32_t stage[32 * intcomp::kStageWords];
   if (blockIdx.x >= n_work[1]) return;
   const uint32_t i = worklist[nlists - 1 - blockIdx.x];
+  const uint32_t* v = in + off[i];
+  const uint32_t n = (uint32_t)(off[i + 1] - off[i]);
+  const uint32_t nb = n >> 7, tail = n & 127u;
+  const uint32_t Y = huge_slices(nb, ymax), y = blockIdx.y;
+  if (y >= Y) return;
+  const uint32_t b0 = (uint32_t)((uint64_t)nb * y / Y), b1 = (uint32_t)((uint64_t)nb * (y + 1) / Y);
   // the block table of list i lives at (off[i] - off[0]) / 128 of the shared table scratch
-  intcomp::enc_emit_cta(in + off[i], (uint32_t)(off[i + 1] - off[i]), words + woff[i],
-                        tables + ((off[i] - off[0]) >> 7), stage, ws);
+  uint32_t* table = tables + ((off[i] - off[0]) >> 7);
+  uint32_t* dst = words + woff[i];
+  // words of the slices before this one, and of all slices (ymax <= 1024 = the CTA)
+  const uint64_t mine = threadIdx.x < Y ? part[(uint64_t)blockIdx.x * ymax + threadIdx.x] : (uint64_t)0;
+  uint64_t total, before;
+  block_exclusive_scan<uint64_t>(mine, ws, total);
+  __syncthreads();
+  block_exclusive_scan<uint64_t>(threadIdx.x < y ? mine : (uint64_t)0, ws, before);
+  __syncthreads();
+  uint64_t run = before;
+  for (uint32_t base = b0; base < b1; base += blockDim.x) {
+    const uint32_t b = base + threadIdx.x;
+    const uint64_t x = b < b1 ? table[b] : 0u;
+    uint64_t tot;
+    const uint64_t ex = block_exclusive_scan(x, ws, tot);
+    if (b < b1) table[b] = (uint32_t)(run + ex);
+    run += tot;
+  }
+  __syncthreads();
+  uint32_t* my_stage = stage + warp_id() * intcomp::kStageWords;
+  for (uint32_t b = b0 + warp_id(); b < b1; b += blockDim.x >> 5)
+    intcomp::enc_block_emit_warp(v, b, dst + 3 + table[b], my_stage);
+  if (y == 0 && threadIdx.x == 0) {
+    dst[0] = nb * 128;
+    dst[1] = 3 + (uint32_t)total;
+    dst[2] = v[0];
+  }
+  if (y == Y - 1 && tail && warp_id() == 0)
+    intcomp::enc_tail_warp(v, nb, tail, dst + 3 + (uint32_t)total, my_stage);
 }
 
 __global__ void __launch_bounds__(kCodecThreads)
@@ -261,6 +511,7 @@ k_enc_emit_long(const uint32_t* __restrict__ in, const uint64_t* __restrict__ of
 int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nlists,
                        uint64_t nvals_hint, DevBuf<uint32_t>& words, DevBuf<uint64_t>& woff,
                        uint64_t* total_words, cudaStream_t s) {
+  ProfScope scope("k3a_encode", s);
   if (nlists >= (1ull << 32)) {
     set_last_error("more than 2^32 lists in one encode batch");
     return II2_ERR_UNSUPPORTED;
@@ -276,8 +527,17 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
   // at most n_vals / kHugeList lists can be huge; n_vals is only known on the device here, so
   // the launch covers min(nlists, that bound from the caller) CTAs that exit when out of work
   const unsigned huge_grid = (unsigned)std::min<uint64_t>(nlists, nvals_hint / kHugeList + 1);
+  // slices per huge list (grid.y): what the longest possible list could use, within 4096 CTAs
+  // for the launch — the number of huge lists is only known on the device, CTAs past it or past
+  // a list's own slice count exit at once, and 64 K of those were measured at +0.2 ms per batch
+  const unsigned ymax = (unsigned)std::min<uint64_t>(
+      1024, std::max<uint64_t>(1, std::min<uint64_t>((nvals_hint >> 7) / kSliceBlocks,
+                                                     4096 / std::max(1u, huge_grid))));
+  const dim3 huge_dim(huge_grid, ymax);
   DevBuf<uint32_t> tables;
+  DevBuf<uint64_t> part;
   II2_TRY(tables.alloc_scratch((nvals_hint >> 7) + nlists + 1, s));
+  II2_TRY(part.alloc_scratch((size_t)huge_grid * ymax + 1, s));
   if (nlists) {
     k_enc_size_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
         d_in, d_off, nlists, woff.p, worklist.p, n_work.p);
@@ -285,7 +545,11 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
     k_enc_size_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_in, d_off, woff.p, worklist.p,
                                                           n_work.p);
     II2_LAUNCHED();
-    k_enc_size_huge<<<huge_grid, 1024, 0, s>>>(d_in, d_off, nlists, woff.p, worklist.p, n_work.p);
+    k_enc_size_huge<<<huge_dim, 1024, 0, s>>>(d_in, d_off, nlists, tables.p, part.p, ymax,
+                                              worklist.p, n_work.p);
+    II2_LAUNCHED();
+    k_enc_size_huge_fin<<<div_up((uint64_t)huge_grid * 32, kCodecThreads), kCodecThreads, 0, s>>>(
+        d_in, d_off, nlists, woff.p, part.p, ymax, worklist.p, n_work.p);
     II2_LAUNCHED();
   }
   II2_TRY(exclusive_scan_u64(woff.p, nlists + 1, d_total.p, s));
@@ -300,8 +564,8 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
     k_enc_emit_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_in, d_off, woff.p, words.p,
                                                           worklist.p, n_work.p);
     II2_LAUNCHED();
-    k_enc_emit_huge<<<huge_grid, 1024, 0, s>>>(d_in, d_off, nlists, woff.p, words.p, tables.p,
-                                               worklist.p, n_work.p);
+    k_enc_emit_huge<<<huge_dim, 1024, 0, s>>>(d_in, d_off, nlists, woff.p, words.p, tables.p,
+                                              part.p, ymax, worklist.p, n_work.p);
     II2_LAUNCHED();
   }
   if (total_words) *total_words = total;

@@ -546,6 +546,40 @@ def test_intcomp_matches_oracle(engine, orc):
     assert np.array_equal(oo, off) and np.array_equal(ov, post)
 
 
+def test_intcomp_long_lists_block_parallel(engine, orc):
+    """Lists of >= 8192 values are decoded block-parallel (header walk in shared memory, delta
+    sums, scan, one warp per block): sizes around the threshold, with and without a var-byte
+    tail, unsorted values (negative deltas, sums wrap modulo 2^32), streams longer than one
+    16384-word walk window, several long lists next to short ones in one batch."""
+    rng = np.random.default_rng(77)
+    lists = [[7], [], list(range(300))]
+    for n in (8191, 8192, 8193, 8192 + 127, 8192 + 128, 16384, 20000, 65536 + 5):
+        lists.append(np.cumsum(rng.integers(1, 33, size=n)).astype(np.uint32).tolist())
+    lists.append(rng.integers(0, 1 << 32, size=40000, dtype=np.uint64).astype(np.uint32).tolist())
+    lists.append([5] * 30000)                                   # all widths 0: one-word blocks
+    lists.append(np.cumsum(rng.integers(1, 1 << 20, size=150000) % (1 << 32)).astype(np.uint32).tolist())
+    lists.append([0xFFFFFFFF, 0, 0xFFFFFFFF, 1] * 4096)         # 32-bit zig-zag groups
+    lists.append([3, 2, 1])
+    post, off = _lists_to_flat(lists)
+    ew, eo = orc.intcomp_encode_batch(post, off)
+    dv, do = engine.intcomp_decode_batch(ew, eo)
+    assert np.array_equal(do, off) and np.array_equal(dv, post)
+    gw, go = engine.intcomp_encode_batch(post, off)
+    assert np.array_equal(go, eo) and np.array_equal(gw, ew)
+    # a long list whose section ends before its blocks do, and one with a width above 32
+    from inverted_index_2_b200.engine import EngineError
+    one = np.arange(0, 3 * 16384, 3, dtype=np.uint32)
+    w, o = orc.intcomp_encode_batch(one, np.array([0, len(one)], dtype=np.uint64))
+    short = w.copy()
+    short[0] += 128                     # one block more than the section holds
+    bad_width = w.copy()
+    bad_width[3] = (bad_width[3] & 0x00FFFFFF) | (40 << 24)
+    for words in (short, bad_width):
+        with pytest.raises(EngineError) as e:
+            engine.intcomp_decode_batch(words, o)
+        assert e.value.code == A.II2_ERR_CORRUPT
+
+
 def test_intcomp_rejects_corrupt(engine):
     from inverted_index_2_b200.engine import EngineError
     words = np.array([256, 2, 0, 0], dtype=np.uint32)  # section length below its own header
