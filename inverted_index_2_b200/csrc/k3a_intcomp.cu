@@ -20,7 +20,7 @@ constexpr int kCodecThreads = 256;
 // (below); n_work = {warp-per-list entries, huge lists, their blocks}.
 constexpr uint32_t kHugeValues = 128u * 64u;
 constexpr uint32_t kWalkThreads = 1024;
-constexpr uint32_t kWalkWindow = 6144;  // words staged per round (three 16-bit arrays of it in shared memory)
+constexpr uint32_t kWalkWindow = 10240;  // words staged per round (two 16-bit arrays of it in shared memory)
 
 __global__ void __launch_bounds__(kCodecThreads)
 k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff, uint64_t nlists,
@@ -49,10 +49,11 @@ k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
 // overlap when a batch holds one 16 M-value list (C4).  Here the chains are cut:
 //   walk      one CTA per list stages a window of the stream in shared memory as
 //             "where the block would end if this word were a header" (all words in parallel);
-//             one thread then hops from header to header, two blocks per dependent
-//             shared-memory load, and the block's threads write the positions out
-//             (full pointer doubling was measured: faster only for 1-bit blocks, 2x slower
-//             for 13-bit ones — W log W shared-memory traffic against one load per block);
+//             three rounds of pointer doubling turn it into "eight blocks ahead", one thread
+//             hops along that (one dependent shared-memory load per eight blocks) and the
+//             CTA's threads fill in the blocks between the hops (one thread hopping block by
+//             block: ~60 clocks per block, 4.2 ms for 16 M values; doubling all the way:
+//             faster only for 1-bit blocks — W log W shared-memory traffic);
 //   sums      one warp per block: the sum of its deltas;  exclusive scan over all blocks;
 //   blocks    one warp per block decodes it from (first value + the deltas before it).
 // What follows the first section (the var-byte tail) goes through dec_warp.
@@ -60,11 +61,12 @@ __global__ void __launch_bounds__(kWalkThreads)
 k_dec_walk(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
            const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_gstart,
            uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist, int* __restrict__ err) {
-  constexpr uint32_t W = kWalkWindow, PER = W / kWalkThreads;
-  __shared__ uint16_t nxt[W];       // where the block ends if word i is a header (window-relative)
-  __shared__ uint16_t nxt2[W];      // the same two blocks ahead (or the exit from the window)
-  __shared__ uint16_t hdr[W];       // the headers found, in order (a block of zero widths is one word)
-  __shared__ uint32_t s_p, s_cnt;
+  constexpr uint32_t W = kWalkWindow, PER = W / kWalkThreads, SENT = 0xFFFFu;
+  constexpr uint32_t HOP = 8;        // blocks per hop of the serial chain (three squarings)
+  __shared__ uint16_t nxt[W];        // where the block ends if word i is a header (window-relative)
+  __shared__ uint16_t jmp[W];        // HOP blocks ahead of i, SENT if that leaves the window
+  __shared__ uint16_t hop[W / HOP + 2];  // every HOP-th header, in order
+  __shared__ uint32_t s_p, s_tot, s_hops;
   const uint32_t L = blockIdx.x, tid = threadIdx.x;
   const uint64_t a = woff[huge_list[L]];
   const uint32_t* w = words + a;
@@ -80,46 +82,66 @@ k_dec_walk(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff
       const uint32_t i = tid + j * kWalkThreads;
       if (i < wn) {
         const uint32_t x = w[wb + i];
-        nxt[i] = (uint16_t)(i + 1 + ((x >> 24) & 0x7Fu) + ((x >> 16) & 0x7Fu) +
-                            ((x >> 8) & 0x7Fu) + (x & 0x7Fu));
+        const uint32_t n = i + 1 + ((x >> 24) & 0x7Fu) + ((x >> 16) & 0x7Fu) + ((x >> 8) & 0x7Fu) +
+                           (x & 0x7Fu);
+        nxt[i] = (uint16_t)n;
+        jmp[i] = (uint16_t)(n < wn ? n : SENT);
       }
     }
-    // the next window starts 0 .. 508 words past this one: have the L2 fetch it during the walk
+    // the next window starts 0 .. 508 words past this one: have the L2 fetch it meanwhile
     if (wb + wn < end) {
       const uint64_t at = wb + wn + (uint64_t)tid * 32;
       if (tid * 32 < W + 512 && at < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(w + at));
     }
     __syncthreads();
+    // jmp: 1 -> 2 -> 4 -> 8 blocks ahead (pointer doubling, all words at once)
+#pragma unroll 1
+    for (uint32_t r = 1; r < HOP; r <<= 1) {
+      uint16_t nj[PER];
 #pragma unroll
-    for (uint32_t j = 0; j < PER; j++) {
-      const uint32_t i = tid + j * kWalkThreads;
-      if (i < wn) {
-        const uint32_t n = nxt[i];
-        nxt2[i] = n < wn ? nxt[n] : (uint16_t)n;
+      for (uint32_t j = 0; j < PER; j++) {
+        const uint32_t i = tid + j * kWalkThreads;
+        const uint32_t t = i < wn ? jmp[i] : SENT;
+        nj[j] = t != SENT ? jmp[t] : (uint16_t)SENT;
       }
+      __syncthreads();
+#pragma unroll
+      for (uint32_t j = 0; j < PER; j++) {
+        const uint32_t i = tid + j * kWalkThreads;
+        if (i < wn) jmp[i] = nj[j];
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    const uint32_t room = nb - b;
     if (tid == 0) {
-      // one thread hops from header to header, two blocks per dependent shared-memory load
-      const uint32_t room = nb - b;
+      // the only serial part: one dependent shared-memory load per HOP blocks
+      const uint32_t max_hops = (room + HOP - 1) / HOP;
       uint32_t p = 0, cnt = 0;
-      while (p < wn && cnt < room) {
-        const uint32_t q = nxt[p];
-        hdr[cnt++] = (uint16_t)p;
-        if (q < wn && cnt < room) hdr[cnt++] = (uint16_t)q;
-        p = nxt2[p];
+      while (p != SENT && cnt < max_hops) {
+        hop[cnt++] = (uint16_t)p;
+        p = jmp[p];
       }
-      s_p = p;
-      s_cnt = cnt;
+      s_hops = cnt;
     }
     __syncthreads();
-    const uint32_t cnt = s_cnt;
-    for (uint32_t k = tid; k < cnt; k += kWalkThreads) {
-      bpos[gs + b + k] = a + wb + hdr[k];
-      blist[gs + b + k] = L;
+    // thread k fills in the blocks between hop k and hop k + 1; the last one finds where the
+    // chain leaves the window
+    const uint32_t hops = s_hops;
+    for (uint32_t k = tid; k < hops; k += kWalkThreads) {
+      uint32_t h = hop[k], v = 0;
+      for (; v < HOP && h < wn && k * HOP + v < room; v++) {
+        bpos[gs + b + k * HOP + v] = a + wb + h;
+        blist[gs + b + k * HOP + v] = L;
+        h = nxt[h];
+      }
+      if (k + 1 == hops) {
+        s_p = h;  // first header past the window (or past the blocks this section holds)
+        s_tot = k * HOP + v;
+      }
     }
+    __syncthreads();
     wb += s_p;
-    b += cnt;
+    b += s_tot;
     __syncthreads();
   }
   if (b < nb && tid == 0) {  // the section ends before its blocks do

@@ -551,6 +551,7 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
     return II2_ERR_UNSUPPORTED;
   }
   cudaStream_t s = cur_stream();
+  ProfScope scope("k3b_put", s);
   II2_TRY(bm_reserve(bm, n, s));
   const uint32_t D = (uint32_t)bm->n;
   const uint64_t mask = bm->table_cap - 1;
@@ -637,6 +638,7 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
   *n = 0;
   II2_TRY(ctx_require());
   cudaStream_t s = cur_stream();
+  ProfScope scope("k3b_get", s);
   const uint32_t meta_cap = (uint32_t)std::min<uint64_t>(65536, nenc / 4 + 1);
   DevBuf<uint8_t> d_enc;
   DevBuf<GetMeta> d_meta;
