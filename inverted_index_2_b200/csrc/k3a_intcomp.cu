@@ -17,16 +17,18 @@ constexpr int kCodecThreads = 256;
 
 // ---------------------------------------------------------------- decode
 // A list whose first bin-pack section holds at least kHugeValues values is decoded block-parallel
-// (below); n_work = {warp-per-list entries, huge lists, their blocks}.
+// (below); n_work = {warp-per-list entries, huge lists, their blocks, their tiles}.
 constexpr uint32_t kHugeValues = 128u * 64u;
 constexpr uint32_t kWalkThreads = 1024;
-constexpr uint32_t kWalkWindow = 10240;  // words staged per round (two 16-bit arrays of it in shared memory)
+constexpr uint32_t kTileWords = 16384;  // stream words per tile of the header walk
+constexpr uint32_t kTileEntries = 512;  // a block is <= 509 words: a tile is entered at offset 0 .. 508
+constexpr uint32_t kChainBatch = 16;    // tiles whose maps the chain kernel stages at once
 
 __global__ void __launch_bounds__(kCodecThreads)
 k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff, uint64_t nlists,
             uint64_t* __restrict__ counts, uint32_t* __restrict__ n_work,
             uint32_t* __restrict__ huge_list, uint32_t* __restrict__ huge_gstart,
-            int* __restrict__ err) {
+            uint32_t* __restrict__ huge_tstart, int* __restrict__ err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = woff[i], b = woff[i + 1];
@@ -38,6 +40,7 @@ k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
     const uint32_t h = atomicAdd(&n_work[1], 1u);
     huge_list[h] = (uint32_t)i;
     huge_gstart[h] = atomicAdd(&n_work[2], words[a] >> 7);
+    huge_tstart[h] = atomicAdd(&n_work[3], (words[a + 1] - 3 + kTileWords - 1) / kTileWords);
   }
   counts[i] = (uint64_t)c;
 }
@@ -46,110 +49,145 @@ k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
 // dec_warp walks a list block by block: the place of a block is known only when the widths of
 // the block before it are, and its first value only when every delta before it is summed —
 // two dependent chains of global loads, ~3 us per 128 values, which is all there is to
-// overlap when a batch holds one 16 M-value list (C4).  Here the chains are cut:
-//   walk      one CTA per list stages a window of the stream in shared memory as
-//             "where the block would end if this word were a header" (all words in parallel);
-//             three rounds of pointer doubling turn it into "eight blocks ahead", one thread
-//             hops along that (one dependent shared-memory load per eight blocks) and the
-//             CTA's threads fill in the blocks between the hops (one thread hopping block by
-//             block: ~60 clocks per block, 4.2 ms for 16 M values; doubling all the way:
-//             faster only for 1-bit blocks — W log W shared-memory traffic);
-//   sums      one warp per block: the sum of its deltas;  exclusive scan over all blocks;
-//   blocks    one warp per block decodes it from (first value + the deltas before it).
+// overlap when a batch holds one 16 M-value list (C4).  Here both chains are cut.
+// Where the headers are (speculative parse over fixed tiles of kTileWords stream words):
+//   tile maps  a block is at most 509 words, so the header chain enters a tile at one of 509
+//              offsets.  One CTA per tile stages "where the block would end if this word were a
+//              header" for every word, and 509 threads walk the tile from every possible entry
+//              at once: map[entry] = (headers met, offset at which the next tile is entered);
+//   chain      one CTA per list composes the maps tile after tile (a shared-memory lookup per
+//              tile): the true entry and the first block number of every tile;
+//   tile walk  one CTA per tile walks it once more from its true entry and writes the header
+//              positions out.
+//   (one thread hopping through the whole stream: ~60 clocks per block, 4.2 ms for 16 M values;
+//   pointer doubling inside a window: W log W shared-memory traffic, 1.4 .. 4.9 ms.)
+// What the first values are:
+//   sums       one warp per block: the sum of its deltas;  exclusive scan over all blocks;
+//   blocks     one warp per block decodes it from (first value + the deltas before it).
 // What follows the first section (the var-byte tail) goes through dec_warp.
-__global__ void __launch_bounds__(kWalkThreads)
-k_dec_walk(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
-           const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_gstart,
-           uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist, int* __restrict__ err) {
-  constexpr uint32_t W = kWalkWindow, PER = W / kWalkThreads, SENT = 0xFFFFu;
-  constexpr uint32_t HOP = 8;        // blocks per hop of the serial chain (three squarings)
-  __shared__ uint16_t nxt[W];        // where the block ends if word i is a header (window-relative)
-  __shared__ uint16_t jmp[W];        // HOP blocks ahead of i, SENT if that leaves the window
-  __shared__ uint16_t hop[W / HOP + 2];  // every HOP-th header, in order
-  __shared__ uint32_t s_p, s_tot, s_hops;
-  const uint32_t L = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_dec_tile_fill(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+                const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_tstart,
+                uint32_t* __restrict__ tile_list) {
+  const uint32_t L = blockIdx.x;
   const uint64_t a = woff[huge_list[L]];
-  const uint32_t* w = words + a;
-  const uint32_t nb = w[0] >> 7;
-  const uint64_t end = w[1];  // dec_count checked 3 <= len <= words of the list
-  const uint32_t gs = huge_gstart[L];
-  uint64_t wb = 3;
-  uint32_t b = 0;
-  while (b < nb && wb < end) {
-    const uint32_t wn = (uint32_t)min((uint64_t)W, end - wb);
-#pragma unroll
-    for (uint32_t j = 0; j < PER; j++) {
-      const uint32_t i = tid + j * kWalkThreads;
-      if (i < wn) {
-        const uint32_t x = w[wb + i];
-        const uint32_t n = i + 1 + ((x >> 24) & 0x7Fu) + ((x >> 16) & 0x7Fu) + ((x >> 8) & 0x7Fu) +
-                           (x & 0x7Fu);
-        nxt[i] = (uint16_t)n;
-        jmp[i] = (uint16_t)(n < wn ? n : SENT);
-      }
+  const uint32_t nt = (words[a + 1] - 3 + kTileWords - 1) / kTileWords;
+  for (uint32_t t = threadIdx.x; t < nt; t += blockDim.x) tile_list[huge_tstart[L] + t] = L;
+}
+
+// stages nxt[] of one tile (dynamic shared memory, kTileWords x 16 bit); returns its length
+__device__ __forceinline__ uint32_t dec_tile_stage(const uint32_t* __restrict__ w, uint64_t len,
+                                                   uint32_t t, uint16_t* nxt) {
+  const uint64_t t0 = 3 + (uint64_t)t * kTileWords;
+  const uint32_t wn = (uint32_t)min((uint64_t)kTileWords, len - t0);
+  for (uint32_t i = threadIdx.x; i < wn; i += blockDim.x) {
+    const uint32_t x = w[t0 + i];
+    nxt[i] = (uint16_t)(i + 1 + ((x >> 24) & 0x7Fu) + ((x >> 16) & 0x7Fu) + ((x >> 8) & 0x7Fu) +
+                        (x & 0x7Fu));
+  }
+  __syncthreads();
+  return wn;
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+k_dec_tile_maps(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+                const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_tstart,
+                const uint32_t* __restrict__ tile_list, uint32_t* __restrict__ maps) {
+  extern __shared__ __align__(16) uint16_t nxt_dyn[];
+  const uint32_t tile = blockIdx.x, L = tile_list[tile];
+  const uint32_t* w = words + woff[huge_list[L]];
+  const uint32_t wn = dec_tile_stage(w, w[1], tile - huge_tstart[L], nxt_dyn);
+  const uint32_t e = threadIdx.x;
+  if (e < kTileEntries) {
+    uint32_t p = e, c = 0;
+    while (p < wn) {
+      p = nxt_dyn[p];
+      c++;
     }
-    // the next window starts 0 .. 508 words past this one: have the L2 fetch it meanwhile
-    if (wb + wn < end) {
-      const uint64_t at = wb + wn + (uint64_t)tid * 32;
-      if (tid * 32 < W + 512 && at < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(w + at));
-    }
+    maps[(uint64_t)tile * kTileEntries + e] = (c << 16) | (p - wn);  // c <= 16384, exit <= 508
+  }
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+k_dec_tile_chain(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+                 const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_gstart,
+                 const uint32_t* __restrict__ huge_tstart, const uint32_t* __restrict__ maps,
+                 uint32_t* __restrict__ tile_entry, uint32_t* __restrict__ tile_bbase,
+                 uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist, int* __restrict__ err) {
+  __shared__ uint32_t smap[kChainBatch * kTileEntries];
+  __shared__ uint32_t s_entry, s_bb;
+  const uint32_t L = blockIdx.x;
+  const uint64_t a = woff[huge_list[L]];
+  const uint32_t nb = words[a] >> 7;
+  const uint32_t nt = (words[a + 1] - 3 + kTileWords - 1) / kTileWords;
+  const uint32_t ts = huge_tstart[L];
+  if (threadIdx.x == 0) {
+    s_entry = 0;
+    s_bb = 0;
+  }
+  __syncthreads();
+  for (uint32_t t0 = 0; t0 < nt; t0 += kChainBatch) {
+    const uint32_t m = min(kChainBatch, nt - t0);
+    for (uint32_t i = threadIdx.x; i < m * kTileEntries; i += blockDim.x)
+      smap[i] = maps[(uint64_t)(ts + t0) * kTileEntries + i];
     __syncthreads();
-    // jmp: 1 -> 2 -> 4 -> 8 blocks ahead (pointer doubling, all words at once)
-#pragma unroll 1
-    for (uint32_t r = 1; r < HOP; r <<= 1) {
-      uint16_t nj[PER];
-#pragma unroll
-      for (uint32_t j = 0; j < PER; j++) {
-        const uint32_t i = tid + j * kWalkThreads;
-        const uint32_t t = i < wn ? jmp[i] : SENT;
-        nj[j] = t != SENT ? jmp[t] : (uint16_t)SENT;
+    if (threadIdx.x == 0) {
+      uint32_t entry = s_entry, bb = s_bb;
+      for (uint32_t j = 0; j < m; j++) {
+        const uint32_t x = smap[j * kTileEntries + entry];
+        tile_entry[ts + t0 + j] = entry;
+        tile_bbase[ts + t0 + j] = bb;
+        bb += x >> 16;
+        entry = x & 0xFFFFu;
       }
-      __syncthreads();
-#pragma unroll
-      for (uint32_t j = 0; j < PER; j++) {
-        const uint32_t i = tid + j * kWalkThreads;
-        if (i < wn) jmp[i] = nj[j];
-      }
-      __syncthreads();
+      s_entry = entry;
+      s_bb = bb;
     }
-    const uint32_t room = nb - b;
-    if (tid == 0) {
-      // the only serial part: one dependent shared-memory load per HOP blocks
-      const uint32_t max_hops = (room + HOP - 1) / HOP;
-      uint32_t p = 0, cnt = 0;
-      while (p != SENT && cnt < max_hops) {
-        hop[cnt++] = (uint16_t)p;
-        p = jmp[p];
-      }
-      s_hops = cnt;
-    }
-    __syncthreads();
-    // thread k fills in the blocks between hop k and hop k + 1; the last one finds where the
-    // chain leaves the window
-    const uint32_t hops = s_hops;
-    for (uint32_t k = tid; k < hops; k += kWalkThreads) {
-      uint32_t h = hop[k], v = 0;
-      for (; v < HOP && h < wn && k * HOP + v < room; v++) {
-        bpos[gs + b + k * HOP + v] = a + wb + h;
-        blist[gs + b + k * HOP + v] = L;
-        h = nxt[h];
-      }
-      if (k + 1 == hops) {
-        s_p = h;  // first header past the window (or past the blocks this section holds)
-        s_tot = k * HOP + v;
-      }
-    }
-    __syncthreads();
-    wb += s_p;
-    b += s_tot;
     __syncthreads();
   }
-  if (b < nb && tid == 0) {  // the section ends before its blocks do
-    atomicExch(err, 1);
-    for (; b < nb; b++) {
+  // fewer headers than blocks: the section ends before its blocks do (more: trailing words the
+  // reference decoder skips as well)
+  const uint32_t found = s_bb;
+  if (found < nb) {
+    if (threadIdx.x == 0) atomicExch(err, 1);
+    const uint32_t gs = huge_gstart[L];
+    for (uint32_t b = found + threadIdx.x; b < nb; b += blockDim.x) {
       bpos[gs + b] = ~0ull;
       blist[gs + b] = L;
     }
+  }
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+k_dec_tile_walk(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
+                const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_gstart,
+                const uint32_t* __restrict__ huge_tstart, const uint32_t* __restrict__ tile_list,
+                const uint32_t* __restrict__ tile_entry, const uint32_t* __restrict__ tile_bbase,
+                uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist) {
+  extern __shared__ __align__(16) uint16_t nxt_dyn[];
+  uint16_t* hdr = nxt_dyn + kTileWords;  // the headers of the tile, in order
+  __shared__ uint32_t s_cnt;
+  const uint32_t tile = blockIdx.x, L = tile_list[tile];
+  const uint64_t a = woff[huge_list[L]];
+  const uint32_t* w = words + a;
+  const uint32_t t = tile - huge_tstart[L];
+  const uint32_t wn = dec_tile_stage(w, w[1], t, nxt_dyn);
+  const uint32_t nb = w[0] >> 7, bb = tile_bbase[tile];
+  if (threadIdx.x == 0) {
+    const uint32_t room = bb < nb ? nb - bb : 0u;
+    uint32_t p = tile_entry[tile], c = 0;
+    while (p < wn && c < room) {
+      hdr[c++] = (uint16_t)p;
+      p = nxt_dyn[p];
+    }
+    s_cnt = c;
+  }
+  __syncthreads();
+  const uint32_t cnt = s_cnt, gs = huge_gstart[L];
+  const uint64_t t0 = a + 3 + (uint64_t)t * kTileWords;
+  for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
+    bpos[gs + bb + k] = t0 + hdr[k];
+    blist[gs + bb + k] = L;
   }
 }
 
@@ -265,7 +303,7 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
     return II2_ERR_UNSUPPORTED;
   }
   DevBuf<int> err;
-  DevBuf<uint32_t> n_work, worklist, huge_list, huge_gstart;
+  DevBuf<uint32_t> n_work, worklist, huge_list, huge_gstart, huge_tstart;
   DevBuf<uint64_t> d_total;
   II2_TRY(err.alloc_scratch(1, s));
   II2_TRY(n_work.alloc_scratch(4, s));
@@ -273,12 +311,14 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
   II2_TRY(worklist.alloc_scratch(nlists ? nlists : 1, s));
   II2_TRY(huge_list.alloc_scratch(nlists ? nlists : 1, s));
   II2_TRY(huge_gstart.alloc_scratch(nlists ? nlists : 1, s));
+  II2_TRY(huge_tstart.alloc_scratch(nlists ? nlists : 1, s));
   II2_CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
   II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, 4 * sizeof(uint32_t), s));
   II2_CUDA_TRY(cudaMemsetAsync(out_off.p + nlists, 0, sizeof(uint64_t), s));
   if (nlists) {
     k_dec_count<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_words, d_woff, nlists, out_off.p, n_work.p, huge_list.p, huge_gstart.p, err.p);
+        d_words, d_woff, nlists, out_off.p, n_work.p, huge_list.p, huge_gstart.p, huge_tstart.p,
+        err.p);
     II2_LAUNCHED();
   }
   II2_TRY(exclusive_scan_u64(out_off.p, nlists + 1, d_total.p, s));
@@ -292,6 +332,7 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
   herr = *reinterpret_cast<const int*>(pinned_scratch() + 21);
   const uint32_t n_huge = reinterpret_cast<const uint32_t*>(pinned_scratch() + 22)[1];
   const uint32_t n_hblocks = reinterpret_cast<const uint32_t*>(pinned_scratch() + 22)[2];
+  const uint32_t n_htiles = reinterpret_cast<const uint32_t*>(pinned_scratch() + 22)[3];
   if (herr) {
     set_last_error("undecodable intcomp stream in batch");
     return II2_ERR_CORRUPT;
@@ -315,9 +356,36 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
     II2_TRY(bpos.alloc_scratch(n_hblocks, s));
     II2_TRY(blist.alloc_scratch(n_hblocks, s));
     II2_TRY(bsum.alloc_scratch((size_t)n_hblocks + 1, s));
-    k_dec_walk<<<n_huge, kWalkThreads, 0, s>>>(d_words, d_woff, huge_list.p, huge_gstart.p, bpos.p,
-                                               blist.p, err.p);
-    II2_LAUNCHED();
+    {
+      DevBuf<uint32_t> tile_list, tile_entry, tile_bbase, maps;
+      II2_TRY(tile_list.alloc_scratch(n_htiles + 1, s));
+      II2_TRY(tile_entry.alloc_scratch(n_htiles + 1, s));
+      II2_TRY(tile_bbase.alloc_scratch(n_htiles + 1, s));
+      II2_TRY(maps.alloc_scratch(((size_t)n_htiles + 1) * kTileEntries, s));
+      static bool attr_set = false;
+      if (!attr_set) {
+        II2_CUDA_TRY(cudaFuncSetAttribute(k_dec_tile_walk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(kTileWords * 4)));
+        attr_set = true;
+      }
+      k_dec_tile_fill<<<n_huge, 256, 0, s>>>(d_words, d_woff, huge_list.p, huge_tstart.p, tile_list.p);
+      II2_LAUNCHED();
+      if (n_htiles) {
+        k_dec_tile_maps<<<n_htiles, kWalkThreads, kTileWords * 2, s>>>(
+            d_words, d_woff, huge_list.p, huge_tstart.p, tile_list.p, maps.p);
+        II2_LAUNCHED();
+      }
+      k_dec_tile_chain<<<n_huge, kWalkThreads, 0, s>>>(d_words, d_woff, huge_list.p, huge_gstart.p,
+                                                       huge_tstart.p, maps.p, tile_entry.p,
+                                                       tile_bbase.p, bpos.p, blist.p, err.p);
+      II2_LAUNCHED();
+      if (n_htiles) {
+        k_dec_tile_walk<<<n_htiles, kWalkThreads, kTileWords * 4, s>>>(
+            d_words, d_woff, huge_list.p, huge_gstart.p, huge_tstart.p, tile_list.p, tile_entry.p,
+            tile_bbase.p, bpos.p, blist.p);
+        II2_LAUNCHED();
+      }
+    }
     k_dec_blocksum<<<div_up(((uint64_t)n_hblocks + 1) * 32, kCodecThreads), kCodecThreads, 0, s>>>(
         d_words, d_woff, huge_list.p, bpos.p, blist.p, n_hblocks, bsum.p, err.p);
     II2_LAUNCHED();

@@ -578,6 +578,10 @@ def test_intcomp_long_lists_block_parallel(engine, orc):
         with pytest.raises(EngineError) as e:
             engine.intcomp_decode_batch(words, o)
         assert e.value.code == A.II2_ERR_CORRUPT
+    hollow = np.array([16384, 3, 0, 5, 0x85], dtype=np.uint32)  # 128 blocks announced, none there
+    with pytest.raises(EngineError) as e:
+        engine.intcomp_decode_batch(hollow, np.array([0, 5], dtype=np.uint64))
+    assert e.value.code == A.II2_ERR_CORRUPT
 
 
 def test_intcomp_rejects_corrupt(engine):
