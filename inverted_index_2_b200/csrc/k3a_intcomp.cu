@@ -398,8 +398,9 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
         d_words, d_woff, huge_list.p, n_huge, out_off.p, out.p, err.p);
     II2_LAUNCHED();
   }
-  II2_CUDA_TRY(cudaMemcpyAsync(&herr, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 24, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  herr = *reinterpret_cast<const int*>(pinned_scratch() + 24);
   if (herr) {
     set_last_error("undecodable intcomp stream in batch");
     return II2_ERR_CORRUPT;
@@ -417,9 +418,11 @@ int val_offsets_to_word_offsets(const uint64_t* d_val_off, uint64_t n, uint64_t 
   k_valoff_to_woff<<<div_up(n + 1, kCodecThreads), kCodecThreads, 0, s>>>(d_val_off, n, val_size,
                                                                           woff.p, err.p);
   II2_LAUNCHED();
-  int herr = 0;
-  II2_CUDA_TRY(cudaMemcpyAsync(&herr, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
+  // (readbacks land in the thread's pinned scratch: a pageable destination would make the copy
+  // wait for every transfer in flight on other streams)
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 25, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  const int herr = *reinterpret_cast<const int*>(pinned_scratch() + 25);
   if (herr) {
     set_last_error("_val offsets are not 4-byte aligned or exceed the file size");
     return II2_ERR_CORRUPT;
@@ -643,9 +646,9 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
     II2_LAUNCHED();
   }
   II2_TRY(exclusive_scan_u64(woff.p, nlists + 1, d_total.p, s));
-  uint64_t total = 0;
-  II2_CUDA_TRY(cudaMemcpyAsync(&total, d_total.p, sizeof(total), cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 26, d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  const uint64_t total = pinned_scratch()[26];
   II2_TRY(words.alloc_scratch(total, s));
   if (nlists) {
     k_enc_emit_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(d_in, d_off, nlists,

@@ -670,13 +670,13 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
                                               bm->n, d_out.p, d_err.p);
     II2_LAUNCHED();
   }
-  int herr = 0;
-  II2_CUDA_TRY(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, s));
+  II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 27, d_err.p, 4, cudaMemcpyDeviceToHost, s));
   uint32_t* h = static_cast<uint32_t*>(pinned_alloc(total * 4 + 4));
   if (!h) return II2_ERR_NOMEM;
   cudaError_t e = cudaSuccess;
   if (total) e = cudaMemcpyAsync(h, d_out.p, total * 4, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  const int herr = *reinterpret_cast<const int*>(pinned_scratch() + 27);
   if (e != cudaSuccess) {
     pinned_free(h);
     set_last_error("bitmask get: %s", cudaGetErrorString(e));
