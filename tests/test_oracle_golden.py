@@ -67,3 +67,53 @@ def test_shard_key(orc):
     for term, key in V["shard_key"]:
         assert shard_key(term.encode()) == key
         assert "%04d" % orc.shard_key(term.encode()) == key
+
+
+def test_intcomp_long_list_header_chain(orc):
+    """The layout facts the block-parallel long-list decoder (k3a_intcomp.cu: k_dec_tile_maps /
+    _chain / _walk) is built on, checked on the oracle's own streams: the first section of a
+    list of n >= 128 values is [128 * blocks, section words, first value] + blocks, a block is
+    1 header + the sum of its four widths (<= 509) words, hopping from header to header from
+    word 3 meets exactly `blocks` headers and ends on the section length; and the speculative
+    parse — per tile, a map from every possible entry offset to (headers met, entry offset of
+    the next tile), composed tile after tile — finds the same headers as the serial walk."""
+    rng = np.random.default_rng(5)
+    cases = [np.cumsum(rng.integers(1, 33, size=20000)).astype(np.uint32),
+             rng.integers(0, 1 << 32, size=9000, dtype=np.uint64).astype(np.uint32),  # zig-zag, 32-bit widths
+             np.full(8192 + 77, 5, dtype=np.uint32),                                   # one-word blocks
+             np.cumsum(rng.integers(1, 1 << 13, size=8192 + 128)).astype(np.uint32)]
+    tile = 1024
+    for vals in cases:
+        w = orc.intcomp_encode(vals)
+        assert np.array_equal(orc.intcomp_decode(w), vals)
+        nb, length = int(w[0]) >> 7, int(w[1])
+        assert int(w[0]) == (len(vals) // 128) * 128 and int(w[2]) == int(vals[0])
+        body = w[3:length].astype(np.int64)
+        nxt = np.arange(len(body)) + 1 + ((body >> 24) & 0x7F) + ((body >> 16) & 0x7F) + \
+            ((body >> 8) & 0x7F) + (body & 0x7F)
+        # serial walk
+        p, headers = 0, []
+        while p < len(body):
+            headers.append(p)
+            assert nxt[p] - p <= 509
+            p = int(nxt[p])
+        assert len(headers) == nb and p == len(body)
+        # speculative parse over tiles
+        entry, base, found = 0, 0, []
+        for t0 in range(0, len(body), tile):
+            wn = min(tile, len(body) - t0)
+            local = nxt[t0:t0 + wn] - t0
+            maps = []
+            for e in range(512):
+                q, c = e, 0
+                while q < wn:
+                    q, c = int(local[q]), c + 1
+                maps.append((c, q - wn))
+            q = entry                              # the walk from the true entry
+            while q < wn:
+                found.append(t0 + q)
+                q = int(local[q])
+            c, nxt_entry = maps[entry]
+            assert q - wn == nxt_entry and len(found) == base + c and nxt_entry <= 508
+            entry, base = nxt_entry, base + c
+        assert found == headers
