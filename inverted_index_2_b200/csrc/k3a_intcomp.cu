@@ -4,7 +4,8 @@
 //   size pass -> exclusive scan (so `_val` offsets equal the reference's running
 //   valuesOffset, file/writer.go:56) -> emit pass.
 // Lists below one 128-block are handled one per thread; longer lists one per warp
-// (32-lane groups match the codec's 32-value groups).
+// (32-lane groups match the codec's 32-value groups); lists of >= 8192 values block-parallel
+// over many CTAs (decode: speculative tile parse + per-block sums; encode: slices of blocks).
 #include <algorithm>
 
 #include "codec.cuh"
@@ -431,7 +432,7 @@ int val_offsets_to_word_offsets(const uint64_t* d_val_off, uint64_t n, uint64_t 
 }
 
 // ---------------------------------------------------------------- encode
-constexpr uint64_t kHugeList = 8192;  // values from which a whole CTA encodes one list
+constexpr uint64_t kHugeList = 8192;  // values from which a list is encoded by CTAs over slices of its blocks
 
 // n_work[0] counts the warp-per-list entries (filled from the front of `worklist`), n_work[1]
 // the CTA-per-list entries (filled from the back)
