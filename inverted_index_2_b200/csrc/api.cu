@@ -1040,15 +1040,17 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
   // range is small; 0.65 and 0.4 of a full range keep every range's merge + download shorter
   // than the next range's upload.  II2_MERGE_TAPER=0 turns it off (tuning).
   std::vector<double> cum(P + 1, 0.0);
-  {
-    const char* env_taper = getenv("II2_MERGE_TAPER");
-    const bool taper = P >= 4 && segs[big].n_terms >= 64ull * P && !(env_taper && atoi(env_taper) == 0);
-    for (int p = 0; p < P; p++)
-      cum[p + 1] = cum[p] + (taper && p == P - 2 ? 0.65 : (taper && p == P - 1 ? 0.4 : 1.0));
-  }
+  const char* env_taper = getenv("II2_MERGE_TAPER");
+  const bool taper = P >= 4 && segs[big].n_terms >= 64ull * P && !(env_taper && atoi(env_taper) == 0);
+  for (int p = 0; p < P; p++)
+    cum[p + 1] = cum[p] + (taper && p == P - 2 ? 0.65 : (taper && p == P - 1 ? 0.4 : 1.0));
   for (int p = 1; p < P; p++) {
-    const uint64_t at = std::min<uint64_t>(
-        segs[big].n_terms - 1, (uint64_t)((double)segs[big].n_terms * (cum[p] / cum[P])));
+    // equal ranges in integers (n_terms >= P: every cut is a different term, also when
+    // n_terms == P); tapered ones are >= 25 terms apart
+    const uint64_t at =
+        taper ? std::min<uint64_t>(segs[big].n_terms - 1,
+                                   (uint64_t)((double)segs[big].n_terms * (cum[p] / cum[P])))
+              : segs[big].n_terms * (uint64_t)p / P;
     const uint32_t o = segs[big].term_off[at], n = segs[big].term_off[at + 1] - o;
     for (int i = 0; i < nseg; i++)
       bounds[(size_t)p * nseg + i] =

@@ -248,6 +248,12 @@ def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
         assert_merge_equal(engine.merge(psegs, w.removed, decoded=True), exp)
         assert_merge_equal(engine.merge(segs, w.removed, decoded=True), exp)  # pageable inputs
     monkeypatch.delenv("II2_MERGE_UPLOAD", raising=False)
+    # as many ranges as the largest segment has terms: every cut is a different term
+    tiny = [FlatSegment.from_items([(b"a", [1]), (b"b", [2]), (b"c", [3])]),
+            FlatSegment.from_items([(b"b", [5]), (b"d", [1])])]
+    for parts in ("2", "3"):
+        monkeypatch.setenv("II2_MERGE_PARTS", parts)
+        assert_merge_equal(engine.merge(tiny, None, decoded=True), orc.merge(tiny, None, decoded=True))
     # everything removed in the first ranges: min/max still come from the first / last range
     monkeypatch.setenv("II2_MERGE_PARTS", "4")
     monkeypatch.delenv("II2_MERGE_SLACK", raising=False)
