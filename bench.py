@@ -9,9 +9,16 @@ filter + intcomp encode, shard.go:158-212) of all resident segments of this rank
              Shard.Merge): pinned host inputs -> H2D -> kernels -> D2H of the new segment
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs measured HBM peak
   cpu_baseline  the CPU oracle (C restatement of the Go path) on a bounded sample, rank 0, N=1
+  range_read_us  BASELINE configs[2] (N=1): term-range reads over 256 resident segments with the
+             5 % removed filter, ranges of 0.1 / 1 / 10 / 100 % of the term space, median / p99 us
 Multi-GPU: shards are independent (shard.go:19-20) -> one process per GPU, each compacting its
-own term range, no data-path collective; weak scaling.  `--impl reference` times the CPU oracle
-with all host threads (InvertedIndex.Merge's worker pool over shards, inverted_index.go:83-103).
+own term range, no data-path collective; `value` is weak scaling (every rank its own C2 shard
+range).  `strong` (N > 1, BASELINE configs[4]): ONE synthetic index partitioned by the reference's
+shardKey rule (shard.go:362-378) into contiguous shard-key ranges, build (ii2_ingest) + merge
+timed per rank, with the imbalance of the partition; `cross_shard_read` gathers a read that spans
+all ranks through the library's own NCCL exchange (ii2_read_gather) and checks it.
+`--impl reference` times the CPU oracle with all host threads (InvertedIndex.Merge's worker
+pool over shards, inverted_index.go:83-103) on bounded samples of the SAME workload.
 """
 from __future__ import annotations
 
@@ -49,6 +56,12 @@ def parse():
                     help="target CPU time of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-range-read", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--strong-postings", type=int, default=1_000_000_000,
+                    help="total postings of the ONE index of the strong-scaling leg (N > 1)")
+    ap.add_argument("--strong-cap", type=int, default=250_000_000,
+                    help="postings one rank holds at most in the strong leg (host RAM / time)")
     ap.add_argument("--verify", action="store_true",
                     help="check the full-size result against an independent numpy union")
     return ap.parse_args()
@@ -119,9 +132,9 @@ def run_reference(a):
     from oracle import orc
     orc.lib()
     cores = os.cpu_count() or 1
-    w = synth.make_workload(min(a.terms, 200_000), a.segments,
-                            int(a.postings * min(a.terms, 200_000) / a.terms),
-                            removed_frac=a.removed_frac)
+    # the SAME workload as the GPU arm (config.workload names it); every step merges a bounded
+    # sample of it: the first `step_terms` terms, cut into term-range shards
+    w = synth.make_workload(a.terms, a.segments, a.postings, removed_frac=a.removed_frac)
     n_terms = len(w.term_off) - 1
     # calibrate one shard, then size a step to ~10 s of wall time on all cores
     probe = slice_prefix(w, 1000)
@@ -140,8 +153,11 @@ def run_reference(a):
         tot_n += n
         tot_t += dt
     value = tot_n / tot_t
-    sample = (f"{len(shards)} term-range shards x {per_shard} terms over {a.segments} segments "
-              f"({tot_n // a.steps} postings per step), {cores} threads")
+    sample = (f"first {len(shards) * per_shard} of {n_terms} terms of the workload as {len(shards)} "
+              f"term-range shards x {per_shard} terms over all {a.segments} segments "
+              f"({tot_n // a.steps} postings per step), {cores} threads; inputs are decoded lists "
+              f"(the input-side intcomp decode of file/reader.go:100 is not in the timed region, "
+              f"as in the GPU arm's `value`)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps,
@@ -246,6 +262,186 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+
+# --------------------------------------------------------------------------- extra legs
+def range_read_leg(eng, a):
+    """BASELINE configs[2]: term-range reads over 256 resident segments, 5 % of the id universe
+    removed (read + merge-style filter, quirk Q2), ranges of 0.1 / 1 / 10 / 100 % of the term
+    space at 16 random positions (4 for the full range); wall clock per call, microseconds."""
+    import torch
+    w = synth.make_workload(a.terms, 256, a.postings, seed=0xC3, presence=0.125,
+                            removed_frac=a.removed_frac)
+    dsegs = [eng.upload(s) for s in w.segments]
+    drem = eng.upload_removed(w.removed)
+    n = len(w.term_off) - 1
+    rng = np.random.default_rng(3)
+    out = {}
+    for frac in (0.001, 0.01, 0.1, 1.0):
+        span = max(1, int(n * frac))
+        lat, info = [], None
+        for _ in range(16 if frac < 1 else 4):
+            lo = int(rng.integers(0, n - span + 1))
+            tlo = synth.term_at(w.term_bytes, w.term_off, lo)
+            thi = synth.term_at(w.term_bytes, w.term_off, lo + span - 1)
+            ts = []
+            for rep in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = eng.read_range_dev(dsegs, tlo, thi, drem)
+                torch.cuda.synchronize()
+                if rep:  # the first call of a position warms the caches
+                    ts.append(time.perf_counter() - t0)
+                info = r.info()
+                r.release()
+            lat.append(float(np.median(ts)))
+        out[f"{frac:g}"] = {"median_us": 1e6 * float(np.median(lat)), "p99_us": 1e6 * float(np.max(lat)),
+                            "terms": int(info.terms_count), "postings_in": int(info.postings_in),
+                            "postings_out": int(info.postings_out)}
+    for d in dsegs:
+        d.release()
+    drem.release()
+    return {"workload": f"256 resident segments, {a.terms} terms, {w.postings_in} postings, "
+                        f"{a.removed_frac:g} of the id universe removed; ii2_read_range_dev, "
+                        f"wall clock per call", "by_range_fraction": out}
+
+
+def strong_leg(eng, a, world, rank, dist, torch, barrier):
+    """BASELINE configs[4]: ONE index partitioned by the reference's shardKey rule into contiguous
+    shard-key ranges (one per rank): build (ii2_ingest of this rank's share of 64 documents) +
+    merge (64 resident segments holding this rank's share of the postings), max over ranks."""
+    import ctypes as C
+
+    from inverted_index_2_b200 import _abi as A
+    from inverted_index_2_b200 import sharded
+    tb, off = synth.make_terms(a.terms, 0x1EE7)
+    keys = sharded.shard_keys_of_sorted(tb, off)
+    weights = np.bincount(keys, minlength=sharded.N_SHARD_KEYS).astype(np.float64)
+    bounds = sharded.partition_shard_keys(weights, world)
+    lo, hi = (int(x) for x in np.searchsorted(keys, [bounds[rank], bounds[rank + 1]]))
+    n_mine, n_terms = hi - lo, len(off) - 1
+    total = int(min(a.strong_postings, a.strong_cap * world))
+    mine = synth.gather_terms(tb, off, np.arange(lo, hi))
+    w = synth.make_workload(n_mine, a.segments, int(total * n_mine / n_terms), terms=mine,
+                            seed=0xC5 + rank, removed_frac=a.removed_frac)
+    dsegs = [eng.upload(s) for s in w.segments]
+    drem = eng.upload_removed(w.removed)
+    # ---- build: 64 documents, each holding a random half of this rank's terms, unsorted
+    rng = np.random.default_rng(0xB1D + rank)
+    ndocs = 64
+    docs = (A.DocView * ndocs)()
+    keep, doc_terms = [], 0
+    for d in range(ndocs):
+        ids = np.nonzero(rng.random(n_mine) < 0.5)[0]
+        rng.shuffle(ids)
+        dtb, doff = synth.gather_terms(mine[0], mine[1], ids)
+        dtb = np.concatenate([dtb, np.zeros(8, dtype=np.uint8)])
+        keep.append((dtb, doff))
+        docs[d].n_terms = len(ids)
+        docs[d].term_bytes = A.np_ptr(dtb, A.u8p)
+        docs[d].term_off = A.np_ptr(doff, A.u32p)
+        docs[d].value = d + 1
+        doc_terms += len(ids)
+    out = A.MergeOut()
+
+    def build():
+        eng._check(eng.lib.ii2_ingest(docs, ndocs, None, 0, 0, C.byref(out)), "ingest")
+        t = int(out.terms_count)
+        eng.lib.ii2_merge_out_free(C.byref(out))
+        return t
+    build()
+    barrier()
+    t0 = time.perf_counter()
+    built_terms = build()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    # ---- merge
+    for _ in range(2):
+        eng.merge_dev(dsegs, drem, encode=True).release()
+    barrier()
+    t0 = time.perf_counter()
+    steps = max(1, min(a.steps, 5))
+    for _ in range(steps):
+        r = eng.merge_dev(dsegs, drem, encode=True)
+        n_in = int(r.info().postings_in)
+        r.release()
+    torch.cuda.synchronize()
+    merge_s = (time.perf_counter() - t0) / steps
+    t = torch.tensor([build_s, merge_s], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([float(n_in), float(doc_terms), float(n_mine)], device="cuda", dtype=torch.float64)
+    allc = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    per_rank = [int(c[0].item()) for c in allc]
+    tot_in, tot_docs = sum(per_rank), sum(int(c[1].item()) for c in allc)
+    res = {"index": f"{n_terms} terms, {tot_in} postings in {a.segments} segments, partitioned by shardKey "
+                    f"(shard.go:362-378) into {world} contiguous key ranges",
+           "scaling": "strong", "total_postings": tot_in,
+           "requested_postings": int(a.strong_postings), "shard_key_bounds": [int(x) for x in bounds],
+           "live_shard_keys": int((weights > 0).sum()),
+           "postings_per_rank": per_rank, "terms_per_rank": [int(c[2].item()) for c in allc],
+           "imbalance_max_over_mean": max(per_rank) / (tot_in / world),
+           "merge": {"ms_per_step": 1e3 * float(t[1].item()), "postings_per_s": tot_in / float(t[1].item()),
+                     "api": "ii2_merge_dev on resident segments, wall clock, max over ranks"},
+           "build": {"ms": 1e3 * float(t[0].item()), "doc_terms": tot_docs, "documents_per_rank": ndocs,
+                     "doc_terms_per_s": tot_docs / float(t[0].item()),
+                     "api": "ii2_ingest (host documents -> sorted, deduped, merged segment)"}}
+    return res, w, dsegs, drem, built_terms
+
+
+def cross_shard_read(eng, w, dsegs, world, rank, dist, torch, barrier, stream):
+    """A read that spans every rank: each rank reads 1 % of its terms, the library's own NCCL
+    exchange (ii2_read_gather, csrc/comm.cu) concatenates the results in rank order on rank 0;
+    checked there against the ranks' local results."""
+    import hashlib
+    nt = len(w.term_off) - 1
+    lo_t = synth.term_at(w.term_bytes, w.term_off, nt // 2)
+    hi_t = synth.term_at(w.term_bytes, w.term_off, nt // 2 + max(1, nt // 100))
+
+    def one(check):
+        r = eng.read_range_dev(dsegs, lo_t, hi_t, None)
+        g = eng.read_gather(r, 0)
+        out = None
+        if check:
+            loc = r.download_read()
+            dig = hashlib.sha256(b"".join(x.tobytes() for x in (loc.term_bytes, loc.term_off, loc.post,
+                                                               loc.post_off))).hexdigest()
+            sizes = (loc.n_terms, len(loc.term_bytes), len(loc.post))
+            every = [None] * world
+            dist.all_gather_object(every, (dig, sizes))
+            if rank == 0:
+                got = g.download_read()
+                ok, t0, b0, p0 = True, 0, 0, 0
+                for dg, (nt_r, nb_r, np_r) in every:
+                    toff = (got.term_off[t0:t0 + nt_r + 1].astype(np.int64) - b0).astype(np.uint32)
+                    poff = (got.post_off[t0:t0 + nt_r + 1] - np.uint64(p0)).astype(np.uint64)
+                    part = hashlib.sha256(b"".join(x.tobytes() for x in (
+                        got.term_bytes[b0:b0 + nb_r], toff, got.post[p0:p0 + np_r], poff))).hexdigest()
+                    ok = ok and part == dg
+                    t0, b0, p0 = t0 + nt_r, b0 + nb_r, p0 + np_r
+                ok = ok and got.n_terms == t0 and len(got.post) == p0
+                out = (bool(ok), int(got.n_terms), int(len(got.post)))
+        g.release()
+        r.release()
+        return out
+    checked = one(True)
+    one(False)
+    barrier()
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        one(False)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"range": "1% of every rank's terms", "us_per_read": 1e6 * float(t.item()),
+           "collective": "ii2_read_gather: one ncclAllGather of a 32-byte size record + one group of "
+                         "ncclSend/ncclRecv straight into the root's result, offsets rebased by a kernel"}
+    if checked is not None:
+        res.update({"verified": checked[0], "gathered_terms": checked[1], "gathered_postings": checked[2]})
+    return res
+
+
 # --------------------------------------------------------------------------- GPU arm
 def pin(arr: np.ndarray):
     """Copy into page-locked host memory (torch owns it); returns (numpy view, keep-alive)."""
@@ -332,7 +528,12 @@ def run_ours(a):
     # K2b (union + dedup + filter + encode): records + gather slots + the removed bitmap in,
     # records + the `_val` staging stream out
     k2b_bytes = 32 * n_groups + 4 * n_in + len(w.removed) // 8 + 32 * n_groups + val_size
+    # K12f (one bucket from its inputs to its finished output): term bytes, both offset arrays,
+    # postings and the removed bitmap in; the merged terms, their offsets and the `_val` words out
+    k12f_bytes = (t_in_bytes + 12 * (t_in + a.segments) + 4 * n_in + len(w.removed) // 8
+                  + val_size + t_out_bytes + 12 * t_out)
     alg = {
+        "k12f_bucket": k12f_bytes,
         "k1b_group": k1b_bytes,
         "k2b_union": k2b_bytes,
         # K6: records + staged `_val` words + surviving term bytes in; the new segment out
@@ -340,8 +541,9 @@ def run_ours(a):
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture
     # of this command (profiles/r01c_ncu_full_metrics.csv); only valid for the default workload
-    ncu_traffic = {"k1b_group": 1279.3e6 + 457.9e6, "k2b_union": 494.1e6 + 308.3e6,
-                   "k6_emit": 521.3e6 + 298.3e6}
+    ncu_traffic = {"k12f_bucket": 1230.4e6 + 253.7e6, "k1b_group": 1279.3e6 + 457.9e6,
+                   "k2b_union": 494.1e6 + 308.3e6, "k6_emit": 521.3e6 + 298.3e6}
+    traffic_src = {"k12f_bucket": "ncu --set full, profiles/r02_ncu_full_metrics.csv"}
     default_workload = (a.terms, a.segments, a.postings, a.removed_frac) == \
         (1_000_000, 64, 100_000_000, 0.05) and world == 1
     peak, peak_src = peaks()
@@ -355,7 +557,8 @@ def run_ours(a):
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak,
                     "traffic": ncu_traffic.get(top["name"]) if default_workload else None,
-                    "traffic_source": "ncu --set full, profiles/r01c_ncu_full_metrics.csv",
+                    "traffic_source": traffic_src.get(top["name"],
+                                                      "ncu --set full, profiles/r01c_ncu_full_metrics.csv"),
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms}
     pipeline_bytes = synth.algorithmic_bytes(n_in, n_out, t_in, t_in_bytes, a.segments, t_out,
@@ -410,36 +613,22 @@ def run_ours(a):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / e_steps,
                "steps": e_steps, "api": "ii2_merge (host buffers, pinned)"}
 
-    # ---- cross-shard read (BASELINE configs[4]): every rank reads its shard range, the
-    # results are gathered in rank order with NCCL (sizes, then a padded all-gather) ----
-    xread = None
+    # ---- N > 1: the exchange behind the C-ABI, the strong-scaling leg, the cross-shard read ----
+    xread = strong = None
     if world > 1:
-        from inverted_index_2_b200.sharded import _gather_var
-        nt = len(w.term_off) - 1
-        lo_t = synth.term_at(w.term_bytes, w.term_off, nt // 2)
-        hi_t = synth.term_at(w.term_bytes, w.term_off, nt // 2 + nt // 100)
+        from inverted_index_2_b200 import sharded
+        sharded.comm_init_from_torch(eng)
+        xw, xsegs = w, dsegs
+        if not a.no_strong:
+            strong, sw, ssegs, srem, _ = strong_leg(eng, a, world, rank, dist, torch, barrier)
+            xw, xsegs = sw, ssegs  # the read spans the ONE index: rank order == term order
+        xread = cross_shard_read(eng, xw, xsegs, world, rank, dist, torch, barrier, stream)
+        xread["index"] = "strong-leg index (one index, shardKey ranges)" if strong else "per-rank sets"
+        eng.comm_shutdown()
 
-        def xstep():
-            with torch.cuda.stream(stream):
-                r = eng.read_range_dev(dsegs, lo_t, hi_t, None)
-                tens = r.as_tensors(local)
-                parts = {k2: _gather_var(dist, v) for k2, v in tens.items()}
-                n_post = sum(int(p.numel()) for p in parts["post"])
-                stream.synchronize()
-                r.release()
-            return n_post
-        for _ in range(2):
-            n_post = xstep()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(5):
-            xstep()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / 5
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        xread = {"range": "1% of every rank's terms", "gathered_postings": int(n_post),
-                 "us_per_read": 1e6 * float(t.item()), "collective": "NCCL all_gather (sizes + padded arrays)"}
+    rread = None
+    if world == 1 and rank == 0 and not a.no_range_read:
+        rread = range_read_leg(eng, a)
 
     verified = None
     if a.verify and rank == 0:
@@ -471,6 +660,11 @@ def run_ours(a):
             line["verified_full_size"] = verified
         if xread is not None:
             line["cross_shard_read"] = xread
+        if strong is not None:
+            line["strong"] = strong
+        if rread is not None:
+            line["range_read_us"] = {k2: v["median_us"] for k2, v in rread["by_range_fraction"].items()}
+            line["range_read"] = rread
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -53,6 +53,13 @@ extern "C" {
  * order (the order vellum iterates them, file/reader.go:147), concatenated in
  * term_bytes; term i is term_bytes[term_off[i] .. term_off[i+1]).
  * Replaces the per-term file.TermValues objects of file/types.go:9-12.
+ *
+ * Alignment contract: term_bytes and val_bytes may start at ANY address (a Go
+ * sub-slice, an mmap offset); term_off / post / post_off / val_off must be
+ * naturally aligned for their element type (4 / 4 / 8 / 8 bytes), as Go slices
+ * of those types always are.  Arrays are borrowed for the call only.  Offsets
+ * are validated (monotone, inside the arrays): corrupt input is II2_ERR_INVALID.
+ * An empty segment (n_terms == 0) may leave every pointer NULL.
  */
 typedef struct ii2_seg_view {
   uint64_t n_terms;
@@ -251,6 +258,32 @@ int ii2_prefix_search_dev(ii2_seg* const* segs, int nseg, const uint8_t* prefix_
 int ii2_prefix_search(const ii2_seg_view* segs, int nseg, const uint8_t* prefix_bytes,
                       const uint32_t* prefix_off, uint32_t nprefix, ii2_prefix_out* out);
 void ii2_prefix_out_free(ii2_prefix_out* out);
+
+/* ---- cross-shard exchange: one process per GPU, contiguous shard-key ranges per
+ *      rank (shardKey, shard.go:362-378), NCCL over NVLink --------------------
+ * Compaction needs no exchange (shards never interact, shard.go:19-20).  Reads
+ * that span ranks do: InvertedIndex.Read concatenates the shard streams in key
+ * order (inverted_index.go:330-338) and PrefixSearch unions the per-shard maps,
+ * then slices.Sort + slices.Compact (inverted_index.go:274-292). */
+#define II2_COMM_ID_BYTES 128
+/* Rank 0 makes the id (ncclGetUniqueId) and hands it to the other processes by
+ * any host channel; then every process calls ii2_comm_init on the device it
+ * bound with ii2_init.  One communicator per process. */
+int ii2_comm_unique_id(uint8_t* id /* II2_COMM_ID_BYTES */);
+int ii2_comm_init(const uint8_t* id, int rank, int world);
+int ii2_comm_info(int* rank, int* world); /* world = 0 before ii2_comm_init */
+void ii2_comm_shutdown(void);
+/* Collective: every rank passes its own decoded result (ii2_read_range_dev over
+ * its shards).  `gathered` on rank `root` (every rank if root < 0) is the
+ * rank-ordered concatenation, offsets rebased — what InvertedIndex.Read yields
+ * over all shards; the other ranks get an empty result.  One size all-gather,
+ * one group of sends / receives, no padding. */
+int ii2_read_gather(const ii2_result* local, int root, ii2_result** gathered);
+/* Collective: every rank passes its ii2_prefix_search(_dev) result for the SAME
+ * prefix list.  `merged` on the root: per prefix the sorted-unique union of
+ * every rank's values, matched = OR of the ranks' flags (the final sort + compact
+ * runs on the root GPU).  Free with ii2_prefix_out_free. */
+int ii2_prefix_gather(const ii2_prefix_out* local, int root, ii2_prefix_out* merged);
 
 /* ---- posting codec: replaces intcomp.CompressUint32 (file/writer.go:49) and
  *      intcomp.UncompressUint32 (file/reader.go:100), batched ---------------- */

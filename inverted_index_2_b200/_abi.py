@@ -180,6 +180,12 @@ PROTOTYPES = {
     "ii2_prefix_search": (C.c_int, [C.POINTER(SegView), C.c_int, u8p, u32p, C.c_uint32,
                                     C.POINTER(PrefixOut)]),
     "ii2_prefix_out_free": (None, [C.POINTER(PrefixOut)]),
+    "ii2_comm_unique_id": (C.c_int, [u8p]),
+    "ii2_comm_init": (C.c_int, [u8p, C.c_int, C.c_int]),
+    "ii2_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ii2_comm_shutdown": (None, []),
+    "ii2_read_gather": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ii2_prefix_gather": (C.c_int, [C.POINTER(PrefixOut), C.c_int, C.POINTER(PrefixOut)]),
     "ii2_intcomp_encode_u32": (C.c_int, [u32p, u64p, C.c_uint64, C.POINTER(u32p),
                                          C.POINTER(u64p)]),
     "ii2_intcomp_decode_u32": (C.c_int, [u32p, u64p, C.c_uint64, C.POINTER(u32p),

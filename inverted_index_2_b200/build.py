@@ -13,8 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libii2.so")
-SOURCES = ["runtime.cu", "k3a_intcomp.cu", "k1_plan.cu", "k12_union.cu", "k6_emit.cu",
-           "k5_prefix.cu", "k7_ingest.cu", "k3b_bitmask.cu", "api.cu", "fst_v1.cpp", "removed_gob.cpp"]
+SOURCES = ["runtime.cu", "k3a_intcomp.cu", "k1_plan.cu", "k12_union.cu", "k12_fused.cu", "k6_emit.cu",
+           "k5_prefix.cu", "k7_ingest.cu", "k3b_bitmask.cu", "api.cu", "comm.cu", "fst_v1.cpp", "removed_gob.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs = list(ex.map(compile_one, srcs))
     if force or _newer(objs, OUT):
         cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                     "-cudart", "shared"]
+                                                     "-cudart", "shared", "-ldl"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)

@@ -10,45 +10,11 @@
 #include "codec.cuh"
 #include "ingest.cuh"
 #include "prefix.cuh"
+#include "handles.cuh"
 #include "union.cuh"
 
 using namespace ii2;
 
-// ------------------------------------------------------------------ opaque handle types
-struct ii2_seg {
-  uint32_t n_terms = 0;
-  uint64_t n_post = 0;
-  uint64_t term_bytes_len = 0;
-  DevBuf<uint8_t> tb;
-  DevBuf<uint32_t> toff;
-  DevBuf<uint32_t> post;
-  DevBuf<uint64_t> poff;
-};
-
-struct ii2_removed {
-  uint64_t n = 0;
-  DevBuf<uint32_t> sorted;
-  DevBuf<uint32_t> bitmap;
-  uint64_t bitmap_bits = 0;
-  RemovedSet set() const {
-    RemovedSet r;
-    r.sorted = sorted.p;
-    r.n = n;
-    r.bitmap = bitmap_bits ? bitmap.p : nullptr;
-    r.bitmap_bits = bitmap_bits;
-    return r;
-  }
-};
-
-struct ii2_result {
-  EmitOut out;
-  uint64_t T = 0, TB = 0, P = 0, E = 0;
-  uint64_t postings_in = 0, terms_merged = 0;
-  bool has_dec = false, has_enc = false;
-  bool has_minmax = false;
-  bool rebased = false;  // offsets already carry the base of a pipelined download
-  std::string min_term, max_term;
-};
 
 namespace {
 
@@ -183,9 +149,19 @@ k_gather_host(const GatherJob* __restrict__ jobs, uint32_t njobs, uint64_t nvec_
 }
 
 __global__ void __launch_bounds__(256)
-k_bitmap_set(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t* __restrict__ bitmap) {
+k_bitmap_set(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t* __restrict__ bitmap,
+             uint64_t bitmap_bits) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicOr(&bitmap[sorted[i] >> 5], 1u << (sorted[i] & 31u));
+  if (i < n && sorted[i] < bitmap_bits) atomicOr(&bitmap[sorted[i] >> 5], 1u << (sorted[i] & 31u));
+}
+
+// stats[0] = 1 if the list is not ascending (RemovedLists.Values sorts it, removed_list.go:44-54;
+// the binary search and the bitmap size both rely on it)
+__global__ void __launch_bounds__(256)
+k_removed_check(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t* __restrict__ stats) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    if (sorted[i + 1] < sorted[i]) atomicExch(&stats[0], 1u);
 }
 
 // Range windows (K4): lo = first term >= min (vellum Iterator(min) seek, file/reader.go:147),
@@ -276,7 +252,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   SegDesc* h = static_cast<SegDesc*>(stage.p);
   uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h + nsegx);
   uint8_t* h_bounds = reinterpret_cast<uint8_t*>(h_sbase + 2 * (nsegx + 1));
-  uint64_t n_total64 = 0, n_in = 0;
+  uint64_t n_total64 = 0, n_in = 0, tb_in = 0;
   for (int i = 0; i < nseg; i++) {
     const ii2_seg* g = segs[i];
     if (!g) return II2_ERR_INVALID;
@@ -290,6 +266,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     h[i].base = (uint32_t)n_total64;
     n_total64 += g->n_terms;
     n_in += g->n_post;
+    tb_in += g->term_bytes_len;
   }
   if (n_total64 >= (1ull << 32)) {
     set_last_error("more than 2^32-1 term instances in one call");
@@ -360,7 +337,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     rs.bitmap_bits = 0;
   }
   UnionOut u;
-  II2_TRY(k12_union(plan, rs, want_dec, want_enc, keep_empty, n_in, u, s));
+  II2_TRY(k12_union(plan, rs, want_dec, want_enc, keep_empty, n_in, tb_in, u, s));
   res->T = u.h_totals[0];
   res->TB = u.h_totals[1];
   res->P = u.h_totals[2];
@@ -423,19 +400,6 @@ int h2d(DevBuf<T>& dst, const T* src, size_t n, cudaStream_t s, size_t pad = 0) 
   if (n) II2_CUDA_TRY(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
   return II2_OK;
 }
-
-struct HostOwner {
-  std::vector<void*> ptrs;
-  ~HostOwner() {
-    for (void* p : ptrs) pinned_free(p);
-  }
-  template <typename T>
-  T* alloc(size_t n) {
-    void* p = pinned_alloc(n * sizeof(T) + 8);
-    if (p) ptrs.push_back(p);
-    return static_cast<T*>(p);
-  }
-};
 
 template <typename T>
 int d2h(T** dst, const T* src, size_t n, HostOwner& own, cudaStream_t s) {
@@ -605,13 +569,28 @@ int ii2_removed_upload(const uint32_t* removed_sorted, uint64_t nrem, ii2_remove
   r->n = nrem;
   II2_TRY(h2d(r->sorted, removed_sorted, (size_t)nrem, s));
   if (nrem) {
+    // the caller's list must be ascending (raw C-ABI input: checked, not trusted)
+    DevBuf<uint32_t> d_bad;
+    II2_TRY(d_bad.alloc_scratch(2, s));
+    II2_CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, 8, s));
+    k_removed_check<<<(unsigned)std::min<uint64_t>(div_up(nrem, 256), 1184), 256, 0, s>>>(r->sorted.p, nrem, d_bad.p);
+    II2_LAUNCHED();
+    uint32_t* h_bad = reinterpret_cast<uint32_t*>(pinned_scratch() + 24);
+    h_bad[0] = 0;
+    II2_TRY(small_copy(h_bad, d_bad.p, 8, s));
+    II2_CUDA_TRY(cudaStreamSynchronize(s));
+    if (h_bad[0]) {
+      arena_reset(s);
+      set_last_error("removed list is not sorted ascending");
+      return II2_ERR_INVALID;
+    }
     // membership bitmap when the id range is small enough to stay L2-friendly (<= 64 MiB)
     const uint64_t maxv = removed_sorted[nrem - 1];
     if (maxv < (1ull << 29) && nrem >= 64) {
       r->bitmap_bits = (maxv + 32) & ~31ull;
       II2_TRY(r->bitmap.alloc(r->bitmap_bits / 32, s));
       II2_CUDA_TRY(cudaMemsetAsync(r->bitmap.p, 0, r->bitmap_bits / 8, s));
-      k_bitmap_set<<<div_up(nrem, 256), 256, 0, s>>>(r->sorted.p, nrem, r->bitmap.p);
+      k_bitmap_set<<<div_up(nrem, 256), 256, 0, s>>>(r->sorted.p, nrem, r->bitmap.p, r->bitmap_bits);
       II2_LAUNCHED();
     }
   }
@@ -981,11 +960,20 @@ static int host_term_cmp(const uint8_t* a, uint32_t na, const uint8_t* b, uint32
   return na < nb ? -1 : (na > nb ? 1 : 0);
 }
 
-static uint64_t host_lower_bound(const ii2_seg_view& v, const uint8_t* t, uint32_t nt) {
+// *bad is set when an offset pair met on the way is not inside [term_off[0], term_off[n]]
+// (corrupt input: the caller falls back to the single-shot path, whose device-side check
+// answers II2_ERR_INVALID); such a pair is never dereferenced.
+static uint64_t host_lower_bound(const ii2_seg_view& v, const uint8_t* t, uint32_t nt, bool* bad) {
   uint64_t lo = 0, hi = v.n_terms;
+  const uint32_t end = v.n_terms ? v.term_off[v.n_terms] : 0u;
   while (lo < hi) {
     const uint64_t mid = lo + ((hi - lo) >> 1);
-    const uint32_t o = v.term_off[mid], n = v.term_off[mid + 1] - o;
+    const uint32_t o = v.term_off[mid], e = v.term_off[mid + 1];
+    if (e < o || e > end) {
+      *bad = true;
+      return lo;
+    }
+    const uint32_t n = e - o;
     if (host_term_cmp(v.term_bytes + o, n, t, nt) < 0)
       lo = mid + 1;
     else
@@ -1012,6 +1000,9 @@ static int merge_single_shot(const ii2_seg_view* segs, int nseg, const uint32_t*
   std::unique_ptr<ii2_result> res_guard(res);
   return ii2_result_download_merge(res, flags, out);
 }
+
+// internal: the pipelined path met input it leaves to the single-shot path (never returned)
+constexpr int II2_ERR_RETRY_SINGLE = -1000;
 
 struct EventList {
   std::vector<cudaEvent_t> v;
@@ -1051,10 +1042,13 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
         taper ? std::min<uint64_t>(segs[big].n_terms - 1,
                                    (uint64_t)((double)segs[big].n_terms * (cum[p] / cum[P])))
               : segs[big].n_terms * (uint64_t)p / P;
-    const uint32_t o = segs[big].term_off[at], n = segs[big].term_off[at + 1] - o;
+    const uint32_t o = segs[big].term_off[at], e = segs[big].term_off[at + 1];
+    if (e < o || e > segs[big].term_off[segs[big].n_terms]) return II2_ERR_RETRY_SINGLE;
+    bool bad = false;
     for (int i = 0; i < nseg; i++)
       bounds[(size_t)p * nseg + i] =
-          i == big ? at : host_lower_bound(segs[i], segs[big].term_bytes + o, n);
+          i == big ? at : host_lower_bound(segs[i], segs[big].term_bytes + o, e - o, &bad);
+    if (bad) return II2_ERR_RETRY_SINGLE;
   }
   ii2_removed* rem = nullptr;
   if (nrem) II2_TRY(ii2_removed_upload(removed_sorted, nrem, &rem));
@@ -1155,6 +1149,10 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     size_t tb_bytes = 0, toff_bytes = 0, post_bytes = 0, poff_bytes = 0;
     for (int i = 0; i < nseg; i++) {
       const ii2_seg_view& v = segs[i];
+      // corrupt offsets are II2_ERR_INVALID, like on the single-shot path, before any size is
+      // computed from a wrapped difference
+      if (hi[i] < lo[i] || v.term_off[hi[i]] < v.term_off[lo[i]] || v.post_off[hi[i]] < v.post_off[lo[i]])
+        return II2_ERR_INVALID;
       const size_t n1 = (size_t)(hi[i] - lo[i]) + 1;
       // every slice: up to 2 x 511 bytes of phase (placed at its source's phase modulo 512)
       tb_bytes += (size_t)(v.term_off[hi[i]] - v.term_off[lo[i]]) + 2 * kGatherAlign + 64;  // + tail padding
@@ -1181,12 +1179,18 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     size_t at_tb = 0, at_toff = 0, at_post = 0, at_poff = 0;  // byte cursors
     uint32_t max_n = 0;
     // one array slice: place it at the phase of its source, queue its copy
+    // `first` = the slice's first offset inside its array, in bytes.  The gather kernel needs
+    // dst = src (mod 512); a copy engine does not, and then the slice lands at the phase of
+    // `first`, so that the moved base pointer (dst - first) is 512-byte aligned whatever the
+    // alignment of the caller's pointer (a Go sub-slice or an mmap offset may start anywhere;
+    // the key loads need a 4-byte aligned term base).
     auto place = [&](uint8_t* blk, size_t& cursor, const void* hsrc, const uint8_t* dsrc,
-                     uint64_t bytes, bool large, uint8_t** dst_out) -> int {
+                     uint64_t bytes, uint64_t first, bool large, uint8_t** dst_out) -> int {
       const bool by_kernel = gather && !(dma_large && large);
       const uint8_t* src = by_kernel ? dsrc : static_cast<const uint8_t*>(hsrc);
       cursor = ((cursor + kGatherAlign - 1) & ~(size_t)(kGatherAlign - 1)) +
-               (reinterpret_cast<uintptr_t>(src) & (kGatherAlign - 1));
+               (by_kernel ? (reinterpret_cast<uintptr_t>(src) & (kGatherAlign - 1))
+                          : (size_t)(first & (kGatherAlign - 1)));
       uint8_t* dst = blk + cursor;
       *dst_out = dst;
       cursor += bytes;
@@ -1214,14 +1218,14 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
       if ((tlen && !v.term_bytes) || (plen && !v.post)) return II2_ERR_INVALID;
       uint8_t *d_tb, *d_toff, *d_post, *d_poff;
       II2_TRY(place(L.blk_tb.p, at_tb, v.term_bytes ? v.term_bytes + tfirst : nullptr,
-                    alias[i].tb ? alias[i].tb + tfirst : nullptr, tlen, true, &d_tb));
+                    alias[i].tb ? alias[i].tb + tfirst : nullptr, tlen, tfirst, true, &d_tb));
       at_tb += 32;  // key loads read past the last term
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_toff.p), at_toff, v.term_off + lo[i],
-                    alias[i].toff + 4 * lo[i], (n + 1) * 4, false, &d_toff));
+                    alias[i].toff + 4 * lo[i], (n + 1) * 4, 4 * lo[i], false, &d_toff));
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_post.p), at_post, v.post ? v.post + pfirst : nullptr,
-                    alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, true, &d_post));
+                    alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, 4 * pfirst, true, &d_post));
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_poff.p), at_poff, v.post_off + lo[i],
-                    alias[i].poff + 8 * lo[i], (n + 1) * 8, false, &d_poff));
+                    alias[i].poff + 8 * lo[i], (n + 1) * 8, 8 * lo[i], false, &d_poff));
       std::unique_ptr<ii2_seg> g(new ii2_seg());
       g->n_terms = (uint32_t)n;
       g->n_post = plen;
@@ -1427,7 +1431,9 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
   bool all_decoded = nseg > 0;
   for (int i = 0; i < nseg; i++) {
     const ii2_seg_view& v = segs[i];
-    if (v.mode != II2_SEG_DECODED || (v.n_terms && (!v.term_off || !v.post_off))) {
+    // (an empty segment may come with NULL arrays: the pipelined path indexes them, the
+    // single-shot path does not)
+    if (v.mode != II2_SEG_DECODED || !v.term_off || !v.post_off) {
       all_decoded = false;
       break;
     }
@@ -1445,7 +1451,11 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
   for (int i = 0; i < nseg; i++) max_terms = std::max<uint64_t>(max_terms, segs[i].n_terms);
   if (max_terms < (uint64_t)P) return merge_single_shot(segs, nseg, removed_sorted, nrem, flags, out);
   std::unique_ptr<HostOwner> own;  // outlives any copy still in flight when a step fails
-  const int rc = merge_pipelined(segs, nseg, removed_sorted, nrem, flags, out, P, own);
+  int rc = merge_pipelined(segs, nseg, removed_sorted, nrem, flags, out, P, own);
+  if (rc == II2_ERR_RETRY_SINGLE) {  // nothing was enqueued yet
+    memset(out, 0, sizeof(*out));
+    return merge_single_shot(segs, nseg, removed_sorted, nrem, flags, out);
+  }
   if (rc != II2_OK) {
     cudaStreamSynchronize(cur_stream());
     cudaStreamSynchronize(aux_stream());

@@ -26,6 +26,7 @@
 #include "intcomp.cuh"
 #include "keys.cuh"
 #include "union.cuh"
+#include "union_dev.cuh"
 
 namespace ii2 {
 
@@ -41,16 +42,11 @@ constexpr uint32_t CAP_I = K1B_CAP_N;   // instances per sub-tile
 constexpr uint32_t K1B_HT = CAP_I > 512 ? 2048 : 1024;  // hash slots (a power of two >= 2 * CAP_I)
 static_assert(CAP_I % K1B_THREADS == 0 && CAP_I <= 1024 && CAP_I % 4 == 0,
               "tile = a whole number of instances per thread, 10-bit tile indexes");
-constexpr uint32_t REG_CAP = 256;  // values a warp sorts in registers
 constexpr uint32_t K1B_STAGE_CAP = CAP_I * 6;  // postings of a tile assembled in the 24 KB of key windows
 constexpr uint32_t K1B_SMALL_D = 64;  // distinct terms ranked by counting instead of sorting
 constexpr uint32_t K1B_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t K12_PENDING = 0xFFFFFFFFu;
 constexpr uint32_t K1B_HEAVY = 0xFFFFFFFFu;   // pbase of a heavy term
-
-// staging words that certainly hold the intcomp stream of n values (oracle/intcomp_ref.c
-// orc_intcomp_bound: 3 + 129 per block + 1 + ceil(5 * tail / 4) + 1; at most two blocks here)
-__host__ __device__ __forceinline__ uint32_t enc_slot_words(uint32_t n) { return n + (n >> 2) + 6; }
 
 struct K1bArgs {
   const SegDesc* segs;
@@ -65,6 +61,7 @@ struct K1bArgs {
   uint32_t* src_len;
   uint32_t* bk_D;   // [B] distinct terms per bucket
   uint32_t bucket0; // first bucket of this launch (the grid covers a chunk of buckets)
+  const uint32_t* list;  // or: the buckets of this launch (those the fused kernel deferred)
 };
 
 
@@ -168,7 +165,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
 #ifdef K1B_TIMING
   long long tick_ = clock64();
 #endif
-  const uint32_t b = a.bucket0 + blockIdx.x;
+  const uint32_t b = a.list ? a.list[blockIdx.x] : a.bucket0 + blockIdx.x;
   uint32_t W = (uint32_t)(a.bk_pos[b + 1] - a.bk_pos[b]);
   if (W == 0) {
     if (tid == 0) a.bk_D[b] = 0;
@@ -689,295 +686,6 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
   if (tid == 0) a.bk_D[b] = dcount;
 }
 
-// ---- union of one term by a group of W lanes (W = 16: two terms per warp; W = 32: one) ------
-// The term's values live BLOCKED in registers: lane hl of the group holds elements
-// hl*8 .. hl*8+7.  Eight values per lane keep most compare-exchanges of the sorting network
-// inside a thread (two min/max instructions, no shuffle): a local 19-comparator network sorts
-// the eight, then one bitonic merge level per doubling — a mirrored "flip" across lanes, the
-// half-cleaners whose distance is a whole number of lanes (one shuffle + one predicated
-// min/max per value), and three local half-cleaners (distance 4, 2, 1).  The shuffle pipe
-// and shared memory share one data path on the SM and were the busiest unit of the striped
-// version (ncu: lsu wavefronts 66 %), hence this layout: 80 shuffles sort two 128-value terms.
-__device__ __forceinline__ void cex(uint32_t& x, uint32_t& y) {
-  const uint32_t lo = min(x, y), hi = max(x, y);
-  x = lo;
-  y = hi;
-}
-
-__device__ __forceinline__ void sort8_local(uint32_t (&v)[8]) {
-  cex(v[0], v[1]); cex(v[2], v[3]); cex(v[4], v[5]); cex(v[6], v[7]);
-  cex(v[0], v[2]); cex(v[1], v[3]); cex(v[4], v[6]); cex(v[5], v[7]);
-  cex(v[1], v[2]); cex(v[5], v[6]); cex(v[0], v[4]); cex(v[3], v[7]);
-  cex(v[1], v[5]); cex(v[2], v[6]);
-  cex(v[1], v[4]); cex(v[3], v[6]);
-  cex(v[2], v[4]); cex(v[3], v[5]);
-  cex(v[3], v[4]);
-}
-
-__device__ __forceinline__ void clean8_local(uint32_t (&v)[8]) {
-  cex(v[0], v[4]); cex(v[1], v[5]); cex(v[2], v[6]); cex(v[3], v[7]);
-  cex(v[0], v[2]); cex(v[1], v[3]); cex(v[4], v[6]); cex(v[5], v[7]);
-  cex(v[0], v[1]); cex(v[2], v[3]); cex(v[4], v[5]); cex(v[6], v[7]);
-}
-
-// one merge level: blocks of K elements (K/8 lanes) become sorted; K >= 16
-template <int K>
-__device__ __forceinline__ void merge_level(uint32_t (&v)[8], unsigned hl) {
-  {  // flip: element e pairs with e ^ (K-1) = (lane ^ (K/8-1), 7 - r)
-    const bool lower = (hl & (K / 16)) == 0;
-    uint32_t o[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) o[r] = __shfl_xor_sync(0xffffffffu, v[7 - r], K / 8 - 1);
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
-  }
-#pragma unroll
-  for (int j = K / 4; j >= 8; j >>= 1) {  // half-cleaners across lanes
-    const bool lower = (hl & (j / 8)) == 0;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j / 8);
-      v[r] = lower ? min(v[r], o) : max(v[r], o);
-    }
-  }
-  clean8_local(v);
-}
-
-// sorts the 8*W values of every group; nmax = largest real length in the warp (padding is
-// 0xFFFFFFFF at the end, so levels whose blocks would only hold padding are skipped)
-template <int W>
-__device__ __forceinline__ void sort_blocked(uint32_t (&v)[8], unsigned hl, uint32_t nmax) {
-  sort8_local(v);
-  if (nmax > 8) merge_level<16>(v, hl);
-  if (nmax > 16) merge_level<32>(v, hl);
-  if (nmax > 32) merge_level<64>(v, hl);
-  if (nmax > 64) merge_level<128>(v, hl);
-  if (W == 32 && nmax > 128) merge_level<256>(v, hl);
-}
-
-// Union of the term of this lane's group: L gathered values at `slot` (global) -> sorted
-// (slices.Sort) and deduped (slices.Compact) when the term has >= 2 sources (a single-source
-// term passes through in source order, duplicates kept: survey Q4) -> removed filter ->
-// survivors compacted into buf[0..outn) (shared, this group's).  Every lane of the warp must
-// call; groups with nothing to do pass L = 0.  Returns outn (uniform inside the group).
-template <int W>
-__device__ __forceinline__ uint32_t union_blocked(const uint32_t* slot, uint32_t* buf, uint32_t L,
-                                                  bool multi, const RemovedSet& rem) {
-  const unsigned lane = lane_id(), hl = lane & (W - 1);
-  uint32_t v[8];
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const uint32_t e = hl * 8 + r;
-    v[r] = e < L ? slot[e] : 0xFFFFFFFFu;
-  }
-  const bool any_multi = __any_sync(0xffffffffu, multi && L > 1);
-  if (any_multi) {
-    const uint32_t nmax = __reduce_max_sync(0xffffffffu, multi ? L : 0u);
-    sort_blocked<W>(v, hl, nmax);
-    if (!multi) {  // the other group of the warp holds a pass-through term: undo
-#pragma unroll
-      for (int r = 0; r < 8; r++) {
-        const uint32_t e = hl * 8 + r;
-        v[r] = e < L ? slot[e] : 0xFFFFFFFFu;
-      }
-    }
-  }
-  // all membership probes first: eight independent loads in flight per lane
-  uint32_t keep = 0;
-  if (rem.bitmap) {  // bit v of the bitmap <=> v removed, for v < bitmap_bits (<= 2^29)
-    const uint32_t nbits = (uint32_t)rem.bitmap_bits;
-    uint32_t word[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const bool probe = hl * 8 + r < L && v[r] < nbits;
-      word[r] = probe ? __ldg(rem.bitmap + (v[r] >> 5)) : 0u;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-      keep |= (hl * 8 + r < L && !((word[r] >> (v[r] & 31u)) & 1u)) ? 1u << r : 0u;
-  } else {
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-      if (hl * 8 + r < L && !is_removed(rem, v[r])) keep |= 1u << r;
-  }
-  const uint32_t up = __shfl_up_sync(0xffffffffu, v[7], 1, W);  // last value of the lane below
-  if (multi) {  // drop a value equal to its predecessor (sorted order)
-    if (hl > 0 && up == v[0]) keep &= ~1u;
-#pragma unroll
-    for (int r = 1; r < 8; r++)
-      if (v[r] == v[r - 1]) keep &= ~(1u << r);
-  }
-  const uint32_t cnt = __popc(keep);
-  uint32_t inc = cnt;
-#pragma unroll
-  for (int d = 1; d < W; d <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d, W);
-    if (hl >= (unsigned)d) inc += o;
-  }
-  const uint32_t outn = __shfl_sync(0xffffffffu, inc, W - 1, W);
-  uint32_t* dst = buf + (inc - cnt);
-#pragma unroll
-  for (int r = 0; r < 8; r++) {  // predicated store + pointer bump: no branches
-    const bool k = (keep >> r) & 1u;
-    if (k) *dst = v[r];
-    dst += k ? 1 : 0;
-  }
-  __syncwarp();
-  return outn;
-}
-
-// intcomp.CompressUint32 of v[0..n), n <= 127 (one var-byte section: count word, then
-// zigzag deltas, 7 bits per byte, low group first, last byte |= 0x80, first delta against 0;
-// oracle/intcomp_ref.c), by a group of W lanes: lane hl codes values hl*8 .. hl*8+7.
-// v and out are the group's shared buffers (16-byte aligned).  Returns the words (uniform in
-// the group); n = 0 -> 0.  Every lane of the warp must call.
-template <int W>
-__device__ __forceinline__ uint32_t encode_small_blocked(const uint32_t* v, uint32_t n,
-                                                         uint32_t* out) {
-  const unsigned hl = lane_id() & (W - 1);
-  const uint32_t e0 = hl * 8;
-  // values past n read as garbage inside the group's buffer and get length 0
-  const uint4 a = *reinterpret_cast<const uint4*>(v + e0);
-  const uint4 b = *reinterpret_cast<const uint4*>(v + e0 + 4);
-  const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t prev = e0 ? v[e0 - 1] : 0u;
-  uint32_t z[8], lens = 0, bytes = 0;  // lens: 4 bits per value
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    z[r] = intcomp::zigzag(x[r], prev);
-    prev = x[r];
-    // ceil(bitlen / 7) for bitlen in 1..32 (z = 0 codes as one byte): (bitlen + 6) * 37 >> 8
-    const uint32_t bl = 32u - __clz(z[r] | 1u);
-    const uint32_t len = e0 + r < n ? ((bl + 6u) * 37u) >> 8 : 0u;
-    lens |= len << (4 * r);
-    bytes += len;
-  }
-  uint32_t inc = bytes;
-#pragma unroll
-  for (int d = 1; d < W; d <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d, W);
-    if (hl >= (unsigned)d) inc += o;
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, inc, W - 1, W);
-  // byte stores predicated in PTX: the compiler would chain branches (len > 1 implies
-  // len > 0 ...), five of them per value
-  uint32_t sb = (uint32_t)__cvta_generic_to_shared(out + 1) + (inc - bytes);
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const uint32_t zz = z[r];
-    const uint32_t len = (lens >> (4 * r)) & 15u;
-    // the low four 7-bit groups spread over four bytes, terminator bit on the last byte
-    uint32_t w = (zz & 0x7Fu) | ((zz << 1) & 0x7F00u) | ((zz << 2) & 0x7F0000u) |
-                 ((zz << 3) & 0x7F000000u);
-    const uint32_t term = 0x80u << ((8 * len - 8) & 31u);
-    w |= len <= 4 ? term : 0u;  // (len 0 stores nothing)
-    const uint32_t b4 = (zz >> 28) | 0x80u;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p0, p1, p2, p3, p4;\n\t"
-        ".reg .b32 t1, t2, t3;\n\t"
-        "setp.gt.u32 p0, %1, 0;\n\t"
-        "setp.gt.u32 p1, %1, 1;\n\t"
-        "setp.gt.u32 p2, %1, 2;\n\t"
-        "setp.gt.u32 p3, %1, 3;\n\t"
-        "setp.gt.u32 p4, %1, 4;\n\t"
-        "shr.u32 t1, %2, 8;\n\t"
-        "shr.u32 t2, %2, 16;\n\t"
-        "shr.u32 t3, %2, 24;\n\t"
-        "@p0 st.shared.u8 [%0], %2;\n\t"
-        "@p1 st.shared.u8 [%0+1], t1;\n\t"
-        "@p2 st.shared.u8 [%0+2], t2;\n\t"
-        "@p3 st.shared.u8 [%0+3], t3;\n\t"
-        "@p4 st.shared.u8 [%0+4], %3;\n\t"
-        "}"
-        :
-        : "r"(sb), "r"(len), "r"(w), "r"(b4)
-        : "memory");
-    sb += len;
-  }
-  if (n) {
-    if (hl == 0) out[0] = n;
-    uint8_t* end = reinterpret_cast<uint8_t*>(out + 1) + total;
-    if (hl < ((4u - (total & 3u)) & 3u)) end[hl] = 0;  // zero padding of the last word
-  }
-  __syncwarp();  // no lane leaves early: the groups of a warp meet here
-  return n ? 1 + (total + 3) / 4 : 0u;
-}
-
-// intcomp.CompressUint32 of v[0..n) (shared memory) into out (shared memory, a different
-// buffer, at least enc_bound(n) words), one pass with rolled loops.  Returns the stream
-// length in words (uniform).
-__device__ __forceinline__ uint32_t encode_shared_warp(const uint32_t* v, uint32_t n, uint32_t* out) {
-  if (n == 0) return 0;
-  const unsigned lane = lane_id();
-  const uint32_t nb = n >> 7, tail = n & 127u;
-  uint32_t pos = 0;
-  if (nb) {
-    pos = 3;
-#pragma unroll 1
-    for (uint32_t blk = 0; blk < nb; blk++) {
-      const uint32_t hpos = pos++;
-      uint32_t hdr = 0;
-#pragma unroll 1
-      for (uint32_t g = 0; g < 4; g++) {
-        const uint32_t idx = blk * 128 + g * 32 + lane;
-        const uint32_t cur = v[idx];
-        const uint32_t prev = idx ? v[idx - 1] : cur;
-        const uint32_t z = intcomp::zigzag(cur, prev);
-        const uint32_t m = __reduce_or_sync(0xffffffffu, z);
-        const uint32_t sgn = m & 1u;
-        const uint32_t bw = sgn ? intcomp::bitlen(m) : intcomp::bitlen(m >> 1);
-        const uint32_t coded = sgn ? z : (cur - prev);
-        hdr |= ((sgn << 7) | bw) << (24 - 8 * g);
-        if (bw == 32) {
-          out[pos + lane] = coded;
-        } else if (bw > 0) {
-          if (lane < bw) out[pos + lane] = 0;
-          __syncwarp();
-          const uint32_t bit = lane * bw, sh = bit & 31u;
-          atomicOr(&out[pos + (bit >> 5)], coded << sh);
-          if (sh + bw > 32u) atomicOr(&out[pos + (bit >> 5) + 1], coded >> (32u - sh));
-        }
-        pos += bw;
-      }
-      if (lane == 0) out[hpos] = hdr;
-    }
-    if (lane == 0) {
-      out[0] = nb * 128;
-      out[1] = pos;
-      out[2] = v[0];
-    }
-  }
-  if (tail) {
-    if (lane == 0) out[pos] = tail;
-    pos += 1;
-    uint8_t* sb = reinterpret_cast<uint8_t*>(out + pos);
-    uint32_t bo = 0;
-#pragma unroll 1
-    for (uint32_t t0 = 0; t0 < tail; t0 += 32) {
-      const uint32_t i = t0 + lane;
-      uint32_t z = 0, len = 0;
-      if (i < tail) {
-        const uint32_t idx = nb * 128 + i;
-        z = intcomp::zigzag(v[idx], i ? v[idx - 1] : 0u);
-        len = intcomp::vbyte_len(z);
-      }
-      const uint32_t inc = warp_inclusive_scan(len);
-      const uint32_t off = bo + inc - len;
-      // 7 bits per byte, low group first, the last byte carries 0x80
-      if (len > 0) sb[off] = (uint8_t)((z & 0x7Fu) | (len == 1 ? 0x80u : 0u));
-      if (len > 1) sb[off + 1] = (uint8_t)(((z >> 7) & 0x7Fu) | (len == 2 ? 0x80u : 0u));
-      if (len > 2) sb[off + 2] = (uint8_t)(((z >> 14) & 0x7Fu) | (len == 3 ? 0x80u : 0u));
-      if (len > 3) sb[off + 3] = (uint8_t)(((z >> 21) & 0x7Fu) | (len == 4 ? 0x80u : 0u));
-      if (len > 4) sb[off + 4] = (uint8_t)(((z >> 28) & 0x7Fu) | 0x80u);
-      bo += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane < ((4u - (bo & 3u)) & 3u)) sb[bo + lane] = 0;  // zero padding of the last word
-    pos += (bo + 3) / 4;
-  }
-  __syncwarp();
-  return pos;
-}
 
 // ---------------------------------------------------------------- K2b: two terms per warp
 #ifndef K2B_THREADS_N
@@ -1007,6 +715,7 @@ struct K2bArgs {
   uint32_t* large_rec;
   uint32_t* large_bucket;
   uint32_t bucket0;  // first bucket of this launch
+  const uint32_t* list;  // or: the buckets of this launch
 };
 
 #ifndef K2B_MIN_CTAS
@@ -1017,7 +726,7 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
   __shared__ __align__(16) uint32_t s_enc[K2B_WARPS][K2B_EBUF];
   const unsigned lane = lane_id(), warp = warp_id();
   const unsigned half = lane >> 4, hl = lane & 15u;
-  const uint32_t b = a.bucket0 + blockIdx.x;
+  const uint32_t b = a.list ? a.list[blockIdx.x] : a.bucket0 + blockIdx.x;
   const uint32_t D = a.bk_D[b];
   if (D == 0) return;
   const uint64_t rec_base = a.bk_pos[b];
@@ -1569,12 +1278,18 @@ extern "C" int ii2_debug_k1b_clocks(unsigned long long* out, int reset) {
 
 // ---------------------------------------------------------------- host driver
 int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool want_enc,
-              bool keep_empty, uint64_t n_in, UnionOut& u, cudaStream_t s) {
+              bool keep_empty, uint64_t n_in, uint64_t tb_in, UnionOut& u, cudaStream_t s) {
   u.keep_empty = keep_empty;
   u.want_dec = want_dec;
   u.want_enc = want_enc;
   const uint32_t B = plan.n_buckets, N = plan.n_total;
   const int k = plan.k;
+  // II2_FUSED=1: the one-kernel-per-bucket path (k12_fused.cu) with the general kernels for the
+  // buckets it passes.  Measured on B200 (profiles/r02_experiments.md): 2.3 ms for 86 % of the C2
+  // instances + 0.46 ms for the rest against 2.3 ms for K1b + K2b over all of them, so the
+  // general kernels stay the default; the fused path moves 1.6x fewer DRAM bytes per step.
+  const char* fused_env = getenv("II2_FUSED");
+  u.fused = fused_env && atoi(fused_env) != 0 && k12f_supported(k);
   DevBuf<GroupIn> gin;
   DevBuf<uint64_t> src_ptr;
   DevBuf<uint32_t> src_len;
@@ -1585,12 +1300,12 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   II2_TRY(u.bk_D.alloc_scratch(B, s));
   II2_TRY(u.bk_raw.alloc_scratch(4 * (size_t)(B + 1), s));
   II2_TRY(u.bk_out.alloc_scratch(4 * (size_t)(B + 1), s));
-  // totals[0..3] scan totals, [4] terms merged, [6] n_large (u32)
+  // totals[0..3] scan totals, [4] terms merged, [6] n_large (u32), [7] deferred buckets (u32)
   II2_TRY(u.totals.alloc_scratch(8, s));
   // `_val` staging: every light term of L values owns a slot of L + L/4 + 6 words; the bucket
   // bases are the plan's upper-bound prefix, so nothing has to be read back before K2b
   const uint64_t enc_cap = n_in + n_in / 4 + 6ull * N + 64;
-  if (want_enc) II2_TRY(u.tmp_enc.alloc_scratch(enc_cap, s));
+  if (want_enc) II2_TRY(u.tmp_enc.alloc_scratch(enc_cap, s, 16));
   // gather slots of the light terms (K1b -> K2b); the decoded union replaces them in place
   II2_TRY(u.tmp_post.alloc_scratch(n_in, s, 16));
   const uint32_t large_cap = (uint32_t)std::min<uint64_t>(N, n_in / REG_CAP + 1);
@@ -1598,6 +1313,14 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   II2_TRY(large_u32.alloc_scratch(2 * (size_t)large_cap, s));
   II2_CUDA_TRY(cudaMemsetAsync(u.totals.p, 0, 64, s));
   II2_CUDA_TRY(cudaMemsetAsync(u.bk_raw.p, 0, 4 * (size_t)(B + 1) * 8, s));
+  II2_TRY(u.bk_mode.alloc_scratch(B, s));
+  if (u.fused) {
+    II2_TRY(u.st_tb.alloc_scratch(tb_in, s, 64));
+    II2_TRY(u.st_off.alloc_scratch(3 * (size_t)N, s));
+    II2_TRY(u.def_list.alloc_scratch(B, s));
+  } else {
+    II2_CUDA_TRY(cudaMemsetAsync(u.bk_mode.p, 0, (size_t)B * 4, s));  // K12F_RECORDS
+  }
 
   K1bArgs a1;
   a1.segs = plan.segs;
@@ -1642,29 +1365,78 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
                                       (int)want));
     attr = want;
   }
-  // (running the two kernels chunk-wise on two streams was measured slower on B200 than back
-  // to back: 3.27 vs 2.94 ms)
-  a1.bucket0 = a2.bucket0 = 0;
-  {
-    ProfScope scope("k1b_group", s);
-    k1b_group_kernel<<<B, K1B_THREADS, smem, s>>>(a1);
-    II2_LAUNCHED();
-  }
-  {
-    ProfScope scope("k2b_union", s);
-    k2b_union_kernel<<<B, K2B_THREADS, 0, s>>>(a2);
-    II2_LAUNCHED();
-  }
-  k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
-  II2_LAUNCHED();
+  // the general kernels over `grid` buckets: all of them, or the list K12f deferred
+  auto general = [&](uint32_t grid, const uint32_t* list) -> int {
+    a1.bucket0 = a2.bucket0 = 0;
+    a1.list = a2.list = list;
+    {
+      ProfScope scope("k1b_group", s);
+      k1b_group_kernel<<<grid, K1B_THREADS, smem, s>>>(a1);
+      II2_LAUNCHED();
+    }
+    {
+      ProfScope scope("k2b_union", s);
+      k2b_union_kernel<<<grid, K2B_THREADS, 0, s>>>(a2);
+      II2_LAUNCHED();
+    }
+    return II2_OK;
+  };
   uint64_t* h_tot = pinned_scratch();  // 8 words
   if (!h_tot) return II2_ERR_NOMEM;
-  // optimistic: scan right away; redone only if heavy terms were deferred
-  {
+  // bucket totals -> prefixes -> host (synchronises the stream)
+  auto totals = [&]() -> int {
     ProfScope scope("k12_scan_sync", s);
+    k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
+    II2_LAUNCHED();
     II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
     II2_TRY(small_copy(h_tot, u.totals.p, 64, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
+    return II2_OK;
+  };
+  if (u.fused) {
+    K12fArgs f;
+    f.segs = plan.segs;
+    f.k = k;
+    f.part = plan.part.p;
+    f.btb = plan.btb.p;
+    f.bpo = plan.bpo.p;
+    f.bk_pos = plan.bk_pos();
+    f.bk_cpl = plan.bk_cpl.p;
+    f.bk_P = plan.bk_P();
+    f.bk_E = plan.bk_E();
+    f.bk_TB = plan.bk_TB();
+    f.rem = rem;
+    f.want_enc = want_enc ? 1 : 0;
+    f.want_dec = want_dec ? 1 : 0;
+    f.keep_empty = keep_empty ? 1 : 0;
+    f.bk_D = u.bk_D.p;
+    f.bk_mode = u.bk_mode.p;
+    f.bk_raw = u.bk_raw.p;
+    f.nb1 = B + 1;
+    f.st_tb = u.st_tb.p;
+    f.st_toff = u.st_off.p;
+    f.st_eoff = u.st_off.p + N;
+    f.st_poff = u.st_off.p + 2 * (size_t)N;
+    f.st_enc = u.tmp_enc.p;
+    f.st_post = u.tmp_post.p;
+    f.n_def = reinterpret_cast<uint32_t*>(u.totals.p + 7);
+    f.def_list = u.def_list.p;
+    {
+      ProfScope scope("k12f_bucket", s);
+      II2_TRY(k12f_launch(f, B, s));
+    }
+    // optimistic: scan right away; redone only if buckets were deferred
+    II2_TRY(totals());
+    u.n_def = (uint32_t)h_tot[7];
+    if (u.n_def) {
+      II2_TRY(general(u.n_def, u.def_list.p));
+      II2_TRY(totals());
+    }
+  } else {
+    // (running the two kernels chunk-wise on two streams was measured slower on B200 than back
+    // to back: 3.27 vs 2.94 ms)
+    II2_TRY(general(B, nullptr));
+    II2_TRY(totals());
   }
   const uint32_t h_nl = (uint32_t)h_tot[6];
   if (h_nl > 0) {
@@ -1684,9 +1456,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     la.bk_raw = u.bk_raw.p;
     la.nb1 = B + 1;
     II2_TRY(k2_large_run(la, h_nl, u.large_tmp, u.large_enc, s));
-    II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
-    II2_TRY(small_copy(h_tot, u.totals.p, 64, s));
-    II2_CUDA_TRY(cudaStreamSynchronize(s));
+    II2_TRY(totals());
   }
   for (int i = 0; i < 4; i++) u.h_totals[i] = h_tot[i];
   u.terms_merged = h_tot[4];

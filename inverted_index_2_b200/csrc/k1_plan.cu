@@ -10,12 +10,15 @@
 //                      segment's samples -> how many are smaller -> the rank of x in the merged
 //                      sample order is the sum over segments (a k-way merge by ranking, no
 //                      sort).  Sorted splitter arrays by scatter.
-//   k1_partition_chunks merge-path partition: one CTA per 2048-term chunk of one segment stages
-//                      the chunk's key windows in shared memory (coalesced, every term byte
-//                      read once) and locates the splitters that fall inside it.  Row r+1 of
-//                      `part` = lower_bound of splitter r in every segment.
-//   k1_bucket_stats    per bucket: instances, input postings (from the posting offsets),
-//                      common prefix length; then one scan -> bucket bases.
+//   k1_partition_chunks_raw  merge-path partition: one CTA per 1024-term chunk of one segment
+//                      stages the chunk's offsets and term bytes in shared memory (coalesced,
+//                      every term byte read once) and locates the splitters that fall inside
+//                      it.  Row r+1 of `part` = lower_bound of splitter r in every segment;
+//                      `btb` / `bpo` = the term-byte and posting offsets at that boundary, so
+//                      that a bucket's four runs per segment (term offsets, posting offsets,
+//                      term bytes, postings) are known without touching the offset arrays.
+//   k1_bucket_stats    per bucket: instances, input postings, term bytes (all from the
+//                      boundary tables), common prefix length; then one scan -> bucket bases.
 //
 // Integer/byte work; every probe is an L2 hit after the first touch (samples and offsets of
 // 64 segments are a few MB).
@@ -121,112 +124,10 @@ k1_rank_samples(int k, const uint32_t* __restrict__ sbase, uint32_t S, SampleArr
   }
 }
 
-// Merge-path partition: one CTA per chunk of K1_CHUNK consecutive terms of one segment.  The
-// chunk's 16-byte key windows are staged in shared memory (coalesced: every term byte of the
-// dictionary is read exactly once), the splitters that fall inside the chunk are found with two
-// searches over the sorted splitter array, and each of them is located in the staged keys.
-// part row r+1 = lower_bound of splitter r in every segment; row 0 / S+1 = window starts / ends.
 #ifndef K1_CHUNK_TERMS
 #define K1_CHUNK_TERMS 1024
 #endif
 constexpr uint32_t K1_CHUNK = K1_CHUNK_TERMS;
-
-__global__ void __launch_bounds__(256)
-k1_partition_chunks(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ cbase,
-                    uint32_t S, SampleArrays sp, uint32_t* __restrict__ part) {
-  __shared__ uint64_t s_hi[K1_CHUNK], s_lo[K1_CHUNK];
-  __shared__ uint32_t s_len[K1_CHUNK];
-  __shared__ uint32_t s_range[2];
-  const uint32_t c = blockIdx.x;
-  int lo = 0, hi = k;  // segment of chunk c: last s with cbase[s] <= c
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (cbase[mid + 1] <= c)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  const int s = lo;
-  const SegDesc sd = segs[s];
-  const uint32_t nchunks = cbase[s + 1] - cbase[s], ci = c - cbase[s];
-  const uint32_t i0 = sd.lo + ci * K1_CHUNK;
-  const uint32_t i1 = (ci + 1 == nchunks) ? sd.hi : i0 + K1_CHUNK;
-  const uint32_t n = i1 - i0;
-  {  // all offset loads first, then all key loads: 8 independent chains per thread in flight
-    constexpr int PER = K1_CHUNK / 256;
-    uint32_t o[PER], e[PER];
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-      const uint32_t t = threadIdx.x + j * 256;
-      if (t < n) {
-        o[j] = __ldg(sd.toff + i0 + t);
-        e[j] = __ldg(sd.toff + i0 + t + 1);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-      const uint32_t t = threadIdx.x + j * 256;
-      if (t < n) {
-        uint64_t kh, kl;
-        load_key16(sd.tb, o[j], e[j] - o[j], 0, kh, kl);
-        s_hi[t] = kh;
-        s_lo[t] = kl;
-        s_len[t] = e[j] - o[j];
-      }
-    }
-  }
-  if (threadIdx.x < 2) {
-    // splitters <= the term before the chunk (0 for the first chunk) and <= its last term
-    // (all of them for the last chunk, whose tail maps to the window end)
-    uint32_t r;
-    const bool first = threadIdx.x == 0;
-    if (first ? ci == 0 : ci + 1 == nchunks) {
-      r = first ? 0u : S;
-    } else {
-      const KeyedTerm t = keyed_term(sd, first ? i0 - 1 : i1 - 1);
-      uint32_t a = 0, b = S;  // first splitter > t
-      while (a < b) {
-        const uint32_t mid = (a + b) >> 1;
-        if (keyed_compare(sample_term(sp, mid), t) <= 0)
-          a = mid + 1;
-        else
-          b = mid;
-      }
-      r = a;
-    }
-    s_range[threadIdx.x] = r;
-    if (ci == 0) part[(uint64_t)(first ? 0 : S + 1) * k + s] = first ? sd.lo : sd.hi;
-  }
-  __syncthreads();
-  const uint32_t ra = s_range[0], rb = s_range[1];
-  for (uint32_t r = ra + threadIdx.x; r < rb; r += 256) {
-    const KeyedTerm x = sample_term(sp, r);
-    uint32_t a = 0, b = n;  // first staged term >= x
-    while (a < b) {
-      const uint32_t mid = (a + b) >> 1;
-      KeyedTerm t;
-      t.hi = s_hi[mid];
-      t.lo = s_lo[mid];
-      t.len = s_len[mid];
-      int cmp;
-      if (t.hi != x.hi) {
-        cmp = t.hi < x.hi ? -1 : 1;
-      } else if (t.lo != x.lo) {
-        cmp = t.lo < x.lo ? -1 : 1;
-      } else if (t.len > 16 && x.len > 16) {
-        t.p = sd.tb + __ldg(sd.toff + i0 + mid);
-        cmp = term_compare(t.p + 16, t.len - 16, x.p + 16, x.len - 16);
-      } else {
-        cmp = t.len < x.len ? -1 : (t.len > x.len ? 1 : 0);
-      }
-      if (cmp < 0)
-        a = mid + 1;
-      else
-        b = mid;
-    }
-    part[(uint64_t)(r + 1) * k + s] = i0 + a;
-  }
-}
 
 // crank[c] = splitters <= the term just before chunk c (0 for the first chunk of a segment):
 // chunk c then owns the splitters [crank[c], crank[c+1]) (all the rest for a segment's last
@@ -299,7 +200,8 @@ __device__ __forceinline__ void smem_key16(const uint32_t* __restrict__ raw, uin
 __global__ void __launch_bounds__(256)
 k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ cbase,
                         uint32_t S, SampleArrays sp, const uint32_t* __restrict__ crank,
-                        uint32_t* __restrict__ part) {
+                        uint32_t* __restrict__ part, uint32_t* __restrict__ btb,
+                        uint64_t* __restrict__ bpo) {
   extern __shared__ __align__(16) uint32_t k1_smem[];
   uint32_t* s_off = k1_smem;                  // [K1_CHUNK + 1] term offsets of the chunk
   uint32_t* s_raw = k1_smem + K1_CHUNK + 4;   // staged term bytes (+ 8 words of slack)
@@ -354,9 +256,13 @@ k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t*
       for (uint32_t q = threadIdx.x; q < words; q += 256) s_raw[q] = __ldg(src + q);
     }
   }
-  if (threadIdx.x < 2 && ci == 0) {
+  if (threadIdx.x < 2 && ci == 0) {  // window start / end rows
     const bool first = threadIdx.x == 0;
-    part[(uint64_t)(first ? 0 : S + 1) * k + s] = first ? sd.lo : sd.hi;
+    const uint64_t at = (uint64_t)(first ? 0 : S + 1) * k + s;
+    const uint32_t idx = first ? sd.lo : sd.hi;
+    part[at] = idx;
+    btb[at] = __ldg(sd.toff + idx);
+    bpo[at] = __ldg(sd.poff + idx);
   }
   if (threadIdx.x == 0) {
     s_range[0] = crank[c];
@@ -392,47 +298,120 @@ k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t*
       else
         b = mid;
     }
-    part[(uint64_t)(r + 1) * k + s] = i0 + a;
+    // the boundary in every array of the segment: term index, first term byte, first posting
+    const uint64_t at = (uint64_t)(r + 1) * k + s;
+    part[at] = i0 + a;
+    btb[at] = s_off[a];
+    bpo[at] = __ldg(sd.poff + i0 + a);
   }
 }
 
 // One warp per bucket.  raw[0][b] = instances, raw[1][b] = input postings, raw[2][b] = staging
-// words (upper bound).
+// words (upper bound), raw[3][b] = term bytes of all instances (upper bound of the bucket's
+// merged term bytes).  Everything comes from the boundary tables the partition wrote.
+// sel != nullptr: rows were coalesced (k1_compact_rows) — row j of the tables is row sel[j] of the
+// fine partition, whose splitter is sample sel[j] - 1 (S_fine samples).
 __global__ void __launch_bounds__(256)
-k1_bucket_stats(const SegDesc* __restrict__ segs, int k, uint32_t S, SampleArrays sp,
-                const uint32_t* __restrict__ part, uint64_t* __restrict__ raw,
-                uint32_t* __restrict__ bk_cpl) {
+k1_bucket_stats(int k, uint32_t S, SampleArrays sp, const uint32_t* __restrict__ part,
+                const uint32_t* __restrict__ btb, const uint64_t* __restrict__ bpo,
+                uint64_t* __restrict__ raw, uint32_t* __restrict__ bk_cpl,
+                const uint32_t* __restrict__ sel, uint32_t S_fine) {
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t B = S + 1;
   if (b > B) return;
   const unsigned lane = lane_id();
   if (b == B) {
-    if (lane == 0) raw[B] = raw[(uint64_t)(B + 1) + B] = raw[2ull * (B + 1) + B] = 0;
+    if (lane < 4) raw[(uint64_t)lane * (B + 1) + B] = 0;
     return;
   }
-  uint64_t w = 0, p = 0;
+  uint64_t w = 0, p = 0, t = 0;
   for (int s = lane; s < k; s += 32) {
-    const uint32_t a = part[(uint64_t)b * k + s], e = part[(uint64_t)(b + 1) * k + s];
-    w += e - a;
-    if (e > a) p += __ldg(segs[s].poff + e) - __ldg(segs[s].poff + a);
+    const uint64_t r0 = (uint64_t)b * k + s, r1 = r0 + k;
+    w += part[r1] - part[r0];
+    p += bpo[r1] - bpo[r0];
+    t += btb[r1] - btb[r0];
   }
   w = warp_sum(w);
   p = warp_sum(p);
+  t = warp_sum(t);
   if (lane == 0) {
     raw[b] = w;
     raw[(uint64_t)(B + 1) + b] = p;
     // `_val` staging words the bucket can need: every term of L values reserves
-    // L + L/4 + 6 words (k12_union.cu enc_slot_words) and there are at most w terms
+    // L + L/4 + 6 words (union_dev.cuh enc_slot_words) and there are at most w terms
     raw[2ull * (B + 1) + b] = p + (p >> 2) + 6 * w;
+    raw[3ull * (B + 1) + b] = t;
     uint32_t c = 0;
-    if (b >= 1 && b < S) {  // both delimiting splitters exist: b-1 and b
-      const uint8_t* x = reinterpret_cast<const uint8_t*>(sp.ptr[b - 1]);
-      const uint8_t* y = reinterpret_cast<const uint8_t*>(sp.ptr[b]);
-      const uint32_t m = sp.len[b - 1] < sp.len[b] ? sp.len[b - 1] : sp.len[b];
+    // the delimiting splitters of bucket b, if both exist (fine sample indexes)
+    const uint32_t r0 = sel ? sel[b] : b, r1 = sel ? sel[b + 1] : b + 1;
+    const uint32_t Sf = sel ? S_fine : S;
+    if (r0 >= 1 && r1 <= Sf && w) {
+      const uint8_t* x = reinterpret_cast<const uint8_t*>(sp.ptr[r0 - 1]);
+      const uint8_t* y = reinterpret_cast<const uint8_t*>(sp.ptr[r1 - 1]);
+      const uint32_t m = sp.len[r0 - 1] < sp.len[r1 - 1] ? sp.len[r0 - 1] : sp.len[r1 - 1];
       while (c < m && x[c] == y[c]) c++;
     }
     bk_cpl[b] = c;
   }
+}
+
+// ---- coalescing of a fine partition -----------------------------------------------------------
+// Evenly spaced terms of one segment are NOT evenly spaced in the merged order (the number of
+// other terms between two of them is negative-binomial: CV 0.2 at 64 segments), and a bucket
+// must fit a tile of the bucket kernel.  So the partition is made four times finer than needed
+// and whole fine buckets are joined: row r of the fine tables survives iff a multiple of the
+// target size lies in (C[r-1], C[r]], C[r] = instances before row r.  A final bucket then
+// holds target +- one fine bucket, and the number of final rows is bounded by N / target + 2
+// without asking the device: the table is padded with copies of the end row (empty buckets).
+__global__ void __launch_bounds__(256)
+k1_fine_sizes(const uint32_t* __restrict__ part, int k, uint32_t rows /* S_fine + 2 */,
+              uint64_t* __restrict__ cum) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // instances before row r
+  if (r >= rows) return;
+  uint64_t w = 0;
+  for (int s = lane_id(); s < k; s += 32) w += part[(uint64_t)r * k + s] - part[s];
+  w = warp_sum(w);
+  if (lane_id() == 0) cum[r] = w;
+}
+
+__global__ void __launch_bounds__(256)
+k1_select_rows(const uint64_t* __restrict__ cum, uint32_t rows, uint32_t target,
+               uint64_t* __restrict__ flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > rows) return;
+  uint64_t f = 0;
+  if (r == 0)
+    f = 1;  // window starts
+  else if (r < rows - 1)
+    f = cum[r] / target > cum[r - 1] / target ? 1 : 0;
+  flag[r] = f;  // flag[rows - 1] (window ends) and flag[rows] stay 0: the padding supplies them
+}
+
+__global__ void __launch_bounds__(256)
+k1_mark_rows(const uint64_t* __restrict__ idx, const uint64_t* __restrict__ cum, uint32_t rows,
+             uint32_t target, uint32_t* __restrict__ sel, uint32_t out_rows) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows - 1) {
+    const bool kept = r == 0 || cum[r] / target > cum[r - 1] / target;
+    if (kept && idx[r] < out_rows) sel[idx[r]] = r;
+  }
+  // rows past the kept ones: the end row
+  const uint64_t kept_total = idx[rows - 1];
+  if (r < out_rows && r >= kept_total) sel[r] = rows - 1;
+}
+
+__global__ void __launch_bounds__(256)
+k1_compact_rows(const uint32_t* __restrict__ sel, int k, uint32_t out_rows,
+                const uint32_t* __restrict__ part_f, const uint32_t* __restrict__ btb_f,
+                const uint64_t* __restrict__ bpo_f, uint32_t* __restrict__ part,
+                uint32_t* __restrict__ btb, uint64_t* __restrict__ bpo) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)out_rows * k) return;
+  const uint32_t j = (uint32_t)(i / k), s = (uint32_t)(i % k);
+  const uint64_t from = (uint64_t)sel[j] * k + s;
+  part[i] = part_f[from];
+  btb[i] = btb_f[from];
+  bpo[i] = bpo_f[from];
 }
 
 int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaStream_t s) {
@@ -443,7 +422,7 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     return II2_ERR_UNSUPPORTED;
   }
   // samples per segment, proportional to its window; chunks of the merge-path partition
-  static const uint32_t per_bucket = [] {  // tuning knob: II2_BUCKET=<instances per bucket>
+  const uint32_t per_bucket = [] {  // tuning knob: II2_BUCKET=<instances per bucket>
     const char* e = getenv("II2_BUCKET");
     const long v = e ? atol(e) : 0;
     return (v >= 32 && v <= 1024) ? (uint32_t)v : kInstancesPerBucket;
@@ -463,6 +442,22 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   }();
   if (small_bucket && want < small_want && N / small_bucket > want)
     want = std::min<uint64_t>(small_want, N / small_bucket);
+  // large calls: a partition `fine` times finer, coalesced afterwards (II2_COALESCE=<fine>, 1 = off)
+  // (II2_COALESCE_MIN=<buckets>: calls cut into fewer buckets keep the plain partition)
+  const uint32_t coalesce = [] {
+    const char* e = getenv("II2_COALESCE");
+    const long v = e ? atol(e) : 4;
+    return (v >= 1 && v <= 16) ? (uint32_t)v : 4u;
+  }();
+  const uint64_t coalesce_min = [] {
+    const char* e = getenv("II2_COALESCE_MIN");
+    const long v = e ? atol(e) : 2048;
+    return v >= 1 ? (uint64_t)v : 2048ull;
+  }();
+  const uint32_t fine =
+      (coalesce > 1 && want >= coalesce_min && want * coalesce < kMaxBuckets - 1) ? coalesce : 1;
+  const uint64_t want_final = want;
+  want *= fine;
   if (want > kMaxBuckets - 1) want = kMaxBuckets - 1;
   uint32_t* cbase = sbase + (k + 1);
   sbase[0] = 0;
@@ -493,14 +488,34 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     sbase[i + 1] = sbase[i] + (uint32_t)m;
     cbase[i + 1] = cbase[i] + (uint32_t)std::max<uint64_t>(1, (n + K1_CHUNK - 1) / K1_CHUNK);
   }
-  const uint32_t S = sbase[k], B = S + 1, n_chunks = cbase[k];
-  plan.n_samples = S;
+  const uint32_t S = sbase[k], n_chunks = cbase[k];  // S samples = S + 1 buckets of the partition
+  // final buckets: the partition's own, or the coalesced ones (an upper bound, padded)
+  const uint32_t target = (uint32_t)std::max<uint64_t>(1, N / std::max<uint64_t>(1, want_final));
+  const uint32_t B = fine > 1 ? (uint32_t)(N / target + 2) : S + 1;
+  plan.n_samples = B - 1;
   plan.n_buckets = B;
   ProfScope scope("k1_plan", s);
-  II2_TRY(plan.part.alloc_scratch((size_t)(S + 2) * k, s));
+  II2_TRY(plan.part.alloc_scratch((size_t)(B + 1) * k, s));
   II2_TRY(plan.bk_cpl.alloc_scratch(B, s));
-  II2_TRY(plan.bk_WP.alloc_scratch(3 * (size_t)(B + 1), s));
-  II2_TRY(plan.totals.alloc_scratch(3, s));
+  II2_TRY(plan.btb.alloc_scratch((size_t)(B + 1) * k, s));
+  II2_TRY(plan.bpo.alloc_scratch((size_t)(B + 1) * k, s));
+  II2_TRY(plan.bk_WP.alloc_scratch(4 * (size_t)(B + 1), s));
+  II2_TRY(plan.totals.alloc_scratch(4, s));
+  DevBuf<uint32_t> part_f, btb_f, d_sel;
+  DevBuf<uint64_t> bpo_f, d_cum, d_idx;
+  uint32_t *p_part = plan.part.p, *p_btb = plan.btb.p;
+  uint64_t* p_bpo = plan.bpo.p;
+  if (fine > 1) {
+    II2_TRY(part_f.alloc_scratch((size_t)(S + 2) * k, s));
+    II2_TRY(btb_f.alloc_scratch((size_t)(S + 2) * k, s));
+    II2_TRY(bpo_f.alloc_scratch((size_t)(S + 2) * k, s));
+    II2_TRY(d_cum.alloc_scratch((size_t)S + 3, s));
+    II2_TRY(d_idx.alloc_scratch((size_t)S + 3, s));
+    II2_TRY(d_sel.alloc_scratch((size_t)B + 1, s));
+    p_part = part_f.p;
+    p_btb = btb_f.p;
+    p_bpo = bpo_f.p;
+  }
   DevBuf<uint32_t> d_base, d_u32;
   DevBuf<uint64_t> d_u64;
   const size_t Sx = S ? S : 1;
@@ -518,11 +533,7 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     k1_rank_samples<<<div_up((uint64_t)S * 32, 256), 256, 0, s>>>(k, d_sbase, S, sa, sp);
     II2_LAUNCHED();
   }
-  // II2_PARTITION_KEYS=1: the first version of the kernel (key windows of every term staged)
-  static const bool old_partition = getenv("II2_PARTITION_KEYS") != nullptr;
-  if (old_partition) {
-    k1_partition_chunks<<<n_chunks, 256, 0, s>>>(plan.segs, k, d_cbase, S, sp, plan.part.p);
-  } else {
+  {
     constexpr size_t smem = (K1_CHUNK + 4 + 8) * 4 + K1_RAW_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
@@ -536,13 +547,28 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
                                                           crank.p);
     II2_LAUNCHED();
     k1_partition_chunks_raw<<<n_chunks, 256, smem, s>>>(plan.segs, k, d_cbase, S, sp, crank.p,
-                                                        plan.part.p);
+                                                        p_part, p_btb, p_bpo);
   }
   II2_LAUNCHED();
+  if (fine > 1) {
+    const uint32_t rows = S + 2;
+    k1_fine_sizes<<<div_up((uint64_t)rows * 32, 256), 256, 0, s>>>(p_part, k, rows, d_cum.p);
+    II2_LAUNCHED();
+    k1_select_rows<<<div_up((uint64_t)rows + 1, 256), 256, 0, s>>>(d_cum.p, rows, target, d_idx.p);
+    II2_LAUNCHED();
+    II2_TRY(exclusive_scan_u64(d_idx.p, (uint64_t)rows + 1, nullptr, s));
+    k1_mark_rows<<<div_up(std::max<uint64_t>(rows, (uint64_t)B + 1), 256), 256, 0, s>>>(
+        d_idx.p, d_cum.p, rows, target, d_sel.p, B + 1);
+    II2_LAUNCHED();
+    k1_compact_rows<<<div_up((uint64_t)(B + 1) * k, 256), 256, 0, s>>>(
+        d_sel.p, k, B + 1, p_part, p_btb, p_bpo, plan.part.p, plan.btb.p, plan.bpo.p);
+    II2_LAUNCHED();
+  }
   k1_bucket_stats<<<div_up((uint64_t)(B + 1) * 32, 256), 256, 0, s>>>(
-      plan.segs, k, S, sp, plan.part.p, plan.bk_WP.p, plan.bk_cpl.p);
+      k, B - 1, sp, plan.part.p, plan.btb.p, plan.bpo.p, plan.bk_WP.p, plan.bk_cpl.p,
+      fine > 1 ? d_sel.p : nullptr, S);
   II2_LAUNCHED();
-  II2_TRY(exclusive_scan_multi_u64(plan.bk_WP.p, plan.bk_WP.p, B + 1, 3, plan.totals.p, s));
+  II2_TRY(exclusive_scan_multi_u64(plan.bk_WP.p, plan.bk_WP.p, B + 1, 4, plan.totals.p, s));
   return II2_OK;
 }
 

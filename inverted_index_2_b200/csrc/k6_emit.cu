@@ -27,6 +27,7 @@ struct K6Args {
   const uint32_t* tmp_enc;
   const uint64_t* bk_out;  // [4][nb1] exclusive prefixes
   uint32_t nb1;
+  const uint32_t* list;    // or: one bucket per CTA, the buckets the fused kernel deferred
   int want_dec, want_enc, keep_empty;
   uint8_t* o_term_bytes;
   uint32_t* o_term_off;
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(K6_THREADS, K6_MIN_CTAS) k6_emit_kernel(const 
   __shared__ uint64_t s_ws64[K6_WARPS + 2];
   __shared__ uint32_t s_pref[K6_MAX_GROUP + 1];
   __shared__ uint64_t s_base[K6_MAX_GROUP];
-  const uint32_t tid = threadIdx.x, b0 = blockIdx.x * group;
-  const uint32_t nb = min(group, n_buckets - b0);
+  const uint32_t tid = threadIdx.x, b0 = a.list ? a.list[blockIdx.x] : blockIdx.x * group;
+  const uint32_t nb = a.list ? 1u : min(group, n_buckets - b0);
   if (tid < 32) {
     const uint32_t d = tid < nb ? a.bk_D[b0 + tid] : 0u;
     const uint32_t inc = warp_inclusive_scan(d);
@@ -201,6 +202,107 @@ __global__ void __launch_bounds__(K6_THREADS, K6_MIN_CTAS) k6_emit_kernel(const 
   }
 }
 
+// ---- dense buckets (K12f) ---------------------------------------------------------------------
+// The fused kernel left bucket b finished and dense in its staging areas; its place in the
+// result is the bucket-level prefix.  One warp per bucket: three contiguous copies (term bytes,
+// `_val` words, decoded postings) with 16-byte stores on the destination's alignment, and the
+// per-term offsets rebased.  Pure HBM copy work.
+struct K6DenseArgs {
+  const uint64_t* bk_pos;
+  const uint64_t* bk_P;
+  const uint64_t* bk_E;
+  const uint64_t* bk_TB;
+  const uint32_t* bk_mode;
+  const uint64_t* bk_raw;  // [4][nb1] per bucket: terms, term bytes, postings, words
+  const uint64_t* bk_out;  // exclusive prefixes of bk_raw
+  uint32_t nb1;
+  int want_dec, want_enc;
+  const uint8_t* st_tb;
+  const uint32_t* st_toff;
+  const uint32_t* st_eoff;
+  const uint32_t* st_poff;
+  const uint32_t* st_enc;
+  const uint32_t* st_post;
+  uint8_t* o_term_bytes;
+  uint32_t* o_term_off;
+  uint32_t* o_post;
+  uint64_t* o_post_off;
+  uint32_t* o_val_words;
+  uint64_t* o_val_off;
+};
+
+// n words src -> dst by one warp: scalar head up to the destination's 16-byte boundary, then one
+// 128-bit store per lane (four coalesced word loads: the source has its own phase), two in flight
+__device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ dst,
+                                                const uint32_t* __restrict__ src, uint32_t n) {
+  const unsigned lane = lane_id();
+  uint32_t head = (uint32_t)(((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
+  head = head < n ? head : n;
+  if (lane < head) dst[lane] = __ldg(src + lane);
+  const uint32_t nvec = (n - head) >> 2;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  const uint32_t* s4 = src + head;
+  uint32_t v = lane;
+  for (; v + 32 < nvec; v += 64) {
+    const uint32_t e0 = 4 * v, e1 = 4 * (v + 32);
+    const uint4 x = make_uint4(__ldg(s4 + e0), __ldg(s4 + e0 + 1), __ldg(s4 + e0 + 2), __ldg(s4 + e0 + 3));
+    const uint4 y = make_uint4(__ldg(s4 + e1), __ldg(s4 + e1 + 1), __ldg(s4 + e1 + 2), __ldg(s4 + e1 + 3));
+    d4[v] = x;
+    d4[v + 32] = y;
+  }
+  if (v < nvec) {
+    const uint32_t e0 = 4 * v;
+    d4[v] = make_uint4(__ldg(s4 + e0), __ldg(s4 + e0 + 1), __ldg(s4 + e0 + 2), __ldg(s4 + e0 + 3));
+  }
+  const uint32_t tail0 = head + 4 * nvec;
+  if (tail0 + lane < n) dst[tail0 + lane] = __ldg(src + tail0 + lane);
+}
+
+// n bytes: byte head up to the destination's 4-byte boundary, then one 32-bit store per lane
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst,
+                                                const uint8_t* __restrict__ src, uint32_t n) {
+  const unsigned lane = lane_id();
+  uint32_t head = (uint32_t)((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+  head = head < n ? head : n;
+  if (lane < head) dst[lane] = __ldg(src + lane);
+  const uint32_t nw = (n - head) >> 2;
+  for (uint32_t w = lane; w < nw; w += 32) {
+    const uint8_t* p = src + head + 4 * w;
+    const uint32_t x = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) |
+                       ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+    *reinterpret_cast<uint32_t*>(dst + head + 4 * w) = x;
+  }
+  const uint32_t tail0 = head + 4 * nw;
+  if (tail0 + lane < n) dst[tail0 + lane] = __ldg(src + tail0 + lane);
+}
+
+__global__ void __launch_bounds__(K6_THREADS) k6_dense_kernel(const K6DenseArgs a, uint32_t n_buckets) {
+  const uint32_t b = blockIdx.x * K6_WARPS + warp_id();
+  if (b >= n_buckets) return;
+  const unsigned lane = lane_id();
+  const uint64_t T0 = a.bk_out[0ull * a.nb1 + b], TB0 = a.bk_out[1ull * a.nb1 + b],
+                 P0 = a.bk_out[2ull * a.nb1 + b], E0 = a.bk_out[3ull * a.nb1 + b];
+  if (a.bk_mode[b] == K12F_DENSE) {
+    const uint32_t T = (uint32_t)a.bk_raw[0ull * a.nb1 + b], TB = (uint32_t)a.bk_raw[1ull * a.nb1 + b],
+                   P = (uint32_t)a.bk_raw[2ull * a.nb1 + b], E = (uint32_t)a.bk_raw[3ull * a.nb1 + b];
+    const uint64_t pos = a.bk_pos[b];
+    for (uint32_t t = lane; t < T; t += 32) {
+      a.o_term_off[T0 + t] = (uint32_t)TB0 + a.st_toff[pos + t];
+      if (a.want_enc) a.o_val_off[T0 + t] = 4ull * (E0 + a.st_eoff[pos + t]);
+      if (a.want_dec) a.o_post_off[T0 + t] = P0 + a.st_poff[pos + t];
+    }
+    warp_copy_bytes(a.o_term_bytes + TB0, a.st_tb + a.bk_TB[b], TB);
+    if (a.want_enc) warp_copy_words(a.o_val_words + E0, a.st_enc + a.bk_E[b], E);
+    if (a.want_dec) warp_copy_words(a.o_post + P0, a.st_post + a.bk_P[b], P);
+  }
+  // terminal offsets: T0 .. of the one-past-the-end bucket row are the totals
+  if (b + 1 == n_buckets && lane == 0) {
+    const uint64_t T = a.bk_out[0ull * a.nb1 + n_buckets];
+    a.o_term_off[T] = (uint32_t)a.bk_out[1ull * a.nb1 + n_buckets];
+    if (a.want_dec) a.o_post_off[T] = a.bk_out[2ull * a.nb1 + n_buckets];
+  }
+}
+
 int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t s) {
   const uint64_t T = u.h_totals[0], TB = u.h_totals[1], P = u.h_totals[2], E = u.h_totals[3];
   if (TB >= (1ull << 32)) {
@@ -208,14 +310,14 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
     return II2_ERR_UNSUPPORTED;
   }
   II2_TRY(out.term_bytes.alloc(TB, s, 32));
-  II2_TRY(out.term_off.alloc(T + 1, s));
+  II2_TRY(out.term_off.alloc(T + 1, s, 16));
   if (u.want_dec) {
     II2_TRY(out.post.alloc(P, s, 16));
-    II2_TRY(out.post_off.alloc(T + 1, s));
+    II2_TRY(out.post_off.alloc(T + 1, s, 16));
   }
   if (u.want_enc) {
-    II2_TRY(out.val_words.alloc(E, s));
-    II2_TRY(out.val_off.alloc(T, s));
+    II2_TRY(out.val_words.alloc(E, s, 16));
+    II2_TRY(out.val_off.alloc(T, s, 16));
   }
   K6Args a;
   a.segs = plan.segs;
@@ -226,6 +328,7 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   a.tmp_enc = u.tmp_enc.p;
   a.bk_out = u.bk_out.p;
   a.nb1 = plan.n_buckets + 1;
+  a.list = nullptr;
   a.want_dec = u.want_dec ? 1 : 0;
   a.want_enc = u.want_enc ? 1 : 0;
   a.keep_empty = u.keep_empty ? 1 : 0;
@@ -236,6 +339,40 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   a.o_val_words = out.val_words.p;
   a.o_val_off = out.val_off.p;
   ProfScope scope("k6_emit", s);
+  if (u.fused) {
+    const uint32_t N = plan.n_total;
+    K6DenseArgs d;
+    d.bk_pos = plan.bk_pos();
+    d.bk_P = plan.bk_P();
+    d.bk_E = plan.bk_E();
+    d.bk_TB = plan.bk_TB();
+    d.bk_mode = u.bk_mode.p;
+    d.bk_raw = u.bk_raw.p;
+    d.bk_out = u.bk_out.p;
+    d.nb1 = plan.n_buckets + 1;
+    d.want_dec = a.want_dec;
+    d.want_enc = a.want_enc;
+    d.st_tb = u.st_tb.p;
+    d.st_toff = u.st_off.p;
+    d.st_eoff = u.st_off.p + N;
+    d.st_poff = u.st_off.p + 2 * (size_t)N;
+    d.st_enc = u.tmp_enc.p;
+    d.st_post = u.tmp_post.p;
+    d.o_term_bytes = out.term_bytes.p;
+    d.o_term_off = out.term_off.p;
+    d.o_post = out.post.p;
+    d.o_post_off = out.post_off.p;
+    d.o_val_words = out.val_words.p;
+    d.o_val_off = out.val_off.p;
+    k6_dense_kernel<<<div_up(plan.n_buckets, K6_WARPS), K6_THREADS, 0, s>>>(d, plan.n_buckets);
+    II2_LAUNCHED();
+    if (u.n_def) {  // the buckets the general kernels ran: one CTA each, from their records
+      a.list = u.def_list.p;
+      k6_emit_kernel<<<u.n_def, K6_THREADS, 0, s>>>(a, 1, plan.n_buckets);
+      II2_LAUNCHED();
+    }
+    return II2_OK;
+  }
   // buckets per CTA: about one CTA-width of records
   const uint64_t tm = u.terms_merged ? u.terms_merged : 1;
   uint32_t group = (uint32_t)std::min<uint64_t>(

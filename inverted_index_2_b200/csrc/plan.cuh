@@ -23,13 +23,19 @@ struct MergePlan {
   // rows of k lower bounds: row 0 = window starts, row r+1 = lower_bound of splitter r (sorted)
   // in every segment, row S+1 = window ends; bucket b spans rows b .. b+1
   DevBuf<uint32_t> part;          // [(S+2) * k]
+  // the same boundaries in the other arrays of the segments: toff[part[..]] and poff[part[..]]
+  // (first term byte / first posting of the run that starts there)
+  DevBuf<uint32_t> btb;           // [(S+2) * k]
+  DevBuf<uint64_t> bpo;           // [(S+2) * k]
   DevBuf<uint32_t> bk_cpl;        // [B]   common prefix length of all terms in the bucket
-  // [3][B+1] exclusive prefixes: instances / input postings / `_val` staging words (upper bound)
+  // [4][B+1] exclusive prefixes: instances / input postings / `_val` staging words (upper
+  // bound) / term bytes of all instances (upper bound of the merged term bytes)
   DevBuf<uint64_t> bk_WP;
   const uint64_t* bk_pos() const { return bk_WP.p; }
   const uint64_t* bk_P() const { return bk_WP.p + (n_buckets + 1); }
   const uint64_t* bk_E() const { return bk_WP.p + 2 * (size_t)(n_buckets + 1); }
-  DevBuf<uint64_t> totals;        // [3] {Σ instances, Σ postings in, Σ staging words}
+  const uint64_t* bk_TB() const { return bk_WP.p + 3 * (size_t)(n_buckets + 1); }
+  DevBuf<uint64_t> totals;        // [4] {Σ instances, Σ postings in, Σ staging words, Σ term bytes}
 };
 
 // K1: choose splitters and partition every segment (the k-way merge of the term dictionaries,

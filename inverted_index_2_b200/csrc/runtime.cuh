@@ -45,14 +45,15 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
-  // `pad_bytes` extra readable bytes past the end (over-reading vector loads).
+  // `pad_bytes` extra readable bytes past the end (over-reading vector loads).  Every buffer
+  // carries 16 bytes more than asked: the fused merge kernel stages the 16-byte aligned
+  // ENVELOPE of a run, which may end up to 15 bytes past the array.
   int alloc(size_t count, cudaStream_t stream, size_t pad_bytes = 0) {
     release();
     s = stream;
     n = count;
     scratch = false;
-    size_t bytes = count * sizeof(T) + pad_bytes;
-    if (bytes == 0) bytes = 16;
+    size_t bytes = count * sizeof(T) + pad_bytes + 16;
     void* q = nullptr;
     II2_CUDA_TRY(cudaMallocAsync(&q, bytes, stream));
     p = static_cast<T*>(q);
@@ -64,8 +65,7 @@ struct DevBuf {
     s = stream;
     n = count;
     scratch = true;
-    size_t bytes = count * sizeof(T) + pad_bytes;
-    if (bytes == 0) bytes = 16;
+    size_t bytes = count * sizeof(T) + pad_bytes + 16;
     p = static_cast<T*>(arena_alloc(bytes, stream));
     return p ? II2_OK : II2_ERR_NOMEM;
   }

@@ -49,6 +49,45 @@ struct LargeArgs {
   uint32_t nb1;
 };
 
+// ---- K12f (k12_fused.cu): a whole bucket in one kernel --------------------------------------
+constexpr uint32_t F_MAXK = 256;  // segments per call on the fused path
+// bk_mode[b]: how bucket b's output is laid out for the placement kernels (k6_emit.cu)
+constexpr uint32_t K12F_RECORDS = 0;   // per-term GroupRec + upper-bound slots (K1b / K2b)
+constexpr uint32_t K12F_DENSE = 1;     // dense, merged order, in the bucket's staging areas (K12f)
+constexpr uint32_t K12F_DEFERRED = 2;  // K12f passed: the general kernels run it (-> records)
+
+struct K12fArgs {
+  const SegDesc* segs;
+  int k;
+  const uint32_t* part;  // boundary tables of the plan
+  const uint32_t* btb;
+  const uint64_t* bpo;
+  const uint64_t* bk_pos;
+  const uint32_t* bk_cpl;
+  const uint64_t* bk_P;
+  const uint64_t* bk_E;
+  const uint64_t* bk_TB;
+  RemovedSet rem;
+  int want_enc, want_dec, keep_empty;
+  uint32_t* bk_D;
+  uint32_t* bk_mode;
+  uint64_t* bk_raw;  // [4][nb1], zeroed
+  uint32_t nb1;
+  // dense staging of bucket b: term bytes at bk_TB[b], `_val` words at bk_E[b], decoded
+  // postings at bk_P[b]; per surviving term (index bk_pos[b] + t) its offsets relative to the
+  // bucket: first term byte, first word, first posting
+  uint8_t* st_tb;
+  uint32_t* st_toff;
+  uint32_t* st_eoff;
+  uint32_t* st_poff;
+  uint32_t* st_enc;
+  uint32_t* st_post;
+  uint32_t* n_def;     // deferred buckets
+  uint32_t* def_list;
+};
+bool k12f_supported(int k);
+int k12f_launch(const K12fArgs& a, uint32_t n_buckets, cudaStream_t s);
+
 int k2_large_run(LargeArgs la, uint32_t n_groups, DevBuf<uint32_t>& large_tmp,
                  DevBuf<uint32_t>& large_enc, cudaStream_t s);
 
@@ -59,6 +98,13 @@ struct UnionOut {
   DevBuf<uint32_t> large_enc;  // the same for heavy terms
   DevBuf<uint32_t> large_tmp;  // sort space of the multi-CTA path for heavy terms
   DevBuf<uint32_t> bk_D;       // [B] distinct terms per bucket
+  // fused path (K12f): dense per-bucket staging
+  bool fused = false;
+  DevBuf<uint8_t> st_tb;       // [Σ term bytes of all instances] merged term bytes, bucket b at bk_TB[b]
+  DevBuf<uint32_t> st_off;     // [3][N_T] bucket-relative term-byte / word / posting offsets
+  DevBuf<uint32_t> bk_mode;    // [B] K12F_*
+  DevBuf<uint32_t> def_list;   // [B] buckets K12f left to the general kernels
+  uint32_t n_def = 0;
   // [4][B+1] per bucket {surviving terms, their term bytes, postings out, encoded words}
   DevBuf<uint64_t> bk_raw;
   DevBuf<uint64_t> bk_out;     // exclusive prefixes of bk_raw
@@ -76,8 +122,9 @@ struct UnionOut {
 // shared memory.  Synchronises the stream once to learn the output sizes.
 // keep_empty: terms left with no values are kept (plain reads) instead of dropped (merge,
 // shard.go:192-194).
+// n_in / tb_in: input postings / term bytes inside the windows (upper bounds size the staging).
 int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool want_enc,
-              bool keep_empty, uint64_t n_in, UnionOut& u, cudaStream_t s);
+              bool keep_empty, uint64_t n_in, uint64_t tb_in, UnionOut& u, cudaStream_t s);
 
 struct EmitOut {
   DevBuf<uint8_t> term_bytes;

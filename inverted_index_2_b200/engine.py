@@ -27,6 +27,11 @@ class EngineError(RuntimeError):
 def load_library(build_if_needed: bool = True) -> C.CDLL:
     """Loads libii2.so built in-tree; never falls back to anything else."""
     so = os.path.join(_HERE, "libii2.so")
+    alt = os.environ.get("II2_LIB")  # tuning sweeps: another build of the same library
+    if alt:
+        lib = C.CDLL(alt)
+        A.bind(lib, A.PROTOTYPES)
+        return lib
     if build_if_needed and os.path.isdir(os.path.join(_HERE, "csrc")):
         from .build import build
         try:
@@ -409,6 +414,46 @@ class Engine:
 
     def bitmask(self, init=None) -> Bitmask:
         return Bitmask(self, init)
+
+    # ---- cross-shard exchange (NCCL behind the C-ABI; one process per GPU) -----------------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._check(self.lib.ii2_comm_unique_id(C.cast(buf, A.u8p)), "comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid.ljust(128, b"\0")[:128])
+        self._check(self.lib.ii2_comm_init(C.cast(buf, A.u8p), rank, world), "comm_init")
+
+    def comm_info(self) -> tuple[int, int]:
+        r, w = C.c_int(), C.c_int()
+        self.lib.ii2_comm_info(C.byref(r), C.byref(w))
+        return r.value, w.value
+
+    def comm_shutdown(self) -> None:
+        self.lib.ii2_comm_shutdown()
+
+    def read_gather(self, local: DeviceResult, root: int = 0) -> DeviceResult:
+        """Collective (every rank): the rank-ordered concatenation of the ranks' decoded read
+        results on `root` (every rank if root < 0) — InvertedIndex.Read over all shards."""
+        h = C.c_void_p()
+        self._check(self.lib.ii2_read_gather(local.h, root, C.byref(h)), "read_gather")
+        return DeviceResult(self, h.value)
+
+    def prefix_search_gather(self, segs: list[DeviceSegment], prefixes: list[bytes], root: int = 0
+                             ) -> dict[bytes, np.ndarray]:
+        """Collective: this rank's prefix search over its resident shards, then the per-prefix
+        sorted-unique union of every rank's values on `root` (other ranks get {})."""
+        blob, off = self._prefix_args(prefixes)
+        local, merged = A.PrefixOut(), A.PrefixOut()
+        self._check(self.lib.ii2_prefix_search_dev(self._handles(segs), len(segs),
+                                                   A.np_ptr(blob, A.u8p), A.np_ptr(off, A.u32p),
+                                                   len(prefixes), C.byref(local)), "prefix_search_dev")
+        try:
+            self._check(self.lib.ii2_prefix_gather(C.byref(local), root, C.byref(merged)), "prefix_gather")
+        finally:
+            self.lib.ii2_prefix_out_free(C.byref(local))
+        return self._prefix_result(prefixes, merged)
 
     # ---- misc --------------------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None):

@@ -4,19 +4,42 @@ The reference already partitions by term prefix into <= 1024 shards that never i
 Put / Merge (shard.go:19-20, shardKey shard.go:362-378), so compaction needs NO collective:
 every rank owns a contiguous range of shard keys and merges its own shards.  Only reads that
 span ranks exchange data — InvertedIndex.Read is an ordered concatenation of shard streams
-(inverted_index.go:330-338), so the gather is: all-gather of the sizes, then a padded
-all-gather of the flat arrays, concatenated in rank order (rank order == shard-key order).
-PrefixSearch adds one dedup pass after the gather (inverted_index.go:289-292).
-`torch.distributed` is the plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+(inverted_index.go:330-338); PrefixSearch adds one sort + compact after the union
+(inverted_index.go:274-292).
+
+The exchange itself is the library's: `ii2_comm_init` / `ii2_read_gather` / `ii2_prefix_gather`
+(include/ii2.h, csrc/comm.cu — NCCL over NVLink, reachable from cgo).  Protocol: ONE all-gather of
+a fixed-size record (sizes / per-prefix offsets), then ONE round of point-to-point transfers of the
+flat arrays, unpadded, straight to their place on the root, offsets rebased there.  This module
+holds the partitioning rule, thin wrappers over those calls for a `torch.distributed` launch
+(`comm_init_from_torch`), and a CPU restatement of the same protocol over a torch process group
+(gloo) so that the multi-rank host logic is testable without GPUs.
 """
 from __future__ import annotations
 
 import numpy as np
 
 from .flat import ReadResult
-from .host import InvertedIndex, shard_key
 
 N_SHARD_KEYS = 1024  # 10 bits, shard.go:371-375
+
+
+def shard_key_of(term: bytes) -> int:
+    """shardKey (shard.go:362-378) as a number: top 10 bits of the first two bytes; terms
+    shorter than two bytes go to shard 0."""
+    if len(term) < 2:
+        return 0
+    return (((term[0] << 8) + term[1]) & 0xFFFF) >> 6
+
+
+def shard_keys_of_sorted(term_bytes: np.ndarray, term_off: np.ndarray) -> np.ndarray:
+    """shardKey of every term of a flat dictionary (vectorised)."""
+    off = term_off[:-1].astype(np.int64)
+    lens = np.diff(term_off.astype(np.int64))
+    tb = np.concatenate([term_bytes, np.zeros(2, dtype=np.uint8)])
+    k = ((tb[off].astype(np.int64) << 8) + tb[off + 1].astype(np.int64)) >> 6
+    k[lens < 2] = 0
+    return k
 
 
 def partition_shard_keys(weights: np.ndarray, world: int) -> np.ndarray:
@@ -37,98 +60,103 @@ def owner_of(key: int, bounds: np.ndarray) -> int:
     return int(np.searchsorted(bounds, key, side="right") - 1)
 
 
-def _gather_var(dist, t, group=None):
-    """All-gather of 1-D tensors of different lengths; returns the list in rank order."""
-    import torch
-    world = dist.get_world_size(group)
-    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
-    pad[: t.numel()] = t
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad, group=group)
-    return [o[:s] for o, s in zip(outs, sizes)]
+# ---- the library's NCCL exchange under a torch.distributed launch ---------------------------
+def comm_init_from_torch(eng, group=None) -> None:
+    """ii2_comm_init on every rank of a torch.distributed job: rank 0 makes the NCCL id
+    (ii2_comm_unique_id), torch broadcasts its 128 bytes, every rank joins."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    eng.comm_init(box[0], rank, world)
 
 
-def gather_read_results(local: ReadResult, device="cpu", group=None) -> ReadResult:
-    """Ordered concatenation of every rank's ReadResult (rank order = term order)."""
+# ---- the same protocol on a torch process group (gloo): CPU shim for the tests ------------------
+def _exchange(arrays: list[np.ndarray], sizes_all: np.ndarray, root: int, group, device):
+    """arrays[j] of every rank -> root, unpadded: per (rank, array) one point-to-point transfer.
+    sizes_all[r][j] = elements of array j on rank r (known everywhere from the all-gather).
+    Returns on the root a list (per array) of per-rank numpy arrays, elsewhere None."""
     import torch
     import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    signed = {np.dtype(np.uint8): np.uint8, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}
+    if rank != root:
+        for a in arrays:
+            if len(a):  # NCCL / gloo have no unsigned 32/64-bit types: move the bits as signed
+                t = torch.from_numpy(np.ascontiguousarray(a).view(signed[a.dtype])).to(device)
+                dist.send(t, dst=root, group=group)
+        return None
+    out = [[None] * world for _ in arrays]
+    for r in range(world):
+        for j, a in enumerate(arrays):
+            n = int(sizes_all[r][j])
+            if r == rank:
+                out[j][r] = np.ascontiguousarray(a)
+            elif n == 0:
+                out[j][r] = np.zeros(0, dtype=a.dtype)
+            else:
+                t = torch.empty(n, dtype=torch.from_numpy(np.zeros(1, dtype=signed[a.dtype])).dtype,
+                                device=device)
+                dist.recv(t, src=r, group=group)
+                out[j][r] = t.cpu().numpy().view(a.dtype)
+    return out
 
-    def tt(a, dt):
-        # NCCL has no unsigned 32/64-bit types: move the bits as signed integers
-        return torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(device)
-    tb = _gather_var(dist, tt(local.term_bytes, np.uint8), group)
-    toff = _gather_var(dist, tt(local.term_off, np.int32), group)
-    post = _gather_var(dist, tt(local.post, np.int32), group)
-    poff = _gather_var(dist, tt(local.post_off, np.int64), group)
-    term_bytes = torch.cat(tb).cpu().numpy()
-    posts = torch.cat(post).cpu().numpy().view(np.uint32)
-    t_parts, p_parts = [np.zeros(1, dtype=np.uint32)], [np.zeros(1, dtype=np.uint64)]
-    tbase, pbase = 0, 0
-    n_terms = 0
-    for to, po in zip(toff, poff):
-        to = to.cpu().numpy().view(np.uint32).astype(np.uint64)
-        po = po.cpu().numpy().view(np.uint64)
-        if len(to) > 1:
-            t_parts.append((to[1:] + tbase).astype(np.uint32))
-            p_parts.append(po[1:] + np.uint64(pbase))
-            n_terms += len(to) - 1
-        tbase += int(to[-1]) if len(to) else 0
-        pbase += int(po[-1]) if len(po) else 0
-    return ReadResult(n_terms, term_bytes, np.concatenate(t_parts), posts, np.concatenate(p_parts))
+
+def gather_read_results(local: ReadResult, device="cpu", group=None, root: int = 0) -> ReadResult:
+    """ii2_read_gather restated: ordered concatenation of every rank's ReadResult on `root`
+    (rank order = term order); the other ranks get an empty result."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    T = local.n_terms
+    mine = torch.tensor([T, len(local.term_bytes), len(local.post), 0], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine, group=group)  # ONE size record per rank
+    sz = np.stack([s.cpu().numpy() for s in sizes])  # [world][4]
+    arrays = [np.asarray(local.term_bytes, dtype=np.uint8), np.asarray(local.term_off[:T], dtype=np.uint32),
+              np.asarray(local.post, dtype=np.uint32), np.asarray(local.post_off[:T], dtype=np.uint64)]
+    per = np.stack([sz[:, 1], sz[:, 0], sz[:, 2], sz[:, 0]], axis=1)
+    got = _exchange(arrays, per, root, group, device)
+    if got is None:
+        return ReadResult(0, np.zeros(0, np.uint8), np.zeros(1, np.uint32), np.zeros(0, np.uint32),
+                          np.zeros(1, np.uint64))
+    tb_base = np.concatenate([[0], np.cumsum(sz[:, 1])]).astype(np.uint64)
+    p_base = np.concatenate([[0], np.cumsum(sz[:, 2])]).astype(np.uint64)
+    toff = np.concatenate([(got[1][r].astype(np.uint64) + tb_base[r]).astype(np.uint32) for r in range(world)]
+                          + [np.array([tb_base[world]], dtype=np.uint32)])
+    poff = np.concatenate([got[3][r] + p_base[r] for r in range(world)]
+                          + [np.array([p_base[world]], dtype=np.uint64)])
+    return ReadResult(int(sz[:, 0].sum()), np.concatenate(got[0]), toff, np.concatenate(got[2]), poff)
 
 
-class ShardedIndex:
-    """One rank's slice of the index: the shards whose key falls in its range."""
-
-    def __init__(self, backend, bounds: np.ndarray, rank: int, device="cpu", group=None):
-        self.local = InvertedIndex(backend)
-        self.bounds, self.rank, self.device, self.group = bounds, rank, device, group
-
-    def _mine(self, term: bytes) -> bool:
-        return owner_of(int(shard_key(term)), self.bounds) == self.rank
-
-    def put(self, terms: list[bytes], val: int) -> None:
-        """Every rank sees the Put; each keeps the terms of its own shards."""
-        mine = [t for t in terms if self._mine(t)]
-        if mine:
-            self.local.put(mine, val)
-
-    def put_batch(self, docs: list[tuple[list[bytes], int]]) -> None:
-        """Batched ingest (ii2_ingest per shard): every rank keeps the terms of its own shards."""
-        mine = [([t for t in terms if self._mine(t)], val) for terms, val in docs]
-        self.local.put_batch([(t, v) for t, v in mine if t])
-
-    def put_removed(self, values) -> None:
-        self.local.put_removed(values)  # tombstones go to every shard (inverted_index.go:41-55)
-
-    def merge(self, req_count: int, m_count: int) -> int:
-        return self.local.merge(req_count, m_count)  # shards are independent: no collective
-
-    def _local_read(self, min_term, max_term) -> ReadResult:
-        items = list(self.local.read(min_term, max_term))
-        from .flat import FlatSegment
-        seg = FlatSegment.from_items(items)
-        return ReadResult(len(items), seg.term_bytes, seg.term_off, seg.post, seg.post_off)
-
-    def read(self, min_term: bytes | None = None, max_term: bytes | None = None) -> ReadResult:
-        """Cross-shard Read: local ordered read, then the NCCL/gloo gather."""
-        return gather_read_results(self._local_read(min_term, max_term), self.device, self.group)
-
-    def prefix_search(self, prefixes: list[bytes]) -> dict[bytes, list[int]]:
-        """Per-rank prefix search, gathered, then the final sort + compact
-        (inverted_index.go:289-292)."""
-        import torch.distributed as dist
-        local = self.local.prefix_search(prefixes)
-        world = dist.get_world_size(self.group)
-        parts = [None] * world
-        dist.all_gather_object(parts, local, group=self.group)
-        out: dict[bytes, list[int]] = {}
-        for p in parts:
-            for k, v in p.items():
-                out.setdefault(k, []).extend(v)
-        return {k: sorted(set(v)) for k, v in out.items()}
+def gather_prefix_results(local: dict, prefixes: list[bytes], device="cpu", group=None, root: int = 0
+                          ) -> dict[bytes, list[int]]:
+    """ii2_prefix_gather restated: per prefix the sorted-unique union of every rank's values on
+    `root` (inverted_index.go:274-292); a prefix is a key iff some rank matched it."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    np_ = len(prefixes)
+    voff = np.zeros(np_ + 1, dtype=np.int64)
+    matched = np.zeros(np_, dtype=np.int64)
+    vals = []
+    for i, p in enumerate(prefixes):
+        v = np.asarray(local.get(p, []), dtype=np.uint32)
+        matched[i] = 1 if p in local else 0
+        vals.append(v)
+        voff[i + 1] = voff[i] + len(v)
+    mine = torch.from_numpy(np.concatenate([voff, matched])).to(device)
+    rows = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine, group=group)  # fixed size: offsets + matched flags of every rank
+    rows = np.stack([r.cpu().numpy() for r in rows])
+    flat = np.concatenate(vals) if vals else np.zeros(0, dtype=np.uint32)
+    got = _exchange([flat.astype(np.uint32)], rows[:, np_:np_ + 1], root, group, device)
+    if got is None:
+        return {}
+    out: dict[bytes, list[int]] = {}
+    for i, p in enumerate(prefixes):
+        if not rows[:, np_ + 1 + i].any():
+            continue
+        parts = [got[0][r][rows[r, i]:rows[r, i + 1]] for r in range(world)]
+        out[p] = np.unique(np.concatenate(parts)).astype(np.int64).tolist()  # slices.Sort + Compact
+    return out

@@ -15,7 +15,7 @@ if [ "$mode" = build ]; then
     cp inverted_index_2_b200/libii2.so scratch/variants/libii2_${tag}.so
     echo "built $tag ($flags)"
   done
-  python -m inverted_index_2_b200.build > /dev/null   # leave the default build in place
+  python -m inverted_index_2_b200.build --force > /dev/null 2>&1  # leave the DEFAULT build in place (forced: the objects are newer than the sources)
 else
   cp inverted_index_2_b200/libii2.so scratch/variants/.default.so
   for so in scratch/variants/libii2_*.so; do

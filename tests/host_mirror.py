@@ -1,4 +1,6 @@
-"""Host-side mirror of the reference's public surface for the hot path.
+"""TEST HARNESS — host-side mirror of the reference's public surface for the hot path (it replays
+the reference's own test sequences against the C-ABI; SURVEY §2 rows 8, 10, 11 are out of scope
+for the product and stay in Go, so this file lives under tests/ and is not shipped).
 
 Same names, argument meaning and error behaviour as the Go API —
 InvertedIndex.{Put, PutRemoved, Merge, Read, PrefixSearch} (inverted_index.go:41,
@@ -23,8 +25,8 @@ from typing import Iterator, Protocol
 
 import numpy as np
 
-from . import _abi as A
-from .flat import FlatSegment, MergeResult, ReadResult
+from inverted_index_2_b200 import _abi as A
+from inverted_index_2_b200.flat import FlatSegment, MergeResult, ReadResult
 
 
 class Backend(Protocol):
@@ -87,14 +89,14 @@ class RemovedLists:
 
     def serialize(self) -> bytes:
         """RemovedLists.Serialize, removed_list.go:73-80 (gob; csrc/removed_gob.cpp)."""
-        from . import fst
+        from inverted_index_2_b200 import fst
         with self.m:
             return fst.removed_list_encode(self.lists)
 
     @classmethod
     def unserialize(cls, data: bytes) -> "RemovedLists":
         """UnserializeRemovedList, removed_list.go:26-33."""
-        from . import fst
+        from inverted_index_2_b200 import fst
         rl = cls()
         rl.lists = fst.removed_list_decode(data)
         return rl
@@ -160,7 +162,7 @@ class Shard:
         self.segments = Segments()
         self.removed_list = RemovedLists()
         if basedir is not None:
-            from . import files
+            from inverted_index_2_b200 import files
             os.makedirs(basedir, exist_ok=True)
             for k in files.list_segments(basedir):  # shard.go:307-331
                 data = files.open_segment(basedir, k)
@@ -183,12 +185,12 @@ class Shard:
 
     def _persist(self, seg: "Segment") -> None:
         if self.basedir is not None:
-            from . import files
+            from inverted_index_2_b200 import files
             files.write_segment(self.basedir, str(seg.key), seg.data)
 
     def _unlink(self, segs: list["Segment"]) -> None:
         if self.basedir is not None:
-            from . import files
+            from inverted_index_2_b200 import files
             for s in segs:
                 files.remove_segment(self.basedir, str(s.key))
 
@@ -288,7 +290,7 @@ class InvertedIndex:
         """basedir: one sub-directory per shard key, each holding that shard's segment files
         (NewInvertedIndex, inverted_index.go:342-378); existing shards are loaded."""
         if backend is None:
-            from .engine import Engine  # the CUDA engine; raises if unavailable
+            from inverted_index_2_b200.engine import Engine  # the CUDA engine; raises if unavailable
             backend = Engine.default()
         self.backend = backend
         self.basedir = basedir

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from inverted_index_2_b200.host import InvertedIndex, Shard
+from host_mirror import InvertedIndex, Shard
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")
 
@@ -82,3 +82,46 @@ def run_shard_scenario(backend, sc):
 
 def run_index_scenario(backend, sc):
     run_steps(InvertedIndex(backend), sc["steps"], True)
+
+
+# ---- spec-derived roaring byte vectors (tests/golden/roaring_vectors.json) -----------------
+def load_roaring_vectors():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "roaring_vectors.json")) as f:
+        return json.load(f)["cases"]
+
+
+def roaring_case_values(case):
+    """The Put() argument of a case, in the order the generator lists it."""
+    import numpy as np
+    spec = case["values"]
+    if "list" in spec:
+        return np.array(spec["list"], dtype=np.uint32)
+    parts = []
+    if "splitmix64" in spec:
+        seed, count, mod = spec["splitmix64"]
+        state, m64 = seed & 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF
+        vals = []
+        for _ in range(count):
+            state = (state + 0x9E3779B97F4A7C15) & m64
+            z = state
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m64
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m64
+            vals.append((z ^ (z >> 31)) % mod)
+        parts.append(np.array(vals, dtype=np.uint32))
+    for key in ("range", "plus_range"):
+        if key in spec:
+            a, b, step = spec[key]
+            parts.append(np.arange(a, b, step, dtype=np.uint32))
+    return np.concatenate(parts)
+
+
+def check_roaring_case(case, data: bytes):
+    import hashlib
+    assert len(data) == case["len"], (case["name"], len(data), case["len"])
+    if "hex" in case:
+        assert data.hex() == case["hex"], case["name"]
+    else:
+        assert data[:64].hex() == case["head_hex"], case["name"]
+    assert hashlib.sha256(data).hexdigest() == case["sha256"], case["name"]

@@ -150,7 +150,7 @@ def test_index_directory_reopen(tmp_path, orc):
     """inverted_index_test.go:140-194: the index written through segment files (one directory
     per shard, `<key>_fst` [+ `<key>_val`]) answers the same after it is reopened; merged
     segments replace their sources on disk (shard.go:232-242)."""
-    from inverted_index_2_b200.host import InvertedIndex
+    from host_mirror import InvertedIndex
     from scenario import OracleBackend
     d = str(tmp_path)
     idx = InvertedIndex(OracleBackend(orc), basedir=d)
@@ -214,7 +214,7 @@ def test_gob_decoder_accepts_named_types_and_other_ids():
 
 
 def test_removed_list_persists_with_the_shard(tmp_path, orc):
-    from inverted_index_2_b200.host import InvertedIndex
+    from host_mirror import InvertedIndex
     from scenario import OracleBackend
     d = str(tmp_path)
     idx = InvertedIndex(OracleBackend(orc), basedir=d)

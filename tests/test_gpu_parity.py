@@ -9,7 +9,8 @@ import pytest
 from inverted_index_2_b200 import _abi as A
 from inverted_index_2_b200 import synth
 from inverted_index_2_b200.flat import FlatSegment
-from scenario import load_vectors, run_index_scenario, run_shard_scenario
+from scenario import (check_roaring_case, load_roaring_vectors, load_vectors, roaring_case_values,
+                      run_index_scenario, run_shard_scenario)
 
 pytestmark = pytest.mark.gpu
 V = load_vectors()
@@ -100,7 +101,7 @@ def test_merge_matches_oracle(engine, orc, case):
     assert np.array_equal(got.post, vals) and np.array_equal(got.post_off, poff)
 
 
-def test_merge_all_segment_modes(engine, orc):
+def test_merge_all_segment_modes(engine, orc, merge_path):
     """DECODED, raw `_val` (file/reader.go:79-100) and direct mode (:73-77) inputs mixed."""
     w = synth.make_workload(5000, 6, 60000, universe=1 << 14, seed=7)
     segs = list(w.segments)
@@ -125,7 +126,7 @@ def test_merged_segment_reads_back(engine, orc):
         assert np.array_equal(rr.term_bytes, got.term_bytes)
 
 
-def test_single_source_passthrough_quirk(engine, orc):
+def test_single_source_passthrough_quirk(engine, orc, merge_path):
     """Survey Q4: a term seen in ONE segment is neither sorted nor deduped
     (file/types.go:14-22 only runs on equal terms); shared terms are."""
     a = FlatSegment.from_items([(b"only_a", [9, 3, 3, 7]), (b"shared", [5, 1, 5])])
@@ -141,7 +142,7 @@ def test_single_source_passthrough_quirk(engine, orc):
     assert got1.as_dict() == {b"only_a": [9, 7], b"shared": [5, 1, 5]}
 
 
-def test_merge_edge_cases(engine, orc):
+def test_merge_edge_cases(engine, orc, merge_path):
     empty = FlatSegment.from_items([])
     one = FlatSegment.from_items([(b"", [4]), (b"a", []), (b"b", [1, 2])])
     two = FlatSegment.from_items([(b"", [4, 5]), (b"a", []), (b"c" * 300, [8])])
@@ -165,7 +166,7 @@ def test_merge_edge_cases(engine, orc):
     assert got.min_term == b"" and got.max_term == b"c" * 300
 
 
-def test_merge_long_and_similar_terms(engine, orc):
+def test_merge_long_and_similar_terms(engine, orc, merge_path):
     """Terms that only differ past the 16-byte key window, 1-byte terms (shard 0000, Q7),
     prefixes of one another, and > 2048 instances sharing one long prefix."""
     rng = np.random.default_rng(5)
@@ -185,7 +186,7 @@ def test_merge_long_and_similar_terms(engine, orc):
     assert_read_equal(engine.read_range(segs, lo, hi), orc.read_range(segs, lo, hi))
 
 
-def test_heavy_terms_multi_cta_union(engine, orc):
+def test_heavy_terms_multi_cta_union(engine, orc, merge_path):
     """Lists far larger than one CTA's shared memory (survey §7 hard part 2): the global
     bitonic path, the bitmap path of long dense unions ("heavy": 350k values below 2^20), heavy
     single-source lists (pass-through, survey Q4) and a long sparse union."""
@@ -262,7 +263,69 @@ def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
     monkeypatch.delenv("II2_MERGE_PARTS", raising=False)
 
 
-def test_union_width_boundaries(engine, orc):
+@pytest.mark.parametrize("bucket,fine", [("64", "4"), ("200", "3"), ("32", "8"), ("1024", "2")])
+def test_merge_with_coalesced_partition(engine, orc, monkeypatch, bucket, fine, merge_path):
+    """Large calls partition the term space finer than needed and join whole fine buckets up to
+    the target size (k1_plan.cu, coalescing); forced on here for a small call.  Unequal segment
+    sizes, a range read and the padding buckets at the end of the table are covered."""
+    monkeypatch.setenv("II2_BUCKET", bucket)
+    monkeypatch.setenv("II2_COALESCE", fine)
+    monkeypatch.setenv("II2_COALESCE_MIN", "4")
+    w = synth.make_workload(40000, 9, 500000, universe=1 << 18, removed_frac=0.07, seed=91,
+                            max_len=200)
+    segs = list(w.segments)
+    segs.append(FlatSegment.from_items([(b"a", [9, 1]), (b"zzzzzzzz", [7])]))      # a tiny segment
+    assert_merge_equal(engine.merge(segs, w.removed, decoded=True), orc.merge(segs, w.removed, decoded=True))
+    lo = synth.term_at(w.term_bytes, w.term_off, 3000)
+    hi = synth.term_at(w.term_bytes, w.term_off, 31000)
+    assert_read_equal(engine.read_range(segs, lo, hi), orc.read_range(segs, lo, hi))
+    for v in ("II2_BUCKET", "II2_COALESCE", "II2_COALESCE_MIN"):
+        monkeypatch.delenv(v, raising=False)
+
+
+def test_merge_pipelined_unaligned_term_bytes(engine, orc, monkeypatch):
+    """A caller's term_bytes may start at any address (a Go sub-slice, an mmap offset): on the
+    copy-engine path every slice lands at the phase of its first offset, so the moved term base
+    stays 4-byte aligned for the key loads (api.cu place())."""
+    w = synth.make_workload(20000, 5, 200000, universe=1 << 16, removed_frac=0.1, seed=77)
+    exp = orc.merge(w.segments, w.removed, decoded=True)
+    odd = []
+    for shift, x in enumerate(w.segments):
+        buf = np.empty(len(x.term_bytes) + 8, dtype=np.uint8)
+        view = buf[1 + (shift % 3):1 + (shift % 3) + len(x.term_bytes)]
+        view[:] = x.term_bytes
+        assert view.ctypes.data % 4 != 0
+        odd.append(FlatSegment(view, x.term_off, x.mode, post=x.post, post_off=x.post_off))
+    for parts in ("1", "3", "6"):
+        monkeypatch.setenv("II2_MERGE_PARTS", parts)
+        assert_merge_equal(engine.merge(odd, w.removed, decoded=True), exp)
+    monkeypatch.delenv("II2_MERGE_PARTS", raising=False)
+
+
+def test_merge_rejects_corrupt_offsets_and_unsorted_removed(engine, monkeypatch):
+    """Raw C-ABI input is checked, not trusted: non-monotone offsets are II2_ERR_INVALID on the
+    pipelined path too (before any size is computed from them), empty segments with NULL arrays
+    are accepted, an unsorted removed list is refused."""
+    from inverted_index_2_b200.engine import EngineError
+    good = FlatSegment.from_items([(b"a%04d" % i, [i, i + 1]) for i in range(200)])
+    bad_toff = good.term_off.copy()
+    bad_toff[50] = bad_toff[120]          # not monotone
+    bad = FlatSegment(good.term_bytes, bad_toff, good.mode, post=good.post, post_off=good.post_off)
+    empty = FlatSegment.from_items([])
+    for parts in ("1", "4"):
+        monkeypatch.setenv("II2_MERGE_PARTS", parts)
+        with pytest.raises(EngineError) as e:
+            engine.merge([good, bad], None, decoded=True)
+        assert e.value.code == A.II2_ERR_INVALID
+        r = engine.merge([good, empty, good], None, decoded=True)
+        assert r.terms_count == 200
+    monkeypatch.delenv("II2_MERGE_PARTS", raising=False)
+    with pytest.raises(EngineError) as e:
+        engine.merge([good], np.array([5, 3, 900000, 7] * 40, dtype=np.uint32), decoded=True)
+    assert e.value.code == A.II2_ERR_INVALID
+
+
+def test_union_width_boundaries(engine, orc, merge_path):
     """Union kernel paths: two terms per warp (< 128 values), one term per warp (128..256),
     multi-CTA (> 256); single-source terms (unsorted, duplicates kept: Q4) paired with
     multi-source ones in the same warp; values needing 5 var-byte bytes and negative deltas."""
@@ -302,7 +365,7 @@ def test_union_width_boundaries(engine, orc):
 
 
 # ---------------------------------------------------------------- range reads vs oracle
-def test_read_range_matches_oracle(engine, orc):
+def test_read_range_matches_oracle(engine, orc, merge_path):
     w = synth.make_workload(20000, 12, 300000, universe=1 << 16, seed=21)
     n = 20000
     t = lambda i: synth.term_at(w.term_bytes, w.term_off, i)
@@ -346,7 +409,7 @@ def test_window_search_boundaries(engine, orc):
     _assert_prefix_equal(engine.prefix_search(segs, prefixes), orc.prefix_search(segs, prefixes))
 
 
-def test_read_keeps_empty_lists(engine, orc):
+def test_read_keeps_empty_lists(engine, orc, merge_path):
     seg = FlatSegment.from_items([(b"t1", [10, 500, 300]), (b"t2", []), (b"t3", [66, 5513])])
     got = engine.read_range([seg])
     assert got.items() == [(b"t1", [10, 500, 300]), (b"t2", []), (b"t3", [66, 5513])]
@@ -421,7 +484,7 @@ def test_merge_through_segment_files(engine, orc, tmp_path):
 
 
 def test_index_on_disk_with_engine(engine, tmp_path):
-    from inverted_index_2_b200.host import InvertedIndex
+    from host_mirror import InvertedIndex
     d = str(tmp_path)
     idx = InvertedIndex(engine, basedir=d)
     idx.put([b"aaaa", b"bbbb"], 1)
@@ -443,7 +506,7 @@ def _random_docs(rng, n_docs, vocab, lo, hi):
     return docs
 
 
-def test_ingest_matches_put_then_merge(engine, orc):
+def test_ingest_matches_put_then_merge(engine, orc, merge_path):
     """ii2_ingest = Put x D + one Merge (oracle chain): unsorted terms, terms repeated inside a
     document, documents sharing terms and values, an empty document, terms that agree on their
     first 16 / 32 bytes, a document far larger than one 2048-record sort tile, removed filter."""
@@ -469,7 +532,7 @@ def test_ingest_matches_put_then_merge(engine, orc):
 
 
 def test_put_batch_on_host_mirror(engine, orc):
-    from inverted_index_2_b200.host import InvertedIndex
+    from host_mirror import InvertedIndex
     from scenario import OracleBackend
     rng = np.random.default_rng(23)
     tb, off = synth.make_terms(500, seed=9)
@@ -484,7 +547,7 @@ def test_put_batch_on_host_mirror(engine, orc):
 
 
 # ---------------------------------------------------------------- device-resident API
-def test_resident_pipeline_and_multipass(engine, orc):
+def test_resident_pipeline_and_multipass(engine, orc, merge_path):
     """Resident segments; a result adopted as a segment and merged again equals the one-pass
     merge (inputs are sorted-unique, so pass structure is invisible)."""
     w = synth.make_workload(8000, 9, 150000, universe=1 << 15, seed=33)
@@ -641,6 +704,17 @@ def test_bitmask_full_chunk_run_container(engine, orc):
         assert np.array_equal(g.get(eg), vals) and np.array_equal(o.get(eg), vals)
 
 
+@pytest.mark.parametrize("case", load_roaring_vectors(), ids=lambda c: c["name"])
+def test_bitmask_bytes_match_roaring_format_spec(engine, case):
+    """K3b's Bitmask.Put bytes against the vectors packed from the public RoaringFormatSpec
+    (tests/golden/make_roaring_vectors.py) — no oracle involved."""
+    bm = engine.bitmask(np.arange(case["dict_n"], dtype=np.uint32))
+    vals = roaring_case_values(case)
+    data = bm.put(vals)
+    check_roaring_case(case, data)
+    assert sorted(set(bm.get(data).tolist())) == sorted(set(vals.tolist()))
+
+
 def test_bitmask_out_of_bound_and_trailing_bytes(engine, orc):
     from inverted_index_2_b200.engine import EngineError
     big = engine.bitmask([5, 6, 7])
@@ -653,3 +727,32 @@ def test_bitmask_out_of_bound_and_trailing_bytes(engine, orc):
     with pytest.raises(EngineError) as e:
         small.get(b"\x00\x01\x02\x03\x04")
     assert e.value.code == A.II2_ERR_CORRUPT
+
+
+# ---------------------------------------------------------------- cross-shard exchange (C-ABI)
+def test_comm_world1_read_and_prefix_gather(engine, orc):
+    """ii2_comm_init / ii2_read_gather / ii2_prefix_gather with a world of one rank: the gathered
+    read is the local read (offsets rebased by 0) and the prefix union is the local one."""
+    w = synth.make_workload(5000, 6, 60000, universe=1 << 16, seed=12)
+    dsegs = [engine.upload(s) for s in w.segments]
+    lo = synth.term_at(w.term_bytes, w.term_off, 100)
+    hi = synth.term_at(w.term_bytes, w.term_off, 4000)
+    engine.comm_init(engine.comm_unique_id(), 0, 1)
+    try:
+        assert engine.comm_info() == (0, 1)
+        r = engine.read_range_dev(dsegs, lo, hi, None)
+        g = engine.read_gather(r, 0)
+        assert_read_equal(g.download_read(), orc.read_range(w.segments, lo, hi))
+        g2 = engine.read_gather(r, -1)      # every rank receives
+        assert_read_equal(g2.download_read(), r.download_read())
+        empty = engine.read_range_dev(dsegs, b"~~~~", None, None)   # nothing in range
+        ge = engine.read_gather(empty, 0).download_read()
+        assert ge.n_terms == 0 and ge.term_off.tolist() == [0] and ge.post_off.tolist() == [0]
+        pref = [b"", lo[:2], hi[:3], b"zzzz", lo[:1]]
+        got = engine.prefix_search_gather(dsegs, pref, 0)
+        exp = orc.prefix_search(w.segments, pref)
+        assert sorted(got) == sorted(exp)
+        assert all([int(x) for x in got[k]] == exp[k] for k in exp)
+    finally:
+        engine.comm_shutdown()
+    assert engine.comm_info() == (0, 0)

@@ -5,8 +5,9 @@ import pytest
 
 from inverted_index_2_b200 import _abi as A
 from inverted_index_2_b200.flat import FlatSegment
-from inverted_index_2_b200.host import RemovedLists, shard_key
-from scenario import OracleBackend, load_vectors, run_index_scenario, run_shard_scenario
+from host_mirror import RemovedLists, shard_key
+from scenario import (OracleBackend, check_roaring_case, load_roaring_vectors, load_vectors,
+                      roaring_case_values, run_index_scenario, run_shard_scenario)
 
 V = load_vectors()
 
@@ -42,6 +43,19 @@ def test_bitmask(orc, b):
     assert bm.get(enc[1]).tolist() == b["get_second_index_order"]
     assert sorted(bm.get(enc[1]).tolist()) == b["get_second_sorted"]
     assert bm.all_values().tolist() == b["all_values"]
+
+
+@pytest.mark.parametrize("case", load_roaring_vectors(), ids=lambda c: c["name"])
+def test_bitmask_bytes_match_roaring_format_spec(orc, case):
+    """Bitmask.Put bytes (file/bitmask.go:53-59) against vectors packed straight from the public
+    RoaringFormatSpec (tests/golden/make_roaring_vectors.py): array / bitmap / run containers,
+    both cookies, with and without the offset header.  Spec-derived, not Go-produced: the
+    container-type rules of roaring's Add() stay restated."""
+    bm = orc.Bitmask(np.arange(case["dict_n"], dtype=np.uint32))
+    vals = roaring_case_values(case)
+    data = bm.put(vals, fast=True)
+    check_roaring_case(case, data)
+    assert sorted(set(bm.get(data).tolist())) == sorted(set(vals.tolist()))
 
 
 def test_bitmask_out_of_bound(orc):

@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from inverted_index_2_b200 import sharded
-from inverted_index_2_b200.host import InvertedIndex, shard_key
+from host_mirror import InvertedIndex, shard_key
+from sharded_harness import ShardedIndex
 
 
 def _free_port():
@@ -48,7 +49,7 @@ def _worker(rank, world, port, q):
         for t in terms:
             weights[int(shard_key(t))] += 1
     bounds = sharded.partition_shard_keys(weights, world)
-    idx = sharded.ShardedIndex(OracleBackend(orc), bounds, rank)
+    idx = ShardedIndex(OracleBackend(orc), bounds, rank)
     for terms, val in docs:
         idx.put(terms, val)
     idx.put_removed([3, 7])
@@ -57,7 +58,7 @@ def _worker(rank, world, port, q):
     lo, hi = vocab[50], vocab[300]
     part = idx.read(lo, hi)
     pref = idx.prefix_search([b"a", b"te", b"Zz"])
-    batched = sharded.ShardedIndex(OracleBackend(orc), bounds, rank)
+    batched = ShardedIndex(OracleBackend(orc), bounds, rank)
     batched.put_batch(docs)  # one ingest call per shard instead of one Put per document
     full_b = batched.read(None, None)
     if rank == 0:
