@@ -568,7 +568,7 @@ def run_ours(a):
     pipe["frac_of_peak"] = pipe["achieved_gbs"] / peak
 
     # ---- end to end through the host-buffer C-ABI call (rank-local, same workload) ----
-    e2e = None
+    e2e = e2e_decoded = None
     if not a.no_e2e:
         keep, hsegs = [], []
         for s in w.segments:
@@ -597,21 +597,53 @@ def run_ours(a):
             eng.lib.ii2_merge_out_free(C.byref(out))
             return d2h
         e_steps = max(1, min(a.steps, 5))
-        for _ in range(2):
-            d2h = e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_in * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / e_steps,
-               "steps": e_steps, "api": "ii2_merge (host buffers, pinned)"}
+
+        def time_e2e(step_fn):
+            for _ in range(2):
+                d2h_ = step_fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                step_fn()
+            torch.cuda.synchronize()
+            dt_ = time.perf_counter() - t0
+            if world > 1:
+                t_ = torch.tensor([dt_], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                dt_ = float(t_.item())
+            return dt_, d2h_
+        dt, d2h = time_e2e(e2e_step)
+        e2e_dec = {"value": total_in * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / e_steps,
+                   "steps": e_steps, "api": "ii2_merge, II2_SEG_DECODED views (pinned decoded lists)"}
+        # the call a Go host makes (INTEGRATION.md seam 1): `_val` views — the mmap of <key>_val
+        # and the FST outputs of every term (file/reader.go:50-52,79-100), here as 32-bit word
+        # offsets — staged per term range, decoded on the device, merged, new segment back
+        vsegs = []
+        for s_, hs in zip(w.segments, hsegs):
+            words, woff = eng.intcomp_encode_batch(s_.post, s_.post_off)
+            vb, k1 = pin(words.view(np.uint8))
+            vo, k2 = pin(woff[:-1].astype(np.uint32))
+            keep += [k1, k2]
+            vsegs.append(FlatSegment(hs.term_bytes, hs.term_off, A.II2_SEG_VAL, val_bytes=vb,
+                                     val_size=int(woff[-1]) * 4, val_woff32=vo))
+        h2d_v = sum(x.term_bytes.nbytes + x.term_off.nbytes + x.val_bytes.nbytes + x.val_woff32.nbytes
+                    for x in vsegs) + hrem.nbytes
+        varr = views_array(vsegs)
+
+        def e2e_val_step():
+            eng._check(eng.lib.ii2_merge(varr, len(vsegs), A.np_ptr(hrem, A.u32p), len(hrem), 0,
+                                         C.byref(out)), "merge")
+            d2h_ = (int(out.val_size) + 8 * int(out.terms_count) + 4 * (int(out.terms_count) + 1) +
+                    int(out.term_off[int(out.terms_count)]))
+            eng.lib.ii2_merge_out_free(C.byref(out))
+            return d2h_
+        dtv, d2hv = time_e2e(e2e_val_step)
+        e2e = {"value": total_in * e_steps / dtv, "unit": UNIT, "h2d_bytes_per_step": int(h2d_v),
+               "d2h_bytes_per_step": int(d2hv), "ms_per_step": 1e3 * dtv / e_steps, "steps": e_steps,
+               "api": "ii2_merge, II2_SEG_VAL views (pinned `_val` bytes + 32-bit FST word offsets): "
+                      "H2D + device decode + merge + D2H of the new segment"}
+        e2e_decoded = e2e_dec
 
     # ---- N > 1: the exchange behind the C-ABI, the strong-scaling leg, the cross-shard read ----
     xread = strong = None
@@ -653,6 +685,7 @@ def run_ours(a):
                        "postings_in": n_in, "postings_out": n_out, "terms_out": t_out,
                        "term_instances": t_in},
             "roofline": roof, "pipeline": pipe, "cpu_baseline": cpu, "e2e": e2e,
+            "e2e_decoded": e2e_decoded,
             "gpu_launches": int(launches), "clocks": clk,
             "kernels": prof,
         }

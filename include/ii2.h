@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define II2_ABI_VERSION 1
+#define II2_ABI_VERSION 2
 
 /* ---- error codes -------------------------------------------------------- */
 #define II2_OK 0
@@ -76,6 +76,10 @@ typedef struct ii2_seg_view {
   const uint8_t* val_bytes;
   const uint64_t* val_off; /* n_terms */
   uint64_t val_size;
+  /* II2_SEG_VAL only, optional (ABI version 2): the same FST outputs as 32-bit WORD offsets
+   * (val_off[i] / 4) for `_val` files below 16 GiB; when non-NULL it is used instead of
+   * val_off (which may then be NULL) and halves the offset bytes that cross the bus. */
+  const uint32_t* val_woff32; /* n_terms */
 } ii2_seg_view;
 
 /* ---- lifecycle ---------------------------------------------------------- */

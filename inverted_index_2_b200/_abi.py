@@ -43,6 +43,7 @@ class SegView(C.Structure):
         ("val_bytes", u8p),
         ("val_off", u64p),
         ("val_size", C.c_uint64),
+        ("val_woff32", u32p),
     ]
 
 

@@ -50,6 +50,11 @@ k_rebase_u32(uint32_t* __restrict__ off, uint64_t n, uint32_t first) {
   if (i < n) off[i] -= first;
 }
 __global__ void __launch_bounds__(256)
+k_woff32_to_bytes(const uint32_t* __restrict__ w, uint64_t n, uint64_t* __restrict__ b) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = 4ull * w[i];
+}
+__global__ void __launch_bounds__(256)
 k_rebase_u64(uint64_t* __restrict__ off, uint64_t n, uint64_t first) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) off[i] -= first;
@@ -71,8 +76,57 @@ k_slices_check(const SliceRef* __restrict__ sl, uint32_t* __restrict__ stats) {
     const uint32_t a = f.toff[i], b = f.toff[i + 1];
     if (b < a) atomicExch(&stats[1], 1u);
     else atomicMax(&stats[0], b - a);
-    if (f.poff[i + 1] < f.poff[i]) atomicExch(&stats[1], 1u);
+    if (f.poff && f.poff[i + 1] < f.poff[i]) atomicExch(&stats[1], 1u);
   }
+}
+
+// `_val` slices of one range of the pipelined ii2_merge (II2_SEG_VAL views): every slice was
+// staged at the phase of its source; the decoder wants one array of words with list i at
+// [woff[i], woff[i+1]), so the slices are moved back to back (grid.y = slice) ...
+struct ValSlice {
+  const uint32_t* src;   // staged words of the slice
+  const void* off;       // staged FST outputs of its terms: u64 byte offsets or u32 word offsets
+  uint64_t first;        // output of the slice's first term, in BYTES
+  uint64_t words;        // words of the slice
+  uint64_t wbase;        // first word of the slice in the compact array
+  uint64_t tbase;        // first list of the slice among the range's `_val` lists
+  uint32_t n;            // terms of the slice
+  uint32_t off32;        // offsets are u32 word offsets
+};
+__global__ void __launch_bounds__(256)
+k_val_compact(const ValSlice* __restrict__ sl, uint32_t* __restrict__ dst) {
+  const ValSlice f = sl[blockIdx.y];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < f.words;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    dst[f.wbase + i] = f.src[i];
+}
+// ... and every term's FST output (file/reader.go:50-52: a run ends where the next one starts,
+// the last one at the end of the slice) becomes a word offset into the compact array.
+// stats[1] = 1 on an offset that is not 4-byte aligned, not monotone or past the slice.
+__global__ void __launch_bounds__(256)
+k_val_woff(const ValSlice* __restrict__ sl, uint32_t nslices, uint64_t* __restrict__ woff,
+           uint32_t* __restrict__ stats) {
+  const ValSlice f = sl[blockIdx.y];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < f.n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t b, nb;  // bytes from the start of the segment's `_val`
+    if (f.off32) {
+      const uint32_t* o = static_cast<const uint32_t*>(f.off);
+      b = 4ull * o[i];
+      nb = i + 1 < f.n ? 4ull * o[i + 1] : f.first + 4ull * f.words;
+    } else {
+      const uint64_t* o = static_cast<const uint64_t*>(f.off);
+      b = o[i];
+      nb = i + 1 < f.n ? o[i + 1] : f.first + 4ull * f.words;
+    }
+    if ((b & 3u) || b < f.first || nb < b || nb > f.first + 4ull * f.words) {
+      atomicExch(&stats[1], 1u);
+      b = f.first;
+    }
+    woff[f.tbase + i] = f.wbase + ((b - f.first) >> 2);
+  }
+  if (blockIdx.y + 1 == nslices && blockIdx.x == 0 && threadIdx.x == 0)
+    woff[f.tbase + f.n] = f.wbase + f.words;  // terminal entry: the slices are back to back
 }
 
 // Staging kernel of the pipelined ii2_merge: gathers many host arrays (pinned, mapped into the
@@ -500,9 +554,9 @@ static int seg_upload_impl(const ii2_seg_view* v, cudaStream_t s, uint32_t* d_st
     II2_LAUNCHED();
     g->n_post = n;
   } else if (v->mode == II2_SEG_VAL) {
-    if (n && !v->val_off) return II2_ERR_INVALID;
+    if (n && !v->val_off && !v->val_woff32) return II2_ERR_INVALID;
     if (v->val_size && !v->val_bytes) return II2_ERR_INVALID;
-    const uint64_t vfirst = n ? v->val_off[0] : 0;
+    const uint64_t vfirst = !n ? 0 : (v->val_woff32 ? 4ull * v->val_woff32[0] : v->val_off[0]);
     if (vfirst > v->val_size) return II2_ERR_INVALID;
     const uint64_t vsize = v->val_size - vfirst;
     if ((vsize & 3) || (vfirst & 3)) {
@@ -512,8 +566,15 @@ static int seg_upload_impl(const ii2_seg_view* v, cudaStream_t s, uint32_t* d_st
     DevBuf<uint64_t> d_vo, d_woff;
     DevBuf<uint32_t> d_words;
     II2_TRY(d_vo.alloc_scratch((size_t)n, s));
-    if (n)
+    if (n && v->val_woff32) {  // 32-bit word offsets -> byte offsets
+      DevBuf<uint32_t> d_w32;
+      II2_TRY(d_w32.alloc_scratch((size_t)n, s));
+      II2_CUDA_TRY(cudaMemcpyAsync(d_w32.p, v->val_woff32, n * 4, cudaMemcpyHostToDevice, s));
+      k_woff32_to_bytes<<<div_up(n, 256), 256, 0, s>>>(d_w32.p, n, d_vo.p);
+      II2_LAUNCHED();
+    } else if (n) {
       II2_CUDA_TRY(cudaMemcpyAsync(d_vo.p, v->val_off, n * 8, cudaMemcpyHostToDevice, s));
+    }
     if (n && vfirst) {
       k_rebase_u64<<<div_up(n, 256), 256, 0, s>>>(d_vo.p, n, vfirst);
       II2_LAUNCHED();
@@ -943,6 +1004,15 @@ struct SegList {
   DevBuf<uint64_t> blk_poff;
   DevBuf<SliceRef> blk_ref;
   DevBuf<GatherJob> blk_job;
+  // II2_SEG_VAL views: staged `_val` slices and FST outputs, the compact words + word offsets,
+  // and the decoded lists of all `_val` segments of the range (shared by their views)
+  DevBuf<uint32_t> blk_val, val_words, post_dec;
+  DevBuf<uint8_t> blk_voff;
+  DevBuf<uint64_t> val_woff, poff_dec;
+  DevBuf<ValSlice> blk_vs;
+  uint64_t n_val_lists = 0, n_val_words = 0;
+  std::vector<int> val_segs;        // which views are `_val` views
+  std::vector<uint64_t> val_tbase;  // their first list
   ~SegList() {
     for (ii2_seg* g : v) delete g;
   }
@@ -1069,8 +1139,14 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
   struct DevAlias {
     const uint8_t* tb;
     const uint8_t* toff;
-    const uint8_t* post;
-    const uint8_t* poff;
+    const uint8_t* post;  // DECODED: postings; `_val` view: the `_val` bytes
+    const uint8_t* poff;  // DECODED: posting offsets; `_val` view: the FST outputs
+  };
+  auto is_val = [&](int i) { return segs[i].mode == II2_SEG_VAL; };
+  // FST output of term t of a `_val` view in bytes (t == n_terms: the end of the file)
+  auto val_at = [&](const ii2_seg_view& v, uint64_t t) -> uint64_t {
+    if (t >= v.n_terms) return v.val_size;
+    return v.val_woff32 ? 4ull * v.val_woff32[t] : v.val_off[t];
   };
   std::vector<DevAlias> alias(nseg);
   // II2_MERGE_UPLOAD picks how the slices cross the bus (tuning; results are the same):
@@ -1114,8 +1190,16 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
   for (int i = 0; i < nseg && gather; i++) {
     dev_alias(segs[i].term_bytes, 4, &alias[i].tb);
     dev_alias(segs[i].term_off, 4, &alias[i].toff);
-    dev_alias(segs[i].post, 4, &alias[i].post);
-    dev_alias(segs[i].post_off, 8, &alias[i].poff);
+    if (is_val(i)) {
+      dev_alias(segs[i].val_bytes, 4, &alias[i].post);
+      if (segs[i].val_woff32)
+        dev_alias(segs[i].val_woff32, 4, &alias[i].poff);
+      else
+        dev_alias(segs[i].val_off, 8, &alias[i].poff);
+    } else {
+      dev_alias(segs[i].post, 4, &alias[i].post);
+      dev_alias(segs[i].post_off, 8, &alias[i].poff);
+    }
   }
 
   if (!gather) dma_large = false;  // hybrid needs the device aliases of the offset arrays
@@ -1141,30 +1225,57 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     ~PinGuard() { pinned_free(p); }
   } tab_guard{h_tab};
   if (!h_tab) return II2_ERR_NOMEM;
+  uint8_t* h_vtab = static_cast<uint8_t*>(pinned_alloc(sizeof(ValSlice) * nx * P + 64));
+  PinGuard vtab_guard{h_vtab};
+  if (!h_vtab) return II2_ERR_NOMEM;
   auto enqueue_upload = [&](int p) -> int {
     parts[p].reset(new SegList());
     SegList& L = *parts[p];
     const uint64_t* lo = &bounds[(size_t)p * nseg];
     const uint64_t* hi = &bounds[(size_t)(p + 1) * nseg];
-    size_t tb_bytes = 0, toff_bytes = 0, post_bytes = 0, poff_bytes = 0;
+    size_t tb_bytes = 0, toff_bytes = 0, post_bytes = 0, poff_bytes = 0, val_bytes = 0, voff_bytes = 0;
+    uint64_t val_lists = 0, val_words = 0;
+    int n_val = 0;
     for (int i = 0; i < nseg; i++) {
       const ii2_seg_view& v = segs[i];
       // corrupt offsets are II2_ERR_INVALID, like on the single-shot path, before any size is
       // computed from a wrapped difference
-      if (hi[i] < lo[i] || v.term_off[hi[i]] < v.term_off[lo[i]] || v.post_off[hi[i]] < v.post_off[lo[i]])
-        return II2_ERR_INVALID;
+      if (hi[i] < lo[i] || v.term_off[hi[i]] < v.term_off[lo[i]]) return II2_ERR_INVALID;
       const size_t n1 = (size_t)(hi[i] - lo[i]) + 1;
       // every slice: up to 2 x 511 bytes of phase (placed at its source's phase modulo 512)
       tb_bytes += (size_t)(v.term_off[hi[i]] - v.term_off[lo[i]]) + 2 * kGatherAlign + 64;  // + tail padding
       toff_bytes += n1 * 4 + 2 * kGatherAlign;
-      post_bytes += (size_t)(v.post_off[hi[i]] - v.post_off[lo[i]]) * 4 + 2 * kGatherAlign;
-      poff_bytes += n1 * 8 + 2 * kGatherAlign;
+      if (is_val(i)) {
+        const uint64_t b0 = val_at(v, lo[i]), b1 = val_at(v, hi[i]);
+        if (b1 < b0 || b1 > v.val_size || ((b0 | b1) & 3)) return II2_ERR_INVALID;
+        val_bytes += (size_t)(b1 - b0) + 2 * kGatherAlign;
+        voff_bytes += n1 * 8 + 2 * kGatherAlign;
+        val_lists += hi[i] - lo[i];
+        val_words += (b1 - b0) / 4;
+        n_val++;
+      } else {
+        if (v.post_off[hi[i]] < v.post_off[lo[i]]) return II2_ERR_INVALID;
+        post_bytes += (size_t)(v.post_off[hi[i]] - v.post_off[lo[i]]) * 4 + 2 * kGatherAlign;
+        poff_bytes += n1 * 8 + 2 * kGatherAlign;
+      }
     }
     II2_TRY(L.blk_tb.alloc(tb_bytes, sA, 64));
     II2_TRY(L.blk_toff.alloc(toff_bytes / 4, sA));
     II2_TRY(L.blk_post.alloc(post_bytes / 4, sA, 16));
     II2_TRY(L.blk_poff.alloc(poff_bytes / 8, sA));
     II2_TRY(L.blk_ref.alloc(nx, sA));
+    L.n_val_lists = val_lists;
+    L.n_val_words = val_words;
+    std::vector<ValSlice> h_vs;
+    if (n_val) {
+      II2_TRY(L.blk_val.alloc(val_bytes / 4, sA, 16));
+      II2_TRY(L.blk_voff.alloc(voff_bytes, sA, 16));
+      II2_TRY(L.val_words.alloc(val_words, sA, 64));
+      II2_TRY(L.val_woff.alloc(val_lists + 1, sA));
+      II2_TRY(L.blk_vs.alloc(n_val, sA));
+    }
+    size_t at_val = 0, at_voff = 0;
+    uint64_t run_lists = 0, run_words = 0;
     if (gather) II2_TRY(L.blk_job.alloc(4 * nx, sA));
     if (dma_streams) {  // the blocks are stream-ordered allocations of sA
       II2_CUDA_TRY(cudaEventRecord(fork_join.v[0], sA));
@@ -1213,34 +1324,63 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
       const uint64_t n = hi[i] - lo[i];
       const uint32_t tfirst = v.term_off[lo[i]];
       const uint64_t tlen = v.term_off[hi[i]] - tfirst;
-      const uint64_t pfirst = v.post_off[lo[i]], plen = v.post_off[hi[i]] - pfirst;
-      if (v.term_off[hi[i]] < tfirst || v.post_off[hi[i]] < pfirst) return II2_ERR_INVALID;
-      if ((tlen && !v.term_bytes) || (plen && !v.post)) return II2_ERR_INVALID;
-      uint8_t *d_tb, *d_toff, *d_post, *d_poff;
+      if (tlen && !v.term_bytes) return II2_ERR_INVALID;
+      uint8_t *d_tb, *d_toff, *d_post = nullptr, *d_poff = nullptr;
       II2_TRY(place(L.blk_tb.p, at_tb, v.term_bytes ? v.term_bytes + tfirst : nullptr,
                     alias[i].tb ? alias[i].tb + tfirst : nullptr, tlen, tfirst, true, &d_tb));
       at_tb += 32;  // key loads read past the last term
       II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_toff.p), at_toff, v.term_off + lo[i],
                     alias[i].toff + 4 * lo[i], (n + 1) * 4, 4 * lo[i], false, &d_toff));
-      II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_post.p), at_post, v.post ? v.post + pfirst : nullptr,
-                    alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, 4 * pfirst, true, &d_post));
-      II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_poff.p), at_poff, v.post_off + lo[i],
-                    alias[i].poff + 8 * lo[i], (n + 1) * 8, 8 * lo[i], false, &d_poff));
       std::unique_ptr<ii2_seg> g(new ii2_seg());
       g->n_terms = (uint32_t)n;
-      g->n_post = plen;
       g->term_bytes_len = tlen;
       // non-owning views into the blocks (scratch = true: never freed through the view)
       g->tb.p = d_tb - tfirst;
       g->tb.scratch = true;
       g->toff.p = reinterpret_cast<uint32_t*>(d_toff);
       g->toff.scratch = true;
-      g->post.p = reinterpret_cast<uint32_t*>(d_post) - pfirst;
       g->post.scratch = true;
-      g->poff.p = reinterpret_cast<uint64_t*>(d_poff);
       g->poff.scratch = true;
+      if (is_val(i)) {
+        // the `_val` run of the slice and the FST outputs of its terms; post / poff of the view
+        // are filled in once the range has been decoded (finish_val)
+        const uint64_t b0 = val_at(v, lo[i]), b1 = val_at(v, hi[i]);
+        uint8_t *d_val, *d_vo;
+        II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_val.p), at_val, v.val_bytes + b0,
+                      alias[i].post ? alias[i].post + b0 : nullptr, b1 - b0, b0, true, &d_val));
+        const bool w32 = v.val_woff32 != nullptr;
+        const size_t esz = w32 ? 4 : 8;
+        II2_TRY(place(L.blk_voff.p, at_voff,
+                      w32 ? static_cast<const void*>(v.val_woff32 + lo[i]) : static_cast<const void*>(v.val_off + lo[i]),
+                      alias[i].poff ? alias[i].poff + esz * lo[i] : nullptr, n * esz, esz * lo[i], false, &d_vo));
+        ValSlice vs;
+        vs.src = reinterpret_cast<const uint32_t*>(d_val);
+        vs.off = d_vo;
+        vs.first = b0;
+        vs.words = (b1 - b0) / 4;
+        vs.wbase = run_words;
+        vs.tbase = run_lists;
+        vs.n = (uint32_t)n;
+        vs.off32 = w32 ? 1u : 0u;
+        h_vs.push_back(vs);
+        L.val_segs.push_back(i);
+        L.val_tbase.push_back(run_lists);
+        run_words += vs.words;
+        run_lists += n;
+        g->n_post = 0;
+      } else {
+        const uint64_t pfirst = v.post_off[lo[i]], plen = v.post_off[hi[i]] - pfirst;
+        if (plen && !v.post) return II2_ERR_INVALID;
+        II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_post.p), at_post, v.post ? v.post + pfirst : nullptr,
+                      alias[i].post ? alias[i].post + 4 * pfirst : nullptr, plen * 4, 4 * pfirst, true, &d_post));
+        II2_TRY(place(reinterpret_cast<uint8_t*>(L.blk_poff.p), at_poff, v.post_off + lo[i],
+                      alias[i].poff + 8 * lo[i], (n + 1) * 8, 8 * lo[i], false, &d_poff));
+        g->n_post = plen;
+        g->post.p = reinterpret_cast<uint32_t*>(d_post) - pfirst;
+        g->poff.p = reinterpret_cast<uint64_t*>(d_poff);
+      }
       refs[i].toff = g->toff.p;
-      refs[i].poff = g->poff.p;
+      refs[i].poff = g->poff.p;  // null for a `_val` view: its posting offsets come from the decoder
       refs[i].n = (uint32_t)n;
       refs[i].pad = 0;
       max_n = std::max<uint32_t>(max_n, (uint32_t)n);
@@ -1264,6 +1404,25 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     if (max_n) {
       const dim3 grid(std::min<unsigned>(div_up(max_n, 256), 64u), (unsigned)nseg);
       k_slices_check<<<grid, 256, 0, sA>>>(L.blk_ref.p, d_stats.p + 2 * p);
+      II2_LAUNCHED();
+    }
+    if (!h_vs.empty()) {  // `_val` slices back to back + the word offset of every list
+      ValSlice* h_tab_vs = reinterpret_cast<ValSlice*>(h_vtab + (size_t)p * nx * sizeof(ValSlice));
+      memcpy(h_tab_vs, h_vs.data(), h_vs.size() * sizeof(ValSlice));
+      II2_TRY(small_copy(L.blk_vs.p, h_tab_vs, h_vs.size() * sizeof(ValSlice), sA));
+      uint64_t max_w = 0;
+      uint32_t max_t = 0;
+      for (const ValSlice& x : h_vs) {
+        max_w = std::max(max_w, x.words);
+        max_t = std::max(max_t, x.n);
+      }
+      const unsigned ns = (unsigned)h_vs.size();
+      if (max_w) {
+        k_val_compact<<<dim3(std::min<unsigned>(div_up(max_w, 256), 256u), ns), 256, 0, sA>>>(L.blk_vs.p, L.val_words.p);
+        II2_LAUNCHED();
+      }
+      k_val_woff<<<dim3(std::max(1u, std::min<unsigned>(div_up(max_t, 256), 64u)), ns), 256, 0, sA>>>(
+          L.blk_vs.p, ns, L.val_woff.p, d_stats.p + 2 * p);
       II2_LAUNCHED();
     }
     II2_CUDA_TRY(cudaEventRecord(ev.v[p], sA));
@@ -1341,6 +1500,20 @@ static int merge_pipelined(const ii2_seg_view* segs, int nseg, const uint32_t* r
     {
       ProfScope sc("e2e_wait_upload", sB);
       II2_TRY(seg_check_result(d_stats.p + 2 * p, sB));
+    }
+    if (parts[p]->n_val_lists) {  // the `_val` views of the range: one batched decode (K3a)
+      SegList& L = *parts[p];
+      ProfScope sc("e2e_val_decode", sB);
+      uint64_t total = 0;
+      II2_TRY(intcomp_decode_dev(L.val_words.p, L.val_woff.p, L.n_val_lists, L.post_dec, L.poff_dec,
+                                 &total, sB, false));
+      arena_reset(sB);  // (the decoder's temporaries; its outputs are stream-ordered allocations)
+      for (size_t j = 0; j < L.val_segs.size(); j++) {
+        ii2_seg* g = L.v[L.val_segs[j]];
+        g->post.p = L.post_dec.p;                       // offsets index the shared decoded array
+        g->poff.p = L.poff_dec.p + L.val_tbase[j];
+        g->n_post = j == 0 ? total : 0;                 // (only the sum over the views is used)
+      }
     }
     ii2_result* res = nullptr;
     II2_TRY(run_pipeline(parts[p]->v.data(), nseg, nullptr, 0, false, nullptr, 0, false, rem,
@@ -1427,19 +1600,25 @@ int ii2_merge(const ii2_seg_view* segs, int nseg, const uint32_t* removed_sorted
   II2_TRY(ctx_require());
   // term-range pipelining pays once staging dominates: DECODED views (no per-segment host
   // synchronisation), at least ~200 MB per range
+  // (DECODED views and `_val` views — what a Go caller holds: the mmap of <key>_val and the FST
+  // outputs, file/reader.go:50-52,79-100 — are staged per term range; DIRECT views are tiny)
   uint64_t bytes = 0;
   bool all_decoded = nseg > 0;
   for (int i = 0; i < nseg; i++) {
     const ii2_seg_view& v = segs[i];
     // (an empty segment may come with NULL arrays: the pipelined path indexes them, the
     // single-shot path does not)
-    if (v.mode != II2_SEG_DECODED || !v.term_off || !v.post_off) {
+    const bool dec = v.mode == II2_SEG_DECODED && v.term_off && v.post_off;
+    const bool val = v.mode == II2_SEG_VAL && v.term_off && (v.val_off || v.val_woff32) && v.n_terms &&
+                     !(v.val_size & 3) && (v.val_size || !v.n_terms) && v.val_bytes;
+    if (!dec && !val) {
       all_decoded = false;
       break;
     }
     if (v.n_terms)
-      bytes += (uint64_t)(v.term_off[v.n_terms] - v.term_off[0]) + 12ull * v.n_terms +
-               4ull * (v.post_off[v.n_terms] - v.post_off[0]);
+      bytes += (uint64_t)(v.term_off[v.n_terms] - v.term_off[0]) + 4ull * v.n_terms +
+               (dec ? 8ull * v.n_terms + 4ull * (v.post_off[v.n_terms] - v.post_off[0])
+                    : (v.val_woff32 ? 4ull : 8ull) * v.n_terms + v.val_size);
   }
   // II2_MERGE_PARTS=<n> forces the number of ranges (tests and tuning; 1 = single shot)
   const char* env_parts = getenv("II2_MERGE_PARTS");

@@ -442,12 +442,15 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   }();
   if (small_bucket && want < small_want && N / small_bucket > want)
     want = std::min<uint64_t>(small_want, N / small_bucket);
-  // large calls: a partition `fine` times finer, coalesced afterwards (II2_COALESCE=<fine>, 1 = off)
+  // II2_COALESCE=<fine> (default 1 = off): a partition `fine` times finer, coalesced afterwards.
+  // Measured on B200 (C2, profiles/r02_experiments.md): fine = 4 takes the buckets above 1024
+  // instances from 9.6 % to 2 %, but the finer partition costs +0.5 ms of plan time (0.38 ->
+  // 0.88 ms) for 0.3 ms saved in the bucket kernels: off by default, kept for skewed inputs.
   // (II2_COALESCE_MIN=<buckets>: calls cut into fewer buckets keep the plain partition)
   const uint32_t coalesce = [] {
     const char* e = getenv("II2_COALESCE");
-    const long v = e ? atol(e) : 4;
-    return (v >= 1 && v <= 16) ? (uint32_t)v : 4u;
+    const long v = e ? atol(e) : 1;
+    return (v >= 1 && v <= 16) ? (uint32_t)v : 1u;
   }();
   const uint64_t coalesce_min = [] {
     const char* e = getenv("II2_COALESCE_MIN");

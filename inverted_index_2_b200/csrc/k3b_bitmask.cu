@@ -30,6 +30,13 @@ struct ii2_bitmask {
   uint64_t values_cap = 0;
   DevBuf<unsigned long long> table;
   uint64_t table_cap = 0;  // slots, power of two
+  // Direct-address inverse of the dictionary, inv[v] = FIRST index of value v (0xFFFFFFFF: not
+  // in the dictionary), kept while the largest value is at most a few times the dictionary
+  // length (a universe of document ids, file/bitmask_test.go:15-21): a Put whose values are all
+  // in the dictionary is then ONE probe per value instead of four passes of hash probes.
+  DevBuf<uint32_t> inv;
+  uint64_t inv_len = 0;    // maxv + 1, 0 = no inverse
+  uint64_t inv_for_n = 0;  // dictionary length the inverse was built for
 };
 
 namespace {
@@ -129,6 +136,36 @@ k_bm_put_fixup(unsigned long long* t, uint64_t mask, const uint32_t* __restrict_
   const uint64_t h = tbl_slot(t, mask, v);
   if ((uint32_t)t[h] == D + (uint32_t)i)
     t[h] = ((unsigned long long)v << 32) | (D + (uint32_t)rank[i]);
+}
+
+// ---- direct-address inverse -------------------------------------------------------------------
+__global__ void __launch_bounds__(BM_THREADS)
+k_bm_max(const uint32_t* __restrict__ values, uint64_t n, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    m = max(m, values[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if (lane_id() == 0 && m) atomicMax(out, m);
+}
+__global__ void __launch_bounds__(BM_THREADS)
+k_bm_inv_build(const uint32_t* __restrict__ values, uint64_t n, uint32_t* __restrict__ inv) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(&inv[values[i]], (uint32_t)i);  // slices.Index: the first occurrence
+}
+// one probe per value; miss[0] counts values that are not in the dictionary (the caller then
+// takes the general path, which appends them in input order)
+__global__ void __launch_bounds__(BM_THREADS)
+k_bm_put_direct(const uint32_t* __restrict__ inv, uint64_t inv_len, const uint32_t* __restrict__ vals,
+                uint64_t n, uint32_t* __restrict__ bits, uint32_t* __restrict__ miss) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = vals[i];
+  const uint32_t e = v < inv_len ? __ldg(inv + v) : BM_NOT_FOUND;
+  if (e == BM_NOT_FOUND)
+    atomicAdd(miss, 1u);
+  else
+    atomicOr(&bits[e >> 5], 1u << (e & 31u));
 }
 
 // cardinality of every 65536-bit chunk
@@ -488,6 +525,31 @@ int bm_reserve(ii2_bitmask* bm, uint64_t extra, cudaStream_t s) {
   return II2_OK;
 }
 
+// (Re)build the inverse if the dictionary allows it.  Synchronises the stream once (the maximum).
+int bm_refresh_inverse(ii2_bitmask* bm, cudaStream_t s) {
+  if (bm->inv_for_n == bm->n) return II2_OK;  // up to date (or known not to pay for this length)
+  bm->inv_for_n = bm->n;
+  bm->inv_len = 0;
+  if (bm->n < 1024) return II2_OK;  // tiny dictionaries: the hash path is launch-bound anyway
+  DevBuf<uint32_t> d_max;
+  II2_TRY(d_max.alloc_scratch(1, s));
+  II2_CUDA_TRY(cudaMemsetAsync(d_max.p, 0, 4, s));
+  k_bm_max<<<(unsigned)std::min<uint64_t>(div_up(bm->n, BM_THREADS), 1184), BM_THREADS, 0, s>>>(
+      bm->values.p, bm->n, d_max.p);
+  II2_LAUNCHED();
+  uint32_t* h = reinterpret_cast<uint32_t*>(pinned_scratch() + 28);
+  II2_TRY(small_copy(h, d_max.p, 4, s));
+  II2_CUDA_TRY(cudaStreamSynchronize(s));
+  const uint64_t len = (uint64_t)h[0] + 1;
+  if (len > 16 * bm->n + (1ull << 20) || len > (1ull << 30)) return II2_OK;  // too sparse
+  II2_TRY(bm->inv.alloc(len, s));
+  II2_CUDA_TRY(cudaMemsetAsync(bm->inv.p, 0xFF, len * 4, s));
+  k_bm_inv_build<<<div_up(bm->n, BM_THREADS), BM_THREADS, 0, s>>>(bm->values.p, bm->n, bm->inv.p);
+  II2_LAUNCHED();
+  bm->inv_len = len;
+  return II2_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -511,7 +573,9 @@ int ii2_bitmask_new(const uint32_t* init, uint64_t n, ii2_bitmask** out) {
                                                             bm->values.p, n);
     II2_LAUNCHED();
   }
+  II2_TRY(bm_refresh_inverse(bm.get(), s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
+  arena_reset(s);
   *out = bm.release();
   return II2_OK;
 }
@@ -569,8 +633,28 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
   II2_TRY(d_tot.alloc_scratch(4, s));
   II2_CUDA_TRY(cudaMemsetAsync(d_bits.p, 0, (size_t)(nchunks ? nchunks : 1) * CHUNK_WORDS * 4, s));
   uint64_t h_tot[4] = {0, 0, 0, 0};
-  if (n) {
-    II2_CUDA_TRY(cudaMemcpyAsync(d_vals.p, vals, n * 4, cudaMemcpyHostToDevice, s));
+  bool direct = false;
+  if (n) II2_CUDA_TRY(cudaMemcpyAsync(d_vals.p, vals, n * 4, cudaMemcpyHostToDevice, s));
+  if (n && bm->inv_len && bm->inv_for_n == bm->n && n >= 1024) {
+    // every value already in the dictionary (the usual Put over a known id universe): one probe
+    // of the direct-address inverse per value; a miss means appends, which the general path
+    // orders (first occurrence, input order)
+    DevBuf<uint32_t> d_miss;
+    II2_TRY(d_miss.alloc_scratch(1, s));
+    II2_CUDA_TRY(cudaMemsetAsync(d_miss.p, 0, 4, s));
+    k_bm_put_direct<<<div_up(n, BM_THREADS), BM_THREADS, 0, s>>>(bm->inv.p, bm->inv_len, d_vals.p, n,
+                                                                 d_bits.p, d_miss.p);
+    II2_LAUNCHED();
+    uint32_t* h_miss = reinterpret_cast<uint32_t*>(pinned_scratch() + 29);
+    II2_TRY(small_copy(h_miss, d_miss.p, 4, s));
+    II2_CUDA_TRY(cudaStreamSynchronize(s));
+    direct = h_miss[0] == 0;
+    if (direct)
+      II2_CUDA_TRY(cudaMemsetAsync(d_tot.p + 3, 0, 8, s));  // nothing appended
+    else
+      II2_CUDA_TRY(cudaMemsetAsync(d_bits.p, 0, (size_t)(nchunks ? nchunks : 1) * CHUNK_WORDS * 4, s));
+  }
+  if (n && !direct) {
     const unsigned g = div_up(n, BM_THREADS), g1 = div_up(n + 1, BM_THREADS);
     k_bm_put_insert<<<g, BM_THREADS, 0, s>>>(bm->table.p, mask, d_vals.p, n, D);
     II2_LAUNCHED();
@@ -582,7 +666,7 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
     II2_LAUNCHED();
     k_bm_put_fixup<<<g, BM_THREADS, 0, s>>>(bm->table.p, mask, d_vals.p, n, D, d_rank.p);
     II2_LAUNCHED();
-  } else {
+  } else if (!n) {
     II2_CUDA_TRY(cudaMemsetAsync(d_tot.p + 3, 0, 8, s));
   }
   if (nchunks) {
@@ -593,7 +677,8 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
   II2_LAUNCHED();
   II2_CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot.p, 32, cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
-  bm->n += h_tot[3];  // appended dictionary entries
+  bm->n += h_tot[3];  // appended dictionary entries (the inverse is rebuilt by the next call)
+  if (h_tot[3]) II2_TRY(bm_refresh_inverse(bm, s));
   const uint32_t nc = (uint32_t)h_tot[0];
   const int has_run = h_tot[2] != 0;
   const int has_off = !has_run || nc >= 4;  // noOffsetThreshold

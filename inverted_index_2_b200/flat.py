@@ -26,6 +26,7 @@ class FlatSegment:
     val_off: np.ndarray | None = None  # uint64 [n]
     val_size: int = 0
     key: str = ""
+    val_woff32: np.ndarray | None = None  # uint32 [n]: val_off / 4 (optional, `_val` views)
 
     @property
     def n_terms(self) -> int:
@@ -51,6 +52,7 @@ class FlatSegment:
         v.val_bytes = A.np_ptr(self.val_bytes, A.u8p)
         v.val_off = A.np_ptr(self.val_off, A.u64p)
         v.val_size = int(self.val_size)
+        v.val_woff32 = A.np_ptr(self.val_woff32, A.u32p)
         return v
 
     # ---- constructors -------------------------------------------------------
@@ -100,6 +102,13 @@ class FlatSegment:
         return FlatSegment(self.term_bytes, self.term_off, A.II2_SEG_VAL,
                            val_bytes=words.view(np.uint8), val_off=(woff[:-1] * 4).astype(np.uint64),
                            val_size=int(woff[-1]) * 4, key=self.key)
+
+    def with_woff32(self) -> "FlatSegment":
+        """The same `_val` view with the FST outputs as 32-bit word offsets (ii2.h val_woff32)."""
+        assert self.mode == A.II2_SEG_VAL and self.val_size < (1 << 34)
+        return FlatSegment(self.term_bytes, self.term_off, A.II2_SEG_VAL, val_bytes=self.val_bytes,
+                           val_off=None, val_size=self.val_size, key=self.key,
+                           val_woff32=(self.val_off // 4).astype(np.uint32))
 
 
 def views_array(segs: list[FlatSegment]):

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.ii2_abi_version() == 1
+    assert lib.ii2_abi_version() == 2
     assert b"bitmask is out of bound" in lib.ii2_strerror(A.II2_ERR_BITMASK_OOB)
     assert b"no CPU fallback" in lib.ii2_strerror(A.II2_ERR_NO_DEVICE)
 

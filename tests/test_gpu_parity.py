@@ -88,8 +88,19 @@ MERGE_CASES = [
 ]
 
 
+@pytest.fixture(params=["general", "fused"])
+def merge_path(request, monkeypatch):
+    """Both bucket pipelines: the general kernels (K1b -> K2b -> K6, default) and the fused
+    bucket kernel (k12_fused.cu, II2_FUSED=1) with its dense placement."""
+    if request.param == "fused":
+        monkeypatch.setenv("II2_FUSED", "1")
+    else:
+        monkeypatch.delenv("II2_FUSED", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", MERGE_CASES, ids=lambda c: "t%d_s%d_p%d_u%d_r%g" % c[:5])
-def test_merge_matches_oracle(engine, orc, case):
+def test_merge_matches_oracle(engine, orc, case, merge_path):
     nt, ns, npost, uni, rf, pres = case
     w = synth.make_workload(nt, ns, npost, universe=uni, removed_frac=rf, presence=pres,
                             seed=nt + ns, max_len=4096 if nt <= 200 else 64)
@@ -281,6 +292,48 @@ def test_merge_with_coalesced_partition(engine, orc, monkeypatch, bucket, fine, 
     assert_read_equal(engine.read_range(segs, lo, hi), orc.read_range(segs, lo, hi))
     for v in ("II2_BUCKET", "II2_COALESCE", "II2_COALESCE_MIN"):
         monkeypatch.delenv(v, raising=False)
+
+
+def test_merge_pipelined_val_views(engine, orc, monkeypatch):
+    """ii2_merge over `_val` views — what a Go caller holds: the mmap of <key>_val and the FST
+    outputs (file/reader.go:50-52,79-100) — staged per term range and decoded on the device, one
+    batched K3a call per range: equal to the oracle for 1, 2 and 5 ranges, with 64-bit byte
+    offsets, with 32-bit word offsets (val_woff32), mixed with decoded views, and from pinned
+    memory (gather kernel) as well as pageable memory (copy engines)."""
+    w = synth.make_workload(30000, 7, 400000, universe=1 << 16, removed_frac=0.1, seed=33, max_len=300)
+    segs = list(w.segments)
+    segs.append(FlatSegment.from_items([(b"zzzz_only_here", [5, 3, 3])]))
+    exp = orc.merge(segs, w.removed, decoded=True)
+    vsegs = [x.to_val(orc.intcomp_encode_batch) for x in segs]
+    v32 = [x.with_woff32() for x in vsegs]
+    mixed = [a if i % 2 else b for i, (a, b) in enumerate(zip(vsegs, segs))]
+    import torch
+    keep = []
+
+    def pinned(a):
+        if a is None:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+    pv32 = [FlatSegment(pinned(x.term_bytes), pinned(x.term_off), x.mode, val_bytes=pinned(x.val_bytes),
+                        val_size=x.val_size, val_woff32=pinned(x.val_woff32)) for x in v32]
+    for parts in ("1", "2", "5"):
+        monkeypatch.setenv("II2_MERGE_PARTS", parts)
+        for views in (vsegs, v32, mixed, pv32):
+            assert_merge_equal(engine.merge(views, w.removed, decoded=True), exp)
+    # a corrupt FST output (not 4-byte aligned / past the file) is refused, not decoded
+    from inverted_index_2_b200.engine import EngineError
+    bad = list(vsegs)
+    off = bad[2].val_off.copy()
+    off[len(off) // 2] += 2
+    bad[2] = FlatSegment(bad[2].term_bytes, bad[2].term_off, bad[2].mode, val_bytes=bad[2].val_bytes,
+                         val_off=off, val_size=bad[2].val_size)
+    monkeypatch.setenv("II2_MERGE_PARTS", "3")
+    with pytest.raises(EngineError):
+        engine.merge(bad, w.removed, decoded=True)
+    monkeypatch.delenv("II2_MERGE_PARTS", raising=False)
+    assert_merge_equal(engine.merge(v32, w.removed, decoded=True), exp)   # single shot
 
 
 def test_merge_pipelined_unaligned_term_bytes(engine, orc, monkeypatch):
