@@ -162,7 +162,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-        "data": "synthetic", "config": {"workload": workload_name(a)},
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "per_gpu": True,
+                   "l2": "inputs (>= 1.3 GB per step) larger than the 126 MB L2"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -21,6 +21,17 @@ import numpy as np  # noqa: E402
 from inverted_index_2_b200 import synth  # noqa: E402
 
 
+def _peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+PEAK = _peak()  # GB/s, measured copy bandwidth (fallback: B200_PROFILING.md)
+
+
 def timed(fn, reps):
     import torch
     fn()
@@ -139,7 +150,7 @@ def c4(eng, a):
     rng = np.random.default_rng(4)
     for lg in range(4, 25, 4):
         L = 1 << lg
-        nlists = max(1, (1 << 24) // L)  # >= 16M values per timing
+        nlists = max(1, a.c4_values // L)  # >= 64M values per timing
         for gap in (1, 16, 4096):
             gaps = rng.integers(1, 2 * gap + 1, size=L * nlists, dtype=np.int64)
             starts = np.arange(nlists, dtype=np.int64) * L
@@ -187,7 +198,9 @@ def c4(eng, a):
                          "api": "ii2_intcomp_*_u32 on pinned host buffers (H2D + kernels + D2H)",
                          "device_encode_ms": ph.get("k3a_encode"), "device_decode_ms": ph.get("k3a_decode"),
                          "device_encode_gbs": alg / ph["k3a_encode"] / 1e6 if ph.get("k3a_encode") else None,
-                         "device_decode_gbs": alg / ph["k3a_decode"] / 1e6 if ph.get("k3a_decode") else None})
+                         "device_decode_gbs": alg / ph["k3a_decode"] / 1e6 if ph.get("k3a_decode") else None,
+                         "encode_frac_of_hbm_peak": alg / ph["k3a_encode"] / 1e6 / PEAK if ph.get("k3a_encode") else None,
+                         "decode_frac_of_hbm_peak": alg / ph["k3a_decode"] / 1e6 / PEAK if ph.get("k3a_decode") else None})
     for lg in range(4, 25, 4):
         L = 1 << lg
         universe = np.sort(rng.choice(max(4 * L, 1 << 10), size=2 * L, replace=False)).astype(np.uint32)
@@ -225,6 +238,7 @@ def c4(eng, a):
                      "put_values_per_s": L / tp, "get_values_per_s": L / tg,
                      "api": "ii2_bitmask_put/get on pinned host buffers (H2D + kernels + D2H)",
                      "device_put_ms": ph.get("k3b_put"), "device_get_ms": ph.get("k3b_get"),
+                     "device_put_values_per_s": L / (ph["k3b_put"] * 1e-3) if ph.get("k3b_put") else None,
                      "device_put_gbs": alg / ph["k3b_put"] / 1e6 if ph.get("k3b_put") else None,
                      "device_get_gbs": alg / ph["k3b_get"] / 1e6 if ph.get("k3b_get") else None})
     print(json.dumps({"config": "C4 codec sweep, list lengths 16..16M", "results": rows}))
@@ -233,6 +247,7 @@ def c4(eng, a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="c3,c4")
+    ap.add_argument("--c4-values", type=int, default=1 << 26)
     ap.add_argument("--terms", type=int, default=1_000_000)
     ap.add_argument("--postings", type=int, default=100_000_000)
     a = ap.parse_args()

@@ -856,6 +856,342 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
   }
 }
 
+// ---------------------------------------------------------------- mid terms (one WARP each)
+// Terms of REG_CAP < L <= MW_CAP (1024) values: 32 values per lane in registers (union_dev.cuh,
+// sort_warp_v<32>: about two warp instructions per value), no block barrier anywhere — the
+// K2b design one size up.  The warps pull terms from the list K2b filled (device-side ticket);
+// longer terms go on to the CTA-per-term kernel below.
+constexpr uint32_t MW_CAP = 1024;
+constexpr int MW_V = 32;
+constexpr int MW_WARPS = 4;
+constexpr uint32_t MW_BUF = MW_CAP + MW_CAP / 32 + 8;   // one pad word per 32 values (bank-conflict-free blocked loads)
+constexpr uint32_t MW_EBUF = 3 + 8 * 129 + 1 + 1 + 6;   // enc_bound(1024) (also holds the source prefix: c + 1 <= 1025 entries)
+static_assert(MW_EBUF >= kMaxSegs + 1, "source prefix fits the stream buffer");
+
+struct MwArgs {
+  const uint32_t* n_in_list;     // terms K2b deferred
+  const uint32_t* in_rec;
+  const uint32_t* in_bucket;
+  const GroupIn* gin;
+  const uint64_t* src_ptr;
+  const uint32_t* src_len;
+  GroupRec* recs;
+  RemovedSet rem;
+  int want_enc, keep_empty;
+  uint64_t* bk_raw;
+  uint32_t nb1;
+  uint32_t* cursor;              // next item
+  uint32_t* n_out_list;          // terms passed on (> MW_CAP values)
+  uint32_t* out_rec;
+  uint32_t* out_bucket;
+  uint32_t* out_post;
+  uint32_t* out_enc;
+  unsigned long long* out_cursor;  // [0] postings, [1] words
+};
+
+__global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs a) {
+  __shared__ __align__(16) uint32_t s_buf[MW_WARPS][MW_BUF];
+  __shared__ __align__(16) uint32_t s_enc[MW_WARPS][MW_EBUF];
+  const unsigned lane = lane_id(), warp = warp_id();
+  uint32_t* const buf = s_buf[warp];
+  uint32_t* const ebuf = s_enc[warp];
+  uint32_t* const moff = ebuf;  // prefix of the source lengths, dead before the encoder runs
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(a.cursor, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= *a.n_in_list) return;
+    const uint32_t rec = a.in_rec[item], bucket = a.in_bucket[item];
+    const GroupIn g = a.gin[rec];
+    const uint32_t c = g.c, beg = g.src;
+    // ---- source lengths -> prefix (saturating); L
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < c; base += 32) {
+      const uint32_t i = base + lane;
+      uint32_t li = i < c ? a.src_len[beg + i] : 0u;
+      li = li > MW_CAP + 1 ? MW_CAP + 1 : li;
+      const uint32_t inc = warp_inclusive_scan(li);
+      if (i < c) moff[i] = min(run + inc - li, MW_CAP + 1);
+      run = min(run + __shfl_sync(0xffffffffu, inc, 31), MW_CAP + 1);
+    }
+    if (run > MW_CAP) {  // uniform: leave it to the CTA-per-term kernel
+      if (lane == 0) {
+        const uint32_t at = atomicAdd(a.n_out_list, 1u);
+        a.out_rec[at] = rec;
+        a.out_bucket[at] = bucket;
+      }
+      continue;
+    }
+    const uint32_t L = run;
+    __syncwarp();
+    // ---- gather (element e lives at e + e / 32: padded blocks).  The lanes fetch 32 source
+    // descriptors at once; the sources are then copied four at a time, their loads issued before
+    // any store, so a term of 32 sources costs ~9 memory round trips instead of 64 dependent ones
+    for (uint32_t base = 0; base < c; base += 32) {
+      const uint32_t j = base + lane;
+      uint64_t my_p = 0;
+      uint32_t my_o = 0, my_n = 0;
+      if (j < c) {
+        my_p = a.src_ptr[beg + j];
+        my_o = moff[j];
+        my_n = (j + 1 < c ? moff[j + 1] : L) - my_o;
+      }
+      const uint32_t cnt = min(32u, c - base);
+      for (uint32_t j0 = 0; j0 < cnt; j0 += 4) {
+        uint32_t x[4], o4[4], n4[4];
+        const uint32_t* p4[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int sl = (int)(j0 + q) & 31;
+          p4[q] = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, my_p, sl));
+          o4[q] = __shfl_sync(0xffffffffu, my_o, sl);
+          n4[q] = j0 + q < cnt ? __shfl_sync(0xffffffffu, my_n, sl) : 0u;
+          x[q] = lane < n4[q] ? __ldg(p4[q] + lane) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (lane < n4[q]) {
+            const uint32_t e = o4[q] + lane;
+            buf[e + (e >> 5)] = x[q];
+          }
+          for (uint32_t t = 32 + lane; t < n4[q]; t += 32) {  // sources of more than 32 values
+            const uint32_t e = o4[q] + t;
+            buf[e + (e >> 5)] = __ldg(p4[q] + t);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    uint32_t v[MW_V];
+#pragma unroll
+    for (int r = 0; r < MW_V; r++) {
+      const uint32_t e = lane * MW_V + r;
+      v[r] = e < L ? buf[lane * (MW_V + 1) + r] : 0xFFFFFFFFu;
+    }
+    const bool multi = c > 1;  // a single source passes through unsorted, duplicates kept (Q4)
+    if (multi) sort_warp_v<MW_V>(v, lane, L);
+    // ---- removed filter (eight probes in flight at a time), dedup against the predecessor
+    uint32_t keep = 0;
+    if (a.rem.bitmap) {
+      const uint32_t nbits = (uint32_t)a.rem.bitmap_bits;
+#pragma unroll
+      for (int r0 = 0; r0 < MW_V; r0 += 8) {
+        uint32_t word[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const bool probe = lane * MW_V + r0 + r < L && v[r0 + r] < nbits;
+          word[r] = probe ? __ldg(a.rem.bitmap + (v[r0 + r] >> 5)) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+          keep |= (lane * MW_V + r0 + r < L && !((word[r] >> (v[r0 + r] & 31u)) & 1u)) ? 1u << (r0 + r) : 0u;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < MW_V; r++)
+        if (lane * MW_V + r < L && !is_removed(a.rem, v[r])) keep |= 1u << r;
+    }
+    const uint32_t up = __shfl_up_sync(0xffffffffu, v[MW_V - 1], 1);
+    if (multi) {
+      if (lane > 0 && up == v[0]) keep &= ~1u;
+#pragma unroll
+      for (int r = 1; r < MW_V; r++)
+        if (v[r] == v[r - 1]) keep &= ~(1u << r);
+    }
+    const uint32_t cnt = __popc(keep);
+    const uint32_t inc = warp_inclusive_scan(cnt);
+    const uint32_t outn = __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();  // every lane holds its values: the buffer can be rewritten, dense this time
+    {
+      uint32_t* dst = buf + (inc - cnt);
+#pragma unroll
+      for (int r = 0; r < MW_V; r++) {
+        const bool k = (keep >> r) & 1u;
+        if (k) *dst = v[r];
+        dst += k ? 1 : 0;
+      }
+    }
+    __syncwarp();
+    // ---- output space, stream, values, record
+    unsigned long long pos_p = 0, pos_e = 0;
+    if (lane == 0) {
+      pos_p = atomicAdd(&a.out_cursor[0], (unsigned long long)outn);
+      if (a.want_enc) pos_e = atomicAdd(&a.out_cursor[1], (unsigned long long)intcomp::enc_bound(outn));
+    }
+    pos_p = __shfl_sync(0xffffffffu, pos_p, 0);
+    pos_e = __shfl_sync(0xffffffffu, pos_e, 0);
+    uint32_t* const dst_post = a.out_post + pos_p;
+    uint32_t* const dst_enc = a.out_enc + pos_e;
+    for (uint32_t e = lane; e < outn; e += 32) dst_post[e] = buf[e];
+    uint32_t enc = 0;
+    if (a.want_enc && outn) {
+      enc = encode_shared_warp(buf, outn, ebuf);
+      for (uint32_t e = lane; e < enc; e += 32) dst_enc[e] = ebuf[e];
+    }
+    if (lane == 0) {
+      GroupRec& r = a.recs[rec];
+      r.cnt = outn;
+      r.enc = enc;
+      r.dec = reinterpret_cast<uint64_t>(dst_post);
+      r.eoff = reinterpret_cast<uint64_t>(dst_enc);
+      if (outn || a.keep_empty) {
+        unsigned long long* bo = reinterpret_cast<unsigned long long*>(a.bk_raw);
+        atomicAdd(&bo[0ull * a.nb1 + bucket], 1ull);
+        atomicAdd(&bo[1ull * a.nb1 + bucket], (unsigned long long)r.tlen);
+        atomicAdd(&bo[2ull * a.nb1 + bucket], (unsigned long long)outn);
+        atomicAdd(&bo[3ull * a.nb1 + bucket], (unsigned long long)enc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- medium terms (one CTA each)
+// Terms of REG_CAP < L <= MED_CAP values — every term of an index with ~1000 postings per term,
+// the head of a Zipf distribution — used to take the multi-kernel global-memory path below: a
+// host round trip for the lengths, a gather pass, a tile sort pass and a finish pass over the
+// same values.  Here one CTA unions a term entirely in shared memory: sources gathered by
+// binary search over their length prefix, bitonic network, dedup + removed filter + block-scan
+// compaction, whole-CTA intcomp encode, one write of the result.  The CTAs pull terms from the
+// list K2b filled (a device-side counter: no host synchronisation); output space comes from two
+// bump cursors over regions sized by the input postings.  Longer terms go on to the `huge`
+// list for the path below.
+constexpr uint32_t MED_CAP = 4096;
+constexpr int MED_THREADS = 256;
+constexpr uint32_t MED_ENC_WORDS = MED_CAP + MED_CAP / 4 + 64;
+
+struct MedArgs {
+  const uint32_t* n_large;       // terms K2b deferred
+  const uint32_t* large_rec;
+  const uint32_t* large_bucket;
+  const GroupIn* gin;
+  const uint64_t* src_ptr;
+  const uint32_t* src_len;
+  GroupRec* recs;
+  RemovedSet rem;
+  int want_enc, keep_empty;
+  uint64_t* bk_raw;
+  uint32_t nb1;
+  uint32_t* cursor;              // next item of the list
+  uint32_t* n_huge;              // terms left to the multi-CTA path
+  uint32_t* huge_rec;
+  uint32_t* huge_bucket;
+  uint32_t* out_post;            // unions, bump-allocated
+  uint32_t* out_enc;             // `_val` streams, bump-allocated (upper-bound slots)
+  unsigned long long* out_cursor;  // [0] postings, [1] words
+};
+
+__global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a) {
+  __shared__ uint32_t s_v[MED_CAP];            // gathered values -> sorted
+  __shared__ uint32_t s_o[MED_ENC_WORDS];      // survivors, then nothing else (encode reads them)
+  __shared__ uint32_t s_moff[kMaxSegs + 1];    // prefix of the source lengths
+  __shared__ uint64_t s_ws[MED_THREADS / 32 + 2];
+  __shared__ uint32_t s_stage[(MED_THREADS / 32) * intcomp::kStageWords];
+  __shared__ uint32_t s_table[MED_CAP / 128 + 1];
+  __shared__ uint32_t s_item;
+  __shared__ unsigned long long s_pos[2];
+  const uint32_t tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(a.cursor, 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= *a.n_large) return;
+    const uint32_t rec = a.large_rec[item], bucket = a.large_bucket[item];
+    const GroupIn g = a.gin[rec];
+    const uint32_t c = g.c, beg = g.src;
+    // ---- source lengths -> prefix; total L (saturating: anything above MED_CAP is "huge")
+    uint64_t run = 0;
+    for (uint32_t base = 0; base < c; base += MED_THREADS) {
+      const uint32_t i = base + tid;
+      const uint64_t li = i < c ? a.src_len[beg + i] : 0u;
+      uint64_t tot;
+      const uint64_t ex = block_exclusive_scan(li, s_ws, tot);
+      if (i < c) s_moff[i] = (uint32_t)min(run + ex, (uint64_t)MED_CAP + 1);
+      run += tot;
+    }
+    if (run > MED_CAP) {  // uniform
+      if (tid == 0) {
+        const uint32_t at = atomicAdd(a.n_huge, 1u);
+        a.huge_rec[at] = rec;
+        a.huge_bucket[at] = bucket;
+      }
+      continue;
+    }
+    const uint32_t L = (uint32_t)run;
+    if (tid == 0) s_moff[c] = L;
+    __syncthreads();
+    // ---- gather
+    for (uint32_t e = tid; e < L; e += MED_THREADS) {
+      uint32_t lo = 0, hi = c;  // source holding element e
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_moff[mid + 1] <= e)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src_ptr[beg + lo]);
+      s_v[e] = __ldg(src + (e - s_moff[lo]));
+    }
+    __syncthreads();
+    const bool single = c == 1;  // passes through unsorted, duplicates kept (survey Q4)
+    if (!single) {
+      bitonic_sort_any(s_v, L, tid, (uint32_t)MED_THREADS, [](uint32_t x, uint32_t y) { return x < y; },
+                       [] { __syncthreads(); });
+      __syncthreads();
+    }
+    // ---- dedup + removed filter + compaction
+    uint32_t outn = 0;
+    for (uint32_t e0 = 0; e0 < L; e0 += MED_THREADS) {
+      const uint32_t e = e0 + tid;
+      const bool valid = e < L;
+      const uint32_t x = valid ? s_v[e] : 0u;
+      const uint64_t keep =
+          (valid && (single || e == 0 || s_v[e - 1] != x) && !is_removed(a.rem, x)) ? 1u : 0u;
+      uint64_t tot;
+      const uint64_t ex = block_exclusive_scan(keep, s_ws, tot);
+      if (keep) s_o[outn + (uint32_t)ex] = x;
+      outn += (uint32_t)tot;
+    }
+    __syncthreads();
+    // ---- output space, then the stream and the values
+    if (tid == 0) {
+      s_pos[0] = atomicAdd(&a.out_cursor[0], (unsigned long long)outn);
+      s_pos[1] = a.want_enc ? atomicAdd(&a.out_cursor[1], (unsigned long long)intcomp::enc_bound(outn)) : 0ull;
+    }
+    __syncthreads();
+    uint32_t* const dst_post = a.out_post + s_pos[0];
+    uint32_t* const dst_enc = a.out_enc + s_pos[1];
+    for (uint32_t e = tid; e < outn; e += MED_THREADS) dst_post[e] = s_o[e];
+    uint32_t enc = 0;
+    if (a.want_enc && outn >= 128) {
+      enc = intcomp::enc_emit_cta(s_o, outn, dst_enc, s_table, s_stage, s_ws);
+    } else if (a.want_enc && outn) {
+      if (warp_id() == 0) {
+        const uint32_t e2 = intcomp::enc_emit_warp(s_o, outn, dst_enc, s_stage);
+        if (lane_id() == 0) s_table[0] = e2;
+      }
+      __syncthreads();
+      enc = s_table[0];
+    }
+    if (tid == 0) {
+      GroupRec& r = a.recs[rec];
+      r.cnt = outn;
+      r.enc = enc;
+      r.dec = reinterpret_cast<uint64_t>(dst_post);
+      r.eoff = reinterpret_cast<uint64_t>(dst_enc);
+      if (outn || a.keep_empty) {
+        unsigned long long* bo = reinterpret_cast<unsigned long long*>(a.bk_raw);
+        atomicAdd(&bo[0ull * a.nb1 + bucket], 1ull);
+        atomicAdd(&bo[1ull * a.nb1 + bucket], (unsigned long long)r.tlen);
+        atomicAdd(&bo[2ull * a.nb1 + bucket], (unsigned long long)outn);
+        atomicAdd(&bo[3ull * a.nb1 + bucket], (unsigned long long)enc);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- heavy terms (global memory)
 __global__ void __launch_bounds__(256) k2_large_len(const LargeArgs a, uint32_t n) {
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1309,8 +1645,16 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   // gather slots of the light terms (K1b -> K2b); the decoded union replaces them in place
   II2_TRY(u.tmp_post.alloc_scratch(n_in, s, 16));
   const uint32_t large_cap = (uint32_t)std::min<uint64_t>(N, n_in / REG_CAP + 1);
+  // [6][large_cap]: K2b's list (rec, bucket), the list the warp kernel passes on, the huge list
   DevBuf<uint32_t> large_u32;
-  II2_TRY(large_u32.alloc_scratch(2 * (size_t)large_cap, s));
+  II2_TRY(large_u32.alloc_scratch(6 * (size_t)large_cap, s));
+  // mid / medium terms (k2_mwarp_kernel, k2_medium_kernel): unions and streams bump-allocated
+  // [0] postings, [1] words, [2] work cursors (2 x u32), [3] terms passed on by the warp kernel
+  DevBuf<unsigned long long> med_cursor;
+  II2_TRY(med_cursor.alloc_scratch(4, s));
+  II2_CUDA_TRY(cudaMemsetAsync(med_cursor.p, 0, 32, s));
+  II2_TRY(u.med_post.alloc_scratch(n_in, s, 16));
+  if (want_enc) II2_TRY(u.med_enc.alloc_scratch(n_in + n_in / 4 + 16ull * large_cap + 64, s, 16));
   II2_CUDA_TRY(cudaMemsetAsync(u.totals.p, 0, 64, s));
   II2_CUDA_TRY(cudaMemsetAsync(u.bk_raw.p, 0, 4 * (size_t)(B + 1) * 8, s));
   II2_TRY(u.bk_mode.alloc_scratch(B, s));
@@ -1379,6 +1723,57 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       k2b_union_kernel<<<grid, K2B_THREADS, 0, s>>>(a2);
       II2_LAUNCHED();
     }
+    {  // the terms K2b deferred: up to MW_CAP values one warp each, up to MED_CAP one CTA each;
+       // device-side work lists, no host round trip
+      ProfScope scope("k2_medium", s);
+      uint32_t* const mid_rec = large_u32.p + 4 * (size_t)large_cap;
+      uint32_t* const mid_bucket = large_u32.p + 5 * (size_t)large_cap;
+      uint32_t* const n_mid = reinterpret_cast<uint32_t*>(med_cursor.p + 3);
+      MwArgs w2;
+      w2.n_in_list = a2.n_large;
+      w2.in_rec = a2.large_rec;
+      w2.in_bucket = a2.large_bucket;
+      w2.gin = gin.p;
+      w2.src_ptr = src_ptr.p;
+      w2.src_len = src_len.p;
+      w2.recs = u.recs.p;
+      w2.rem = rem;
+      w2.want_enc = want_enc ? 1 : 0;
+      w2.keep_empty = keep_empty ? 1 : 0;
+      w2.bk_raw = u.bk_raw.p;
+      w2.nb1 = B + 1;
+      w2.cursor = reinterpret_cast<uint32_t*>(med_cursor.p + 2) + 1;
+      w2.n_out_list = n_mid;
+      w2.out_rec = mid_rec;
+      w2.out_bucket = mid_bucket;
+      w2.out_post = u.med_post.p;
+      w2.out_enc = u.med_enc.p;
+      w2.out_cursor = med_cursor.p;
+      k2_mwarp_kernel<<<kNumSMs * 4, MW_WARPS * 32, 0, s>>>(w2);
+      II2_LAUNCHED();
+      MedArgs m;
+      m.n_large = n_mid;
+      m.large_rec = mid_rec;
+      m.large_bucket = mid_bucket;
+      m.gin = gin.p;
+      m.src_ptr = src_ptr.p;
+      m.src_len = src_len.p;
+      m.recs = u.recs.p;
+      m.rem = rem;
+      m.want_enc = want_enc ? 1 : 0;
+      m.keep_empty = keep_empty ? 1 : 0;
+      m.bk_raw = u.bk_raw.p;
+      m.nb1 = B + 1;
+      m.cursor = reinterpret_cast<uint32_t*>(med_cursor.p + 2);
+      m.n_huge = a2.n_large + 1;  // the high half of totals[6]
+      m.huge_rec = large_u32.p + 2 * (size_t)large_cap;
+      m.huge_bucket = large_u32.p + 3 * (size_t)large_cap;
+      m.out_post = u.med_post.p;
+      m.out_enc = u.med_enc.p;
+      m.out_cursor = med_cursor.p;
+      k2_medium_kernel<<<kNumSMs * 4, MED_THREADS, 0, s>>>(m);
+      II2_LAUNCHED();
+    }
     return II2_OK;
   };
   uint64_t* h_tot = pinned_scratch();  // 8 words
@@ -1438,12 +1833,12 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     II2_TRY(general(B, nullptr));
     II2_TRY(totals());
   }
-  const uint32_t h_nl = (uint32_t)h_tot[6];
+  const uint32_t h_nl = (uint32_t)(h_tot[6] >> 32);  // terms the medium kernel passed on (> MED_CAP values)
   if (h_nl > 0) {
     ProfScope scope("k2_large", s);
     LargeArgs la;
-    la.rec = large_u32.p;
-    la.bucket = large_u32.p + large_cap;
+    la.rec = large_u32.p + 2 * (size_t)large_cap;
+    la.bucket = large_u32.p + 3 * (size_t)large_cap;
     la.gin = gin.p;
     la.src_ptr = src_ptr.p;
     la.src_len = src_len.p;

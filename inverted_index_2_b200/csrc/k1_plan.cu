@@ -228,28 +228,29 @@ k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t*
   const uint32_t b0 = wide ? t0 - mis : (t0 & ~3u);
   const uint32_t words = (b1 - b0 + 3u) >> 2;
   const bool staged = words * 4u + 16u <= K1_RAW_BYTES;
+  // offsets and term bytes go straight from global to shared memory (cp.async / LDGSTS: no
+  // register round trip — the LSU data pipe was this kernel's busiest unit, 71 % of its peak
+  // with LDG + STS, profiles/r02_ncu_full_metrics.csv)
   {
     constexpr int PER = K1_CHUNK / 256;
-    uint32_t o[PER];
+    const uint32_t s_off_a = (uint32_t)__cvta_generic_to_shared(s_off);
 #pragma unroll
     for (int j = 0; j < PER; j++) {
       const uint32_t t = threadIdx.x + j * 256;
-      o[j] = t <= n ? __ldg(sd.toff + i0 + t) : 0u;
+      if (t < n)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_off_a + 4 * t), "l"(sd.toff + i0 + t)
+                     : "memory");
     }
     if (threadIdx.x == 0) s_off[n] = b1;
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-      const uint32_t t = threadIdx.x + j * 256;
-      if (t < n) s_off[t] = o[j];
-    }
   }
   if (staged) {
     if (wide) {
       const uint4* src = reinterpret_cast<const uint4*>(sd.tb + b0);
-      uint4* dst = reinterpret_cast<uint4*>(s_raw);
+      const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(s_raw);
       const uint32_t quads = (words + 3u) >> 2;
 #pragma unroll 4
-      for (uint32_t q = threadIdx.x; q < quads; q += 256) dst[q] = __ldg(src + q);
+      for (uint32_t q = threadIdx.x; q < quads; q += 256)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_a + 16 * q), "l"(src + q) : "memory");
     } else {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(sd.tb + b0);
 #pragma unroll 8
@@ -268,6 +269,7 @@ k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t*
     s_range[0] = crank[c];
     s_range[1] = ci + 1 == nchunks ? S : crank[c + 1];
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const uint32_t ra = s_range[0], rb = s_range[1];
   for (uint32_t r = ra + threadIdx.x; r < rb; r += 256) {

@@ -97,6 +97,8 @@ struct UnionOut {
   DevBuf<uint32_t> tmp_enc;    // encoded streams, one upper-bound slot per light term
   DevBuf<uint32_t> large_enc;  // the same for heavy terms
   DevBuf<uint32_t> large_tmp;  // sort space of the multi-CTA path for heavy terms
+  DevBuf<uint32_t> med_post;   // unions of the medium terms (one CTA each)
+  DevBuf<uint32_t> med_enc;    // their `_val` streams
   DevBuf<uint32_t> bk_D;       // [B] distinct terms per bucket
   // fused path (K12f): dense per-bucket staging
   bool fused = false;

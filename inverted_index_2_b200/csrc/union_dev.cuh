@@ -83,6 +83,77 @@ __device__ __forceinline__ void sort_blocked(uint32_t (&v)[8], unsigned hl, uint
   if (W == 32 && nmax > 128) merge_level<256>(v, hl);
 }
 
+// ---- the same network with V values per lane over a whole warp (V * 32 values) ----------------
+// Used for terms of REG_CAP < L <= 1024 values (k12_union.cu, k2_mwarp_kernel): 32 values per
+// lane keep five of every six compare-exchanges of a 1024-value sort inside a thread.
+template <int V>
+__device__ __forceinline__ void sort_local_v(uint32_t (&v)[V]) {  // bitonic network, ascending
+#pragma unroll
+  for (int k = 2; k <= V; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < V; i++) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t lo = min(v[i], v[l]), hi = max(v[i], v[l]);
+          const bool asc = (i & k) == 0;  // compile time
+          v[i] = asc ? lo : hi;
+          v[l] = asc ? hi : lo;
+        }
+      }
+    }
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void clean_local_v(uint32_t (&v)[V]) {  // bitonic -> ascending
+#pragma unroll
+  for (int d = V / 2; d > 0; d >>= 1) {
+#pragma unroll
+    for (int i = 0; i < V; i++)
+      if ((i & d) == 0) cex(v[i], v[i + d]);
+  }
+}
+
+// Sorts the V * 32 values of the warp; n = real length (padding 0xFFFFFFFF at the end).  The
+// merge levels are ONE rolled loop over the block size K (the shuffle distance is a run-time
+// value): fully unrolled, five levels of a 32-values-per-lane network are ~35 KB of SASS and the
+// kernel starved on instruction fetch (ncu: `no_inst` the top stall of every min / max).
+// Level K: blocks of K elements (K / V lanes) become sorted —
+//   flip: element e pairs with e ^ (K-1) = (lane ^ (K/V - 1), V-1-r), two values at a time;
+//   half-cleaners whose distance is a whole number of lanes; then the local half-cleaners.
+template <int V>
+__device__ __forceinline__ void sort_warp_v(uint32_t (&v)[V], unsigned lane, uint32_t n) {
+  sort_local_v<V>(v);
+#pragma unroll 1
+  for (uint32_t K = 2 * V; K <= 32 * V && n > K / 2; K <<= 1) {
+    {
+      const unsigned dist = K / V - 1;
+      const bool lower = (lane & (K / (2 * V))) == 0;
+#pragma unroll
+      for (int r = 0; r < V / 2; r++) {
+        const uint32_t a = v[r], b = v[V - 1 - r];
+        const uint32_t oa = __shfl_xor_sync(0xffffffffu, b, dist);
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, a, dist);
+        v[r] = ((a < oa) == lower) ? a : oa;
+        v[V - 1 - r] = ((b < ob) == lower) ? b : ob;
+      }
+    }
+#pragma unroll 1
+    for (uint32_t j = K / 4; j >= V; j >>= 1) {
+      const unsigned dist = j / V;
+      const bool lower = (lane & dist) == 0;
+#pragma unroll
+      for (int r = 0; r < V; r++) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], dist);
+        v[r] = ((v[r] < o) == lower) ? v[r] : o;
+      }
+    }
+    clean_local_v<V>(v);
+  }
+}
+
 // Union of the term of this lane's group: L gathered values at `slot` (global) -> sorted
 // (slices.Sort) and deduped (slices.Compact) when the term has >= 2 sources (a single-source
 // term passes through in source order, duplicates kept: survey Q4) -> removed filter ->

@@ -219,6 +219,37 @@ def test_heavy_terms_multi_cta_union(engine, orc, merge_path):
                        orc.merge(segs, removed, decoded=True))
 
 
+def test_mid_and_medium_terms(engine, orc, merge_path):
+    """Terms of 257 ... 4097+ values: one warp per term with 32 values per lane up to 1024
+    (k2_mwarp_kernel), one CTA per term up to 4096 (k2_medium_kernel), the multi-CTA path beyond;
+    every boundary, many and few sources, a source longer than 32 values, single-source
+    pass-through with duplicates (survey Q4), values that all fall to the removed filter, with and
+    without a removed bitmap (ids >= 2^29 force the binary-search filter)."""
+    rng = np.random.default_rng(21)
+    for hi_bits, rem_n in ((20, 30000), (31, 500)):
+        sizes = [257, 300, 511, 512, 513, 1000, 1023, 1024, 1025, 1500, 2048, 4095, 4096, 4097, 6000]
+        nseg = 12
+        per_seg = [[] for _ in range(nseg)]
+        for ti, total in enumerate(sizes):
+            name = b"t%05d" % ti
+            k = [2, 12, 5][ti % 3]                       # sources of the term
+            cuts = np.sort(rng.integers(0, total + 1, size=k - 1))
+            lens = np.diff(np.concatenate([[0], cuts, [total]]))
+            for s_i, n in zip(rng.permutation(nseg)[:k], lens):
+                vals = np.unique(rng.integers(0, 1 << hi_bits, size=int(n), dtype=np.int64)).tolist()
+                per_seg[int(s_i)].append((name, vals))   # overlap between sources: the union dedups
+        per_seg[0].append((b"u_solo", rng.integers(0, 1 << hi_bits, size=900, dtype=np.int64).tolist()))   # unsorted, kept
+        per_seg[1].append((b"v_solo", [7, 7, 3] * 700))                                                   # CTA path, kept
+        gone = np.arange(1000, 1700, dtype=np.int64)
+        per_seg[2].append((b"w_gone", gone[:400].tolist()))
+        per_seg[3].append((b"w_gone", gone[300:].tolist()))
+        segs = [FlatSegment.from_items(sorted(x)) for x in per_seg]
+        removed = np.unique(np.concatenate([rng.integers(0, 1 << hi_bits, size=rem_n, dtype=np.int64), gone])
+                            ).astype(np.uint32)
+        assert_merge_equal(engine.merge(segs, removed, decoded=True), orc.merge(segs, removed, decoded=True))
+        assert_read_equal(engine.read_range(segs, b"t00003", b"v"), orc.read_range(segs, b"t00003", b"v"))
+
+
 def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
     """ii2_merge over host buffers cuts the term space into ranges and overlaps staging with
     the kernels; the concatenated result is the single-shot result, also when the output
