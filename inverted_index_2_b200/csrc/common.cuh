@@ -189,10 +189,29 @@ __device__ __forceinline__ uint32_t warp_partition_point(uint32_t lo, uint32_t h
 }
 
 // slices.BinarySearch(removedValues, v) membership (shard.go:183), answered from the bitmap
-// when one covers v.  The search itself is kept out of line: the union kernels test up to 32
-// register-resident values per lane, and 32 inlined search loops were a quarter of their SASS
-// (they run only for removed lists whose largest id is >= 2^29).
-static __device__ __noinline__ bool is_removed_search(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t v) {
+// when one covers v.
+__device__ __forceinline__ bool is_removed(const RemovedSet& r, uint32_t v) {
+  if (r.n == 0) return false;
+  if (r.bitmap) {
+    if ((uint64_t)v >= r.bitmap_bits) return false;
+    return (__ldg(r.bitmap + (v >> 5)) >> (v & 31u)) & 1u;
+  }
+  uint64_t lo = 0, hi = r.n;
+  while (lo < hi) {
+    uint64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(r.sorted + mid) < v)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo < r.n && __ldg(r.sorted + lo) == v;
+}
+
+// The same test kept out of line, for kernels that apply it to dozens of register-resident
+// values per lane (32 inlined search loops were a quarter of k2_mwarp_kernel's SASS; the loop
+// only runs for removed lists whose largest id is >= 2^29).
+static __device__ __noinline__ bool is_removed_call(const uint32_t* __restrict__ sorted, uint64_t n,
+                                                    uint32_t v) {
   uint64_t lo = 0, hi = n;
   while (lo < hi) {
     uint64_t mid = lo + ((hi - lo) >> 1);
@@ -202,15 +221,6 @@ static __device__ __noinline__ bool is_removed_search(const uint32_t* __restrict
       hi = mid;
   }
   return lo < n && __ldg(sorted + lo) == v;
-}
-
-__device__ __forceinline__ bool is_removed(const RemovedSet& r, uint32_t v) {
-  if (r.n == 0) return false;
-  if (r.bitmap) {
-    if ((uint64_t)v >= r.bitmap_bits) return false;
-    return (__ldg(r.bitmap + (v >> 5)) >> (v & 31u)) & 1u;
-  }
-  return is_removed_search(r.sorted, r.n, v);
 }
 
 // Bitonic sorting network without direction flags, valid for ANY n (indices >= n behave as

@@ -52,6 +52,8 @@ struct K1bArgs {
   const SegDesc* segs;
   int k;
   const uint32_t* part;
+  const uint32_t* btb;   // boundary tables of the plan: first term byte / first posting of every run
+  const uint64_t* bpo;
   const uint64_t* bk_pos;
   const uint32_t* bk_cpl;
   const uint64_t* bk_P;
@@ -118,6 +120,9 @@ __device__ unsigned long long g_k1b_clk[10];
 #else
 #define K1B_TICK(slot) do { } while (0)
 #endif
+// LIST: the CTA's bucket comes from a.list (the buckets the fused kernel deferred) — a separate
+// instantiation, because one more live pointer in the default one costs spills (64 registers).
+template <bool LIST>
 __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(const K1bArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t s_ws64[K1B_WARPS + 2];
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
 #ifdef K1B_TIMING
   long long tick_ = clock64();
 #endif
-  const uint32_t b = a.list ? a.list[blockIdx.x] : a.bucket0 + blockIdx.x;
+  const uint32_t b = LIST ? a.list[blockIdx.x] : a.bucket0 + blockIdx.x;
   uint32_t W = (uint32_t)(a.bk_pos[b + 1] - a.bk_pos[b]);
   if (W == 0) {
     if (tid == 0) a.bk_D[b] = 0;
@@ -188,6 +193,23 @@ __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(co
       asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.toff + cur[s]));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.poff + cur[s]));
       if (endr[s] - cur[s] > 12) asm volatile("prefetch.global.L2 [%0];" ::"l"(sd.poff + endr[s]));
+#endif
+#ifdef K1B_PREFETCH_RUNS
+      // With the plan's boundary tables the term bytes and postings of the run are known NOW, two
+      // dependent round trips before their addresses arrive through the offsets.  Measured
+      // (profiles/r02_experiments.md section 2): 1.30 ms instead of the per-instance prefetches
+      // below (1.23 ms), 1.45 ms with both - the extra live values cost spills at 64 registers.
+      if (endr[s] > cur[s]) {
+        const uint64_t r0s = (uint64_t)r0 * k + s, r1s = (uint64_t)r1 * k + s;
+        const uint32_t t0 = a.btb[r0s], t1 = a.btb[r1s];
+        const uint64_t p0 = a.bpo[r0s], p1 = a.bpo[r1s];
+        const char* tp = reinterpret_cast<const char*>(sd.tb) + t0;
+        const char* pp = reinterpret_cast<const char*>(sd.post + p0);
+        const uint32_t tbytes = min(t1 - t0, 512u);
+        const uint32_t pbytes = (uint32_t)min((p1 - p0) * 4, (uint64_t)512);
+        for (uint32_t o = 0; o < tbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
+        for (uint32_t o = 0; o < pbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + o));
+      }
 #endif
 #endif
     }
@@ -721,12 +743,13 @@ struct K2bArgs {
 #ifndef K2B_MIN_CTAS
 #define K2B_MIN_CTAS 8
 #endif
+template <bool LIST>
 __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(const K2bArgs a) {
   __shared__ __align__(16) uint32_t s_buf[K2B_WARPS][REG_CAP];
   __shared__ __align__(16) uint32_t s_enc[K2B_WARPS][K2B_EBUF];
   const unsigned lane = lane_id(), warp = warp_id();
   const unsigned half = lane >> 4, hl = lane & 15u;
-  const uint32_t b = a.list ? a.list[blockIdx.x] : a.bucket0 + blockIdx.x;
+  const uint32_t b = LIST ? a.list[blockIdx.x] : a.bucket0 + blockIdx.x;
   const uint32_t D = a.bk_D[b];
   if (D == 0) return;
   const uint64_t rec_base = a.bk_pos[b];
@@ -989,7 +1012,7 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs
     } else {
 #pragma unroll
       for (int r = 0; r < MW_V; r++)
-        if (lane * MW_V + r < L && !is_removed(a.rem, v[r])) keep |= 1u << r;
+        if (lane * MW_V + r < L && !(a.rem.n && is_removed_call(a.rem.sorted, a.rem.n, v[r]))) keep |= 1u << r;
     }
     const uint32_t up = __shfl_up_sync(0xffffffffu, v[MW_V - 1], 1);
     if (multi) {
@@ -1624,8 +1647,11 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   // buckets it passes.  Measured on B200 (profiles/r02_experiments.md): 2.3 ms for 86 % of the C2
   // instances + 0.46 ms for the rest against 2.3 ms for K1b + K2b over all of them, so the
   // general kernels stay the default; the fused path moves 1.6x fewer DRAM bytes per step.
+  // Small calls (narrow range reads) are launch-latency bound and the fused path has three
+  // launches fewer: 185 vs 219 us for a 0.1 % read of C3; it takes them unless II2_FUSED=0.
   const char* fused_env = getenv("II2_FUSED");
-  u.fused = fused_env && atoi(fused_env) != 0 && k12f_supported(k);
+  const bool fused_on = fused_env ? atoi(fused_env) != 0 : N <= 65536;
+  u.fused = fused_on && k12f_supported(k);
   DevBuf<GroupIn> gin;
   DevBuf<uint64_t> src_ptr;
   DevBuf<uint32_t> src_len;
@@ -1670,6 +1696,8 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   a1.segs = plan.segs;
   a1.k = k;
   a1.part = plan.part.p;
+  a1.btb = plan.btb.p;
+  a1.bpo = plan.bpo.p;
   a1.bk_pos = plan.bk_pos();
   a1.bk_cpl = plan.bk_cpl.p;
   a1.bk_P = plan.bk_P();
@@ -1705,7 +1733,9 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   static size_t attr = 0;
   if (smem > attr) {
     const size_t want = std::max(k1b_smem_bytes(kMaxSegs), smem);
-    II2_CUDA_TRY(cudaFuncSetAttribute(k1b_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    II2_CUDA_TRY(cudaFuncSetAttribute(k1b_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)want));
+    II2_CUDA_TRY(cudaFuncSetAttribute(k1b_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)want));
     attr = want;
   }
@@ -1715,12 +1745,18 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     a1.list = a2.list = list;
     {
       ProfScope scope("k1b_group", s);
-      k1b_group_kernel<<<grid, K1B_THREADS, smem, s>>>(a1);
+      if (list)
+        k1b_group_kernel<true><<<grid, K1B_THREADS, smem, s>>>(a1);
+      else
+        k1b_group_kernel<false><<<grid, K1B_THREADS, smem, s>>>(a1);
       II2_LAUNCHED();
     }
     {
       ProfScope scope("k2b_union", s);
-      k2b_union_kernel<<<grid, K2B_THREADS, 0, s>>>(a2);
+      if (list)
+        k2b_union_kernel<true><<<grid, K2B_THREADS, 0, s>>>(a2);
+      else
+        k2b_union_kernel<false><<<grid, K2B_THREADS, 0, s>>>(a2);
       II2_LAUNCHED();
     }
     {  // the terms K2b deferred: up to MW_CAP values one warp each, up to MED_CAP one CTA each;

@@ -54,10 +54,8 @@ __device__ __forceinline__ void merge_level(uint32_t (&v)[8], unsigned hl) {
     uint32_t o[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) o[r] = __shfl_xor_sync(0xffffffffu, v[7 - r], K / 8 - 1);
-    // keep-own test folded into one compare (ISETP.LT.XOR) + one select instead of min, max
-    // and a select: (v < o) == lower keeps v, else takes o (equal values: either)
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = ((v[r] < o[r]) == lower) ? v[r] : o[r];
+    for (int r = 0; r < 8; r++) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
   }
 #pragma unroll
   for (int j = K / 4; j >= 8; j >>= 1) {  // half-cleaners across lanes
@@ -65,7 +63,7 @@ __device__ __forceinline__ void merge_level(uint32_t (&v)[8], unsigned hl) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j / 8);
-      v[r] = ((v[r] < o) == lower) ? v[r] : o;
+      v[r] = lower ? min(v[r], o) : max(v[r], o);
     }
   }
   clean8_local(v);

@@ -30,7 +30,8 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     alt = os.environ.get("II2_LIB")  # tuning sweeps: another build of the same library
     if alt:
         lib = C.CDLL(alt)
-        A.bind(lib, A.PROTOTYPES)
+        # (an older build may lack the newest entry points: bind what it exports)
+        A.bind(lib, {k: v for k, v in A.PROTOTYPES.items() if hasattr(lib, k)})
         return lib
     if build_if_needed and os.path.isdir(os.path.join(_HERE, "csrc")):
         from .build import build
