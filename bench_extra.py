@@ -238,6 +238,12 @@ def c4(eng, a):
                      "put_values_per_s": L / tp, "get_values_per_s": L / tg,
                      "api": "ii2_bitmask_put/get on pinned host buffers (H2D + kernels + D2H)",
                      "device_put_ms": ph.get("k3b_put"), "device_get_ms": ph.get("k3b_get"),
+                     "note": "device_*_ms = the call's stream time INCLUDING its H2D / D2H copies "
+                             "(64 MB of values at L = 16 M); kernels_*_ms = kernels only",
+                     "kernels_put_ms": ph.get("k3b_put_kernels"), "kernels_get_ms": ph.get("k3b_get_kernels"),
+                     "kernels_put_values_per_s": L / (ph["k3b_put_kernels"] * 1e-3) if ph.get("k3b_put_kernels") else None,
+                     "kernels_get_values_per_s": L / (ph["k3b_get_kernels"] * 1e-3) if ph.get("k3b_get_kernels") else None,
+                     "kernels_put_gbs": alg / ph["k3b_put_kernels"] / 1e6 if ph.get("k3b_put_kernels") else None,
                      "device_put_values_per_s": L / (ph["k3b_put"] * 1e-3) if ph.get("k3b_put") else None,
                      "device_put_gbs": alg / ph["k3b_put"] / 1e6 if ph.get("k3b_put") else None,
                      "device_get_gbs": alg / ph["k3b_get"] / 1e6 if ph.get("k3b_get") else None})

@@ -635,6 +635,7 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
   uint64_t h_tot[4] = {0, 0, 0, 0};
   bool direct = false;
   if (n) II2_CUDA_TRY(cudaMemcpyAsync(d_vals.p, vals, n * 4, cudaMemcpyHostToDevice, s));
+  ProfScope kscope("k3b_put_kernels", s);  // values resident -> serialised bitmap resident
   if (n && bm->inv_len && bm->inv_for_n == bm->n && n >= 1024) {
     // every value already in the dictionary (the usual Put over a known id universe): one probe
     // of the direct-address inverse per value; a miss means appends, which the general path
@@ -701,6 +702,7 @@ int ii2_bitmask_put(ii2_bitmask* bm, const uint32_t* vals, uint64_t n, uint8_t**
                                            (uint32_t)data_at);
     II2_LAUNCHED();
   }
+  kscope.end();
   uint8_t* h = static_cast<uint8_t*>(pinned_alloc(total + 8));
   if (!h) return II2_ERR_NOMEM;
   cudaError_t e = cudaMemcpyAsync(h, d_out.p, total, cudaMemcpyDeviceToHost, s);
@@ -735,6 +737,7 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
   II2_TRY(d_err.alloc_scratch(1, s));
   if (nenc) II2_CUDA_TRY(cudaMemcpyAsync(d_enc.p, enc, nenc, cudaMemcpyHostToDevice, s));
   II2_CUDA_TRY(cudaMemsetAsync(d_err.p, 0, 4, s));
+  ProfScope kscope("k3b_get_kernels", s);  // bytes resident -> values resident
   k_bm_get_parse<<<1, 1024, 0, s>>>(d_enc.p, nenc, d_meta.p, meta_cap, d_info.p);
   II2_LAUNCHED();
   uint64_t info[3] = {0, 0, 0};
@@ -755,6 +758,7 @@ int ii2_bitmask_get(const ii2_bitmask* bm, const uint8_t* enc, uint64_t nenc, ui
                                               bm->n, d_out.p, d_err.p);
     II2_LAUNCHED();
   }
+  kscope.end();
   II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 27, d_err.p, 4, cudaMemcpyDeviceToHost, s));
   uint32_t* h = static_cast<uint32_t*>(pinned_alloc(total * 4 + 4));
   if (!h) return II2_ERR_NOMEM;
