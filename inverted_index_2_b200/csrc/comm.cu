@@ -239,7 +239,7 @@ int read_gather_impl(const ii2_result* local, int root, ii2_result** out, cudaSt
     II2_NCCL_TRY(n.Recv(dst, bytes, ncclUint8, r, g_comm.comm, s));
     return II2_OK;
   };
-  II2_NCCL_TRY(n.GroupStart());
+  II2_NCCL_TRY(n.GroupStart());  // (closed below whatever happens inside: an open group poisons the communicator)
   int rc = II2_OK;
   for (int dst_rank = 0; dst_rank < world && rc == II2_OK; dst_rank++) {
     if (!(root < 0 || dst_rank == root) || dst_rank == rank) continue;
@@ -265,8 +265,11 @@ int read_gather_impl(const ii2_result* local, int root, ii2_result** out, cudaSt
       if (rc == II2_OK) rc = put(r, me ? l.post_off.p : nullptr, o.post_off.p + b.T[r], T * 8);
     }
   }
-  II2_NCCL_TRY(n.GroupEnd());
-  II2_TRY(rc);
+  {
+    const ncclResult_t ge = n.GroupEnd();
+    II2_TRY(rc);
+    II2_NCCL_TRY(ge);
+  }
   if (recv) {
     const unsigned grid = (unsigned)std::min<uint64_t>(div_up(res->T + 1, 256), 1184);
     k_rebase_parts<<<grid, 256, 0, s>>>(o.term_off.p, o.post_off.p, b);
@@ -315,21 +318,37 @@ int prefix_gather_impl(const ii2_prefix_out* local, int root, ii2_prefix_out* ou
   II2_TRY(d_mine.alloc_scratch(nv, s));
   if (nv) II2_CUDA_TRY(cudaMemcpyAsync(d_mine.p, local->values, nv * 4, cudaMemcpyHostToDevice, s));
   II2_NCCL_TRY(n.GroupStart());
-  for (int dst_rank = 0; dst_rank < world; dst_rank++) {
-    if (!(root < 0 || dst_rank == root) || dst_rank == rank || !nv) continue;
-    II2_NCCL_TRY(n.Send(d_mine.p, nv * 4, ncclUint8, dst_rank, g_comm.comm, s));
-  }
-  if (recv) {
-    for (int r = 0; r < world; r++) {
-      const uint64_t cnt = vbase[r + 1] - vbase[r];
-      if (!cnt) continue;
-      if (r == rank)
-        II2_CUDA_TRY(cudaMemcpyAsync(d_vals.p + vbase[r], d_mine.p, cnt * 4, cudaMemcpyDeviceToDevice, s));
+  {
+    int rc = II2_OK;
+    auto xfer = [&](bool send, void* p, uint64_t bytes, int peer) -> int {
+      if (send)
+        II2_NCCL_TRY(n.Send(p, bytes, ncclUint8, peer, g_comm.comm, s));
       else
-        II2_NCCL_TRY(n.Recv(d_vals.p + vbase[r], cnt * 4, ncclUint8, r, g_comm.comm, s));
+        II2_NCCL_TRY(n.Recv(p, bytes, ncclUint8, peer, g_comm.comm, s));
+      return II2_OK;
+    };
+    for (int dst_rank = 0; dst_rank < world && rc == II2_OK; dst_rank++) {
+      if (!(root < 0 || dst_rank == root) || dst_rank == rank || !nv) continue;
+      rc = xfer(true, d_mine.p, nv * 4, dst_rank);
     }
+    if (recv) {
+      for (int r = 0; r < world && rc == II2_OK; r++) {
+        const uint64_t cnt = vbase[r + 1] - vbase[r];
+        if (!cnt) continue;
+        if (r == rank) {
+          if (cudaMemcpyAsync(d_vals.p + vbase[r], d_mine.p, cnt * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+            set_last_error("prefix gather: local copy failed");
+            rc = II2_ERR_CUDA;
+          }
+        } else {
+          rc = xfer(false, d_vals.p + vbase[r], cnt * 4, r);
+        }
+      }
+    }
+    const ncclResult_t ge = n.GroupEnd();  // always closed
+    II2_TRY(rc);
+    II2_NCCL_TRY(ge);
   }
-  II2_NCCL_TRY(n.GroupEnd());
   std::unique_ptr<HostOwner> own(new HostOwner());
   out->n_prefixes = np;
   out->matched = own->alloc<uint8_t>((size_t)np + 1);
