@@ -323,8 +323,9 @@ def strong_leg(eng, a, world, rank, dist, torch, barrier):
     n_mine, n_terms = hi - lo, len(off) - 1
     total = int(min(a.strong_postings, a.strong_cap * world))
     mine = synth.gather_terms(tb, off, np.arange(lo, hi))
+    # (max_len 512: lists of ~31 values on average are not clipped, so the requested total is met)
     w = synth.make_workload(n_mine, a.segments, int(total * n_mine / n_terms), terms=mine,
-                            seed=0xC5 + rank, removed_frac=a.removed_frac)
+                            seed=0xC5 + rank, removed_frac=a.removed_frac, max_len=512)
     dsegs = [eng.upload(s) for s in w.segments]
     drem = eng.upload_removed(w.removed)
     # ---- build: 64 documents, each holding a random half of this rank's terms, unsorted
