@@ -1074,14 +1074,18 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs
 // the head of a Zipf distribution — used to take the multi-kernel global-memory path below: a
 // host round trip for the lengths, a gather pass, a tile sort pass and a finish pass over the
 // same values.  Here one CTA unions a term entirely in shared memory: sources gathered by
-// binary search over their length prefix, bitonic network, dedup + removed filter + block-scan
-// compaction, whole-CTA intcomp encode, one write of the result.  The CTAs pull terms from the
+// binary search over their length prefix, runs of 512 values sorted in registers (one warp
+// each, sort_warp_v<16>), up to three merge-path levels between two shared buffers, dedup +
+// removed filter + block-scan compaction, whole-CTA intcomp encode, one write of the result.  The CTAs pull terms from the
 // list K2b filled (a device-side counter: no host synchronisation); output space comes from two
 // bump cursors over regions sized by the input postings.  Longer terms go on to the `huge`
 // list for the path below.
 constexpr uint32_t MED_CAP = 4096;
 constexpr int MED_THREADS = 256;
-constexpr uint32_t MED_ENC_WORDS = MED_CAP + MED_CAP / 4 + 64;
+constexpr int MED_V = 16;                 // values per lane of a warp-sorted run
+constexpr uint32_t MED_RUN = 32 * MED_V;  // 512
+// Word of s_o that holds gathered value e: runs of MED_RUN values, one pad word per 16.
+__device__ __forceinline__ uint32_t med_run_slot(uint32_t e) { return e + (e >> 4); }
 
 struct MedArgs {
   const uint32_t* n_large;       // terms K2b deferred
@@ -1105,13 +1109,14 @@ struct MedArgs {
 };
 
 __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a) {
-  __shared__ uint32_t s_v[MED_CAP];            // gathered values -> sorted
-  __shared__ uint32_t s_o[MED_ENC_WORDS];      // survivors, then nothing else (encode reads them)
+  __shared__ uint32_t s_v[MED_CAP];                 // sorted runs / merge ping-pong / survivors
+  __shared__ uint32_t s_o[MED_CAP + MED_CAP / 16];  // gathered (padded runs) / ping-pong / survivors
   __shared__ uint32_t s_moff[kMaxSegs + 1];    // prefix of the source lengths
   __shared__ uint64_t s_ws[MED_THREADS / 32 + 2];
   __shared__ uint32_t s_stage[(MED_THREADS / 32) * intcomp::kStageWords];
   __shared__ uint32_t s_table[MED_CAP / 128 + 1];
   __shared__ uint32_t s_item;
+  __shared__ uint32_t s_cnt[MED_THREADS / 32];
   __shared__ unsigned long long s_pos[2];
   const uint32_t tid = threadIdx.x;
   for (;;) {
@@ -1144,38 +1149,186 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
     const uint32_t L = (uint32_t)run;
     if (tid == 0) s_moff[c] = L;
     __syncthreads();
-    // ---- gather
-    for (uint32_t e = tid; e < L; e += MED_THREADS) {
-      uint32_t lo = 0, hi = c;  // source holding element e
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (s_moff[mid + 1] <= e)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src_ptr[beg + lo]);
-      s_v[e] = __ldg(src + (e - s_moff[lo]));
-    }
-    __syncthreads();
+    // ---- gather.  A multi-source term lands in s_o as runs of MED_RUN values, every run padded
+    // (one word per 16) so that the blocked register load below is free of bank conflicts; the
+    // tail up to a power-of-two number of runs is filled with the sentinel 0xFFFFFFFF.
     const bool single = c == 1;  // passes through unsorted, duplicates kept (survey Q4)
+    uint32_t nrun = 1;
+    while (nrun * MED_RUN < L) nrun <<= 1;
+    const uint32_t Lpad = single ? L : nrun * MED_RUN;
+    // The source pointers wait in s_v (free until the runs are sorted) and every thread resolves
+    // eight elements before it stores any: eight value loads in flight instead of a chain of
+    // pointer load -> value load per element.
+    uint64_t* const s_ptr = reinterpret_cast<uint64_t*>(s_v);
+    const uint32_t* const src0 = reinterpret_cast<const uint32_t*>(a.src_ptr[beg]);
     if (!single) {
-      bitonic_sort_any(s_v, L, tid, (uint32_t)MED_THREADS, [](uint32_t x, uint32_t y) { return x < y; },
-                       [] { __syncthreads(); });
+      for (uint32_t i = tid; i < c; i += MED_THREADS) s_ptr[i] = a.src_ptr[beg + i];
       __syncthreads();
     }
-    // ---- dedup + removed filter + compaction
-    uint32_t outn = 0;
-    for (uint32_t e0 = 0; e0 < L; e0 += MED_THREADS) {
-      const uint32_t e = e0 + tid;
-      const bool valid = e < L;
-      const uint32_t x = valid ? s_v[e] : 0u;
-      const uint64_t keep =
-          (valid && (single || e == 0 || s_v[e - 1] != x) && !is_removed(a.rem, x)) ? 1u : 0u;
-      uint64_t tot;
-      const uint64_t ex = block_exclusive_scan(keep, s_ws, tot);
-      if (keep) s_o[outn + (uint32_t)ex] = x;
-      outn += (uint32_t)tot;
+    uint32_t top = 1;  // largest power of two below c
+    while (top * 2 < c) top <<= 1;
+    const bool by_source = !single && c * 8 <= L;  // sources of >= 8 values on average
+    if (by_source) {
+      // a warp per source, two sources (eight loads per lane) in flight; no search at all
+      const uint32_t w = warp_id(), lane = lane_id();
+      for (uint32_t e = L + tid; e < Lpad; e += MED_THREADS) s_o[med_run_slot(e)] = 0xFFFFFFFFu;
+      for (uint32_t j0 = 2 * w; j0 < c; j0 += 2 * (MED_THREADS / 32)) {
+        uint32_t x[2][4], o2[2], n2[2];
+        const uint32_t* p2[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const uint32_t j = j0 + q;
+          const bool in = j < c;
+          p2[q] = reinterpret_cast<const uint32_t*>(in ? s_ptr[j] : 0ull);
+          o2[q] = in ? s_moff[j] : 0u;
+          n2[q] = in ? s_moff[j + 1] - o2[q] : 0u;
+#pragma unroll
+          for (int t = 0; t < 4; t++) x[q][t] = t * 32 + lane < n2[q] ? __ldg(p2[q] + t * 32 + lane) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+#pragma unroll
+          for (int t = 0; t < 4; t++)
+            if (t * 32 + lane < n2[q]) s_o[med_run_slot(o2[q] + t * 32 + lane)] = x[q][t];
+          for (uint32_t i = 128 + lane; i < n2[q]; i += 32) s_o[med_run_slot(o2[q] + i)] = __ldg(p2[q] + i);
+        }
+      }
+    }
+    for (uint32_t e0 = tid; e0 < (by_source ? 0u : Lpad); e0 += 8 * MED_THREADS) {
+      uint32_t x[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const uint32_t e = e0 + q * MED_THREADS;
+        x[q] = 0xFFFFFFFFu;
+        if (e < L) {
+          if (single) {
+            x[q] = __ldg(src0 + e);
+          } else {
+            uint32_t lo = 0;  // last source whose first element is <= e (empty sources skipped)
+            for (uint32_t st = top; st; st >>= 1) {
+              const uint32_t m = lo + st;
+              if (m < c && s_moff[m] <= e) lo = m;
+            }
+            x[q] = __ldg(reinterpret_cast<const uint32_t*>(s_ptr[lo]) + (e - s_moff[lo]));
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const uint32_t e = e0 + q * MED_THREADS;
+        if (e < Lpad) {
+          if (single)
+            s_v[e] = x[q];
+          else
+            s_o[med_run_slot(e)] = x[q];
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t* fin = s_v;  // the sorted values end here, the survivors in the other buffer
+    uint32_t* oth = s_o;
+    if (!single) {
+      // every warp sorts one run in registers (16 values per lane) ...
+      const uint32_t w = warp_id(), lane = lane_id();
+      if (w < nrun) {
+        uint32_t v[MED_V];
+#pragma unroll
+        for (int r = 0; r < MED_V; r++) v[r] = s_o[med_run_slot(w * MED_RUN + lane * MED_V + r)];
+        const uint32_t at = w * MED_RUN, n = L > at ? min(L - at, MED_RUN) : 0u;
+        if (n > 1) sort_warp_v<MED_V>(v, lane, n);
+#pragma unroll
+        for (int r = 0; r < MED_V; r++) s_v[at + lane * MED_V + r] = v[r];
+      }
+      __syncthreads();
+      // ... then pairs of runs merge, every thread the Lpad / 256 outputs behind its diagonal
+      const uint32_t E = Lpad / MED_THREADS;  // 2, 4, 8 or 16
+      for (uint32_t R = MED_RUN; R < Lpad; R <<= 1) {
+        const uint32_t out0 = tid * E, pb = out0 & ~(2 * R - 1), d = out0 - pb;
+        const uint32_t* A = fin + pb;
+        const uint32_t* B = A + R;
+        uint32_t lo = d > R ? d - R : 0u, hi = min(d, R);
+        while (lo < hi) {  // how many of the first d outputs come from A (ties: A first)
+          const uint32_t mid = (lo + hi) >> 1;
+          if (A[mid] <= B[d - 1 - mid])
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        uint32_t i = lo, j = d - lo;
+        uint32_t xa = i < R ? A[i] : 0u, xb = j < R ? B[j] : 0u;
+        uint32_t* out = oth + out0;
+        for (uint32_t t = 0; t < E; t++) {
+          const bool ta = j >= R || (i < R && xa <= xb);
+          out[t] = ta ? xa : xb;
+          if (ta) {
+            i++;
+            xa = i < R ? A[i] : 0u;
+          } else {
+            j++;
+            xb = j < R ? B[j] : 0u;
+          }
+        }
+        __syncthreads();
+        uint32_t* const sw = fin;
+        fin = oth;
+        oth = sw;
+      }
+    }
+    // ---- dedup + removed filter + compaction.  Warp w owns a contiguous slice of up to 512
+    // values (16 rounds of 32): all its membership probes are issued before any is used, the
+    // keep flags stay in a register, positions come from ballots — two block barriers in all.
+    uint32_t outn;
+    {
+      const uint32_t w = warp_id(), lane = lane_id();
+      const uint32_t seg = ((L + MED_THREADS - 1) / MED_THREADS) * 32;  // values per warp
+      const uint32_t e_w = w * seg;
+      uint32_t keep = 0;  // bit i: the value of round i survives
+      if (a.rem.bitmap) {
+        const uint32_t nbits = (uint32_t)a.rem.bitmap_bits;
+        uint32_t word[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const uint32_t e = e_w + i * 32 + lane;
+          const bool in = (uint32_t)i * 32 < seg && e < L;
+          const uint32_t x = in ? fin[e] : 0xFFFFFFFFu;
+          word[i] = (in && x < nbits) ? __ldg(a.rem.bitmap + (x >> 5)) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const uint32_t e = e_w + i * 32 + lane;
+          const bool in = (uint32_t)i * 32 < seg && e < L;
+          const uint32_t x = in ? fin[e] : 0u;
+          const bool k = in && (single || e == 0 || fin[e - 1] != x) && !((word[i] >> (x & 31u)) & 1u);
+          keep |= k ? 1u << i : 0u;
+        }
+      } else {
+        for (uint32_t i = 0; i * 32 < seg; i++) {
+          const uint32_t e = e_w + i * 32 + lane;
+          const bool in = e < L;
+          const uint32_t x = in ? fin[e] : 0u;
+          const bool k = in && (single || e == 0 || fin[e - 1] != x) &&
+                         !(a.rem.n && is_removed_call(a.rem.sorted, a.rem.n, x));
+          keep |= k ? 1u << i : 0u;
+        }
+      }
+      const uint32_t mine = warp_sum(__popc(keep));
+      if (lane == 0) s_cnt[w] = mine;
+      __syncthreads();
+      uint32_t at = 0, tot = 0;
+#pragma unroll
+      for (int q = 0; q < MED_THREADS / 32; q++) {
+        const uint32_t cq = s_cnt[q];
+        at += (uint32_t)q < w ? cq : 0u;
+        tot += cq;
+      }
+      outn = tot;
+      const uint32_t lt = (1u << lane) - 1u;
+      for (uint32_t i = 0; i * 32 < seg; i++) {
+        const bool k = (keep >> i) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, k);
+        if (k) oth[at + __popc(bal & lt)] = fin[e_w + i * 32 + lane];
+        at += __popc(bal);
+      }
     }
     __syncthreads();
     // ---- output space, then the stream and the values
@@ -1186,13 +1339,13 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
     __syncthreads();
     uint32_t* const dst_post = a.out_post + s_pos[0];
     uint32_t* const dst_enc = a.out_enc + s_pos[1];
-    for (uint32_t e = tid; e < outn; e += MED_THREADS) dst_post[e] = s_o[e];
+    for (uint32_t e = tid; e < outn; e += MED_THREADS) dst_post[e] = oth[e];
     uint32_t enc = 0;
     if (a.want_enc && outn >= 128) {
-      enc = intcomp::enc_emit_cta(s_o, outn, dst_enc, s_table, s_stage, s_ws);
+      enc = intcomp::enc_emit_cta(oth, outn, dst_enc, s_table, s_stage, s_ws);
     } else if (a.want_enc && outn) {
       if (warp_id() == 0) {
-        const uint32_t e2 = intcomp::enc_emit_warp(s_o, outn, dst_enc, s_stage);
+        const uint32_t e2 = intcomp::enc_emit_warp(oth, outn, dst_enc, s_stage);
         if (lane_id() == 0) s_table[0] = e2;
       }
       __syncthreads();
@@ -1807,7 +1960,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       m.out_post = u.med_post.p;
       m.out_enc = u.med_enc.p;
       m.out_cursor = med_cursor.p;
-      k2_medium_kernel<<<kNumSMs * 4, MED_THREADS, 0, s>>>(m);
+      k2_medium_kernel<<<kNumSMs * 5, MED_THREADS, 0, s>>>(m);
       II2_LAUNCHED();
     }
     return II2_OK;

@@ -18,8 +18,10 @@ ap.add_argument("--terms", type=int, default=1_000_000)
 ap.add_argument("--segments", type=int, default=64)
 ap.add_argument("--postings", type=int, default=100_000_000)
 ap.add_argument("--presence", type=float, default=0.5)
+ap.add_argument("--max-len", type=int, default=64)
 a = ap.parse_args()
-w = synth.make_workload(a.terms, a.segments, a.postings, removed_frac=0.05, presence=a.presence)
+w = synth.make_workload(a.terms, a.segments, a.postings, removed_frac=0.05, presence=a.presence,
+                        max_len=a.max_len)
 # --libs "lib1:b1+b2,lib2:b3" (a lib named "default" = the in-tree build)
 specs = [x for x in a.libs.split(",") if x] or ["default"]
 for spec in specs:

@@ -248,6 +248,33 @@ def test_mid_and_medium_terms(engine, orc, merge_path):
         assert_read_equal(engine.read_range(segs, b"t00003", b"v"), orc.read_range(segs, b"t00003", b"v"))
 
 
+def test_medium_terms_of_many_short_sources(engine, orc, merge_path):
+    """CTA-per-term union, the other gather: a term held by hundreds of segments with a few
+    values each (sources located by search instead of a warp per source), terms that end exactly
+    on a run / merge boundary of the shared-memory sort (512, 1024, 2048, 4096 values), empty
+    leading and trailing sources, heavy overlap between sources."""
+    rng = np.random.default_rng(77)
+    nseg = 420
+    per_seg = [[] for _ in range(nseg)]
+    plans = [(b"a_1100", 1100, 300), (b"b_1536", 1536, 420), (b"c_2048", 2048, 400), (b"d_2049", 2049, 257),
+             (b"e_3000", 3000, 420), (b"f_4096", 4096, 420), (b"g_1025", 1025, 129), (b"h_overlap", 2600, 420)]
+    for name, total, k in plans:
+        cuts = np.sort(rng.integers(0, total + 1, size=k - 1))
+        lens = np.diff(np.concatenate([[0], cuts, [total]]))
+        lens[0] = 0 if name != b"g_1025" else lens[0]   # an empty list in a segment that has the term
+        uni = 1 << 12 if name == b"h_overlap" else 1 << 22
+        for s_i, n in zip(rng.permutation(nseg)[:k], lens):
+            vals = np.unique(rng.integers(0, uni, size=int(n), dtype=np.int64)).tolist()
+            per_seg[int(s_i)].append((name, vals))
+    for s_i in range(nseg):   # every segment needs at least one term
+        per_seg[s_i].append((b"z_pad%03d" % (s_i % 7), [s_i, s_i + 1]))
+    segs = [FlatSegment.from_items(sorted(x)) for x in per_seg]
+    removed = np.unique(rng.integers(0, 1 << 22, size=40000, dtype=np.int64)).astype(np.uint32)
+    assert_merge_equal(engine.merge(segs, removed, decoded=True), orc.merge(segs, removed, decoded=True))
+    assert_merge_equal(engine.merge(segs, removed, decoded=False), orc.merge(segs, removed, decoded=False),
+                       decoded=False)
+
+
 def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
     """ii2_merge over host buffers cuts the term space into ranges and overlaps staging with
     the kernels; the concatenated result is the single-shot result, also when the output
