@@ -887,6 +887,9 @@ __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(co
 constexpr uint32_t MW_CAP = 1024;
 constexpr int MW_V = 32;
 constexpr int MW_WARPS = 4;
+#ifndef MW_MIN_CTAS
+#define MW_MIN_CTAS 5  // 96 registers (6 = 80 registers measured no faster)
+#endif
 constexpr uint32_t MW_BUF = MW_CAP + MW_CAP / 32 + 8;   // one pad word per 32 values (bank-conflict-free blocked loads)
 constexpr uint32_t MW_EBUF = 3 + 8 * 129 + 1 + 1 + 6;   // enc_bound(1024) (also holds the source prefix: c + 1 <= 1025 entries)
 static_assert(MW_EBUF >= kMaxSegs + 1, "source prefix fits the stream buffer");
@@ -912,7 +915,7 @@ struct MwArgs {
   unsigned long long* out_cursor;  // [0] postings, [1] words
 };
 
-__global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs a) {
+__global__ void __launch_bounds__(MW_WARPS * 32, MW_MIN_CTAS) k2_mwarp_kernel(const MwArgs a) {
   __shared__ __align__(16) uint32_t s_buf[MW_WARPS][MW_BUF];
   __shared__ __align__(16) uint32_t s_enc[MW_WARPS][MW_EBUF];
   const unsigned lane = lane_id(), warp = warp_id();
@@ -948,8 +951,9 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs
     const uint32_t L = run;
     __syncwarp();
     // ---- gather (element e lives at e + e / 32: padded blocks).  The lanes fetch 32 source
-    // descriptors at once; the sources are then copied four at a time, their loads issued before
-    // any store, so a term of 32 sources costs ~9 memory round trips instead of 64 dependent ones
+    // descriptors at once; the sources are then copied four at a time (64 values of each), their loads
+    // issued before any store, so a term of 32 sources costs ~9 memory round trips instead of 64
+    // dependent ones
     for (uint32_t base = 0; base < c; base += 32) {
       const uint32_t j = base + lane;
       uint64_t my_p = 0;
@@ -961,7 +965,7 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs
       }
       const uint32_t cnt = min(32u, c - base);
       for (uint32_t j0 = 0; j0 < cnt; j0 += 4) {
-        uint32_t x[4], o4[4], n4[4];
+        uint32_t x[4][2], o4[4], n4[4];
         const uint32_t* p4[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -969,17 +973,28 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs
           p4[q] = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, my_p, sl));
           o4[q] = __shfl_sync(0xffffffffu, my_o, sl);
           n4[q] = j0 + q < cnt ? __shfl_sync(0xffffffffu, my_n, sl) : 0u;
-          x[q] = lane < n4[q] ? __ldg(p4[q] + lane) : 0u;
+          x[q][0] = lane < n4[q] ? __ldg(p4[q] + lane) : 0u;
+          x[q][1] = 32 + lane < n4[q] ? __ldg(p4[q] + 32 + lane) : 0u;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          if (lane < n4[q]) {
-            const uint32_t e = o4[q] + lane;
-            buf[e + (e >> 5)] = x[q];
-          }
-          for (uint32_t t = 32 + lane; t < n4[q]; t += 32) {  // sources of more than 32 values
-            const uint32_t e = o4[q] + t;
-            buf[e + (e >> 5)] = __ldg(p4[q] + t);
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+            if (h * 32 + lane < n4[q]) {
+              const uint32_t e = o4[q] + h * 32 + lane;
+              buf[e + (e >> 5)] = x[q][h];
+            }
+          // sources of more than 64 values: four loads in flight per lane
+          for (uint32_t t0 = 64 + lane; t0 < n4[q]; t0 += 128) {
+            uint32_t y[4];
+#pragma unroll
+            for (int h = 0; h < 4; h++) y[h] = t0 + h * 32 < n4[q] ? __ldg(p4[q] + t0 + h * 32) : 0u;
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+              if (t0 + h * 32 < n4[q]) {
+                const uint32_t e = o4[q] + t0 + h * 32;
+                buf[e + (e >> 5)] = y[h];
+              }
           }
         }
       }
@@ -1074,9 +1089,10 @@ __global__ void __launch_bounds__(MW_WARPS * 32, 3) k2_mwarp_kernel(const MwArgs
 // the head of a Zipf distribution — used to take the multi-kernel global-memory path below: a
 // host round trip for the lengths, a gather pass, a tile sort pass and a finish pass over the
 // same values.  Here one CTA unions a term entirely in shared memory: sources gathered by
-// binary search over their length prefix, runs of 512 values sorted in registers (one warp
-// each, sort_warp_v<16>), up to three merge-path levels between two shared buffers, dedup +
-// removed filter + block-scan compaction, whole-CTA intcomp encode, one write of the result.  The CTAs pull terms from the
+// binary search over their length prefix (or a warp per source), runs of 512 values sorted in
+// registers (one warp each, sort_warp_v<16>), up to three bitonic merge levels whose cross-warp
+// stages go through shared memory, dedup + removed filter + compaction from the registers,
+// whole-CTA intcomp encode, one write of the result.  The CTAs pull terms from the
 // list K2b filled (a device-side counter: no host synchronisation); output space comes from two
 // bump cursors over regions sized by the input postings.  Longer terms go on to the `huge`
 // list for the path below.
@@ -1108,7 +1124,7 @@ struct MedArgs {
   unsigned long long* out_cursor;  // [0] postings, [1] words
 };
 
-__global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a) {
+__global__ void __launch_bounds__(MED_THREADS, 5) k2_medium_kernel(const MedArgs a) {
   __shared__ uint32_t s_v[MED_CAP];                 // sorted runs / merge ping-pong / survivors
   __shared__ uint32_t s_o[MED_CAP + MED_CAP / 16];  // gathered (padded runs) / ping-pong / survivors
   __shared__ uint32_t s_moff[kMaxSegs + 1];    // prefix of the source lengths
@@ -1117,6 +1133,7 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
   __shared__ uint32_t s_table[MED_CAP / 128 + 1];
   __shared__ uint32_t s_item;
   __shared__ uint32_t s_cnt[MED_THREADS / 32];
+  __shared__ uint32_t s_last[MED_THREADS / 32];
   __shared__ unsigned long long s_pos[2];
   const uint32_t tid = threadIdx.x;
   for (;;) {
@@ -1149,14 +1166,15 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
     const uint32_t L = (uint32_t)run;
     if (tid == 0) s_moff[c] = L;
     __syncthreads();
-    // ---- gather.  A multi-source term lands in s_o as runs of MED_RUN values, every run padded
-    // (one word per 16) so that the blocked register load below is free of bank conflicts; the
-    // tail up to a power-of-two number of runs is filled with the sentinel 0xFFFFFFFF.
+    // ---- gather.  The term lands in s_o as runs of MED_RUN values (one per warp), every run
+    // padded (one word per 16) so that the blocked register load below is free of bank
+    // conflicts; the tail up to a power-of-two number of runs is the sentinel 0xFFFFFFFF.
     const bool single = c == 1;  // passes through unsorted, duplicates kept (survey Q4)
+    const uint32_t w = warp_id(), lane = lane_id();
     uint32_t nrun = 1;
     while (nrun * MED_RUN < L) nrun <<= 1;
-    const uint32_t Lpad = single ? L : nrun * MED_RUN;
-    // The source pointers wait in s_v (free until the runs are sorted) and every thread resolves
+    const uint32_t Lpad = nrun * MED_RUN;
+    // The source pointers wait in s_v (free until the first exchange) and every thread resolves
     // eight elements before it stores any: eight value loads in flight instead of a chain of
     // pointer load -> value load per element.
     uint64_t* const s_ptr = reinterpret_cast<uint64_t*>(s_v);
@@ -1170,7 +1188,6 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
     const bool by_source = !single && c * 8 <= L;  // sources of >= 8 values on average
     if (by_source) {
       // a warp per source, two sources (eight loads per lane) in flight; no search at all
-      const uint32_t w = warp_id(), lane = lane_id();
       for (uint32_t e = L + tid; e < Lpad; e += MED_THREADS) s_o[med_run_slot(e)] = 0xFFFFFFFFu;
       for (uint32_t j0 = 2 * w; j0 < c; j0 += 2 * (MED_THREADS / 32)) {
         uint32_t x[2][4], o2[2], n2[2];
@@ -1216,105 +1233,93 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         const uint32_t e = e0 + q * MED_THREADS;
-        if (e < Lpad) {
-          if (single)
-            s_v[e] = x[q];
-          else
-            s_o[med_run_slot(e)] = x[q];
-        }
+        if (e < Lpad) s_o[med_run_slot(e)] = x[q];
       }
     }
     __syncthreads();
-    uint32_t* fin = s_v;  // the sorted values end here, the survivors in the other buffer
-    uint32_t* oth = s_o;
-    if (!single) {
-      // every warp sorts one run in registers (16 values per lane) ...
-      const uint32_t w = warp_id(), lane = lane_id();
-      if (w < nrun) {
-        uint32_t v[MED_V];
+    // ---- sort.  From here to the compaction the values live in registers: warp w holds run w,
+    // lane l its values 16 l .. 16 l + 15.  Each run is sorted by its warp (sort_warp_v<16>);
+    // then 1 / 2 / 3 bitonic merge levels double the sorted blocks up to Lpad.  A level starts
+    // with the stages whose partner sits in another warp — the flip (value e against the
+    // mirrored value of the partner run), then half-cleaners at warp distances — exchanged
+    // through shared memory in a transposed, conflict-free layout, alternating between the two
+    // buffers so that one barrier per stage is enough; the rest of the level is shuffles and
+    // register compare-exchanges (clean_warp_v).
+    const bool active = w < nrun;
+    uint32_t v[MED_V];
 #pragma unroll
-        for (int r = 0; r < MED_V; r++) v[r] = s_o[med_run_slot(w * MED_RUN + lane * MED_V + r)];
+    for (int r = 0; r < MED_V; r++)
+      v[r] = active ? s_o[med_run_slot(w * MED_RUN + lane * MED_V + r)] : 0xFFFFFFFFu;
+    if (!single) {
+      {
         const uint32_t at = w * MED_RUN, n = L > at ? min(L - at, MED_RUN) : 0u;
         if (n > 1) sort_warp_v<MED_V>(v, lane, n);
-#pragma unroll
-        for (int r = 0; r < MED_V; r++) s_v[at + lane * MED_V + r] = v[r];
       }
-      __syncthreads();
-      // ... then pairs of runs merge, every thread the Lpad / 256 outputs behind its diagonal
-      const uint32_t E = Lpad / MED_THREADS;  // 2, 4, 8 or 16
-      for (uint32_t R = MED_RUN; R < Lpad; R <<= 1) {
-        const uint32_t out0 = tid * E, pb = out0 & ~(2 * R - 1), d = out0 - pb;
-        const uint32_t* A = fin + pb;
-        const uint32_t* B = A + R;
-        uint32_t lo = d > R ? d - R : 0u, hi = min(d, R);
-        while (lo < hi) {  // how many of the first d outputs come from A (ties: A first)
-          const uint32_t mid = (lo + hi) >> 1;
-          if (A[mid] <= B[d - 1 - mid])
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        uint32_t i = lo, j = d - lo;
-        uint32_t xa = i < R ? A[i] : 0u, xb = j < R ? B[j] : 0u;
-        uint32_t* out = oth + out0;
-        for (uint32_t t = 0; t < E; t++) {
-          const bool ta = j >= R || (i < R && xa <= xb);
-          out[t] = ta ? xa : xb;
-          if (ta) {
-            i++;
-            xa = i < R ? A[i] : 0u;
-          } else {
-            j++;
-            xb = j < R ? B[j] : 0u;
+      uint32_t stage = 0;
+      for (uint32_t nw = 2; nw <= nrun; nw <<= 1) {  // warps per sorted block after this level
+        for (uint32_t dw = nw; dw >= 2; dw >>= 1) {  // dw == nw: the flip; below: half-cleaners
+          const bool flip = dw == nw;
+          uint32_t* const X = (stage++ & 1u) ? s_o : s_v;
+          if (active) {
+#pragma unroll
+            for (int r = 0; r < MED_V; r++) X[w * MED_RUN + r * 32 + lane] = v[r];
+          }
+          __syncthreads();
+          if (active) {
+            const uint32_t pw = flip ? (w ^ (nw - 1)) : (w ^ (dw >> 1));
+            const bool lower = (w & (dw >> 1)) == 0;
+            const uint32_t* const P = X + pw * MED_RUN;
+#pragma unroll
+            for (int r = 0; r < MED_V; r++) {
+              const uint32_t o = flip ? P[(MED_V - 1 - r) * 32 + (31 - lane)] : P[r * 32 + lane];
+              v[r] = ((v[r] < o) == lower) ? v[r] : o;
+            }
           }
         }
-        __syncthreads();
-        uint32_t* const sw = fin;
-        fin = oth;
-        oth = sw;
+        if (active) clean_warp_v<MED_V>(v, lane);
       }
     }
-    // ---- dedup + removed filter + compaction.  Warp w owns a contiguous slice of up to 512
-    // values (16 rounds of 32): all its membership probes are issued before any is used, the
-    // keep flags stay in a register, positions come from ballots — two block barriers in all.
+    // ---- dedup + removed filter + compaction, still from the registers: sixteen membership
+    // probes per lane issued eight at a time, keep flags in a register, positions from one warp
+    // scan + the warps' totals; the survivors end in s_v.
     uint32_t outn;
     {
-      const uint32_t w = warp_id(), lane = lane_id();
-      const uint32_t seg = ((L + MED_THREADS - 1) / MED_THREADS) * 32;  // values per warp
-      const uint32_t e_w = w * seg;
-      uint32_t keep = 0;  // bit i: the value of round i survives
+      if (lane == 31) s_last[w] = v[MED_V - 1];
+      __syncthreads();  // (also: every partner has read the last exchange buffer)
+      const uint32_t e_l = w * MED_RUN + lane * MED_V;  // index of v[0]
+      uint32_t keep = 0;
       if (a.rem.bitmap) {
         const uint32_t nbits = (uint32_t)a.rem.bitmap_bits;
-        uint32_t word[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const uint32_t e = e_w + i * 32 + lane;
-          const bool in = (uint32_t)i * 32 < seg && e < L;
-          const uint32_t x = in ? fin[e] : 0xFFFFFFFFu;
-          word[i] = (in && x < nbits) ? __ldg(a.rem.bitmap + (x >> 5)) : 0u;
-        }
+        for (int r0 = 0; r0 < MED_V; r0 += 8) {
+          uint32_t word[8];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const uint32_t e = e_w + i * 32 + lane;
-          const bool in = (uint32_t)i * 32 < seg && e < L;
-          const uint32_t x = in ? fin[e] : 0u;
-          const bool k = in && (single || e == 0 || fin[e - 1] != x) && !((word[i] >> (x & 31u)) & 1u);
-          keep |= k ? 1u << i : 0u;
+          for (int r = 0; r < 8; r++) {
+            const bool probe = e_l + r0 + r < L && v[r0 + r] < nbits;
+            word[r] = probe ? __ldg(a.rem.bitmap + (v[r0 + r] >> 5)) : 0u;
+          }
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+            keep |= (e_l + r0 + r < L && !((word[r] >> (v[r0 + r] & 31u)) & 1u)) ? 1u << (r0 + r) : 0u;
         }
       } else {
-        for (uint32_t i = 0; i * 32 < seg; i++) {
-          const uint32_t e = e_w + i * 32 + lane;
-          const bool in = e < L;
-          const uint32_t x = in ? fin[e] : 0u;
-          const bool k = in && (single || e == 0 || fin[e - 1] != x) &&
-                         !(a.rem.n && is_removed_call(a.rem.sorted, a.rem.n, x));
-          keep |= k ? 1u << i : 0u;
-        }
+#pragma unroll
+        for (int r = 0; r < MED_V; r++)
+          if (e_l + r < L && !(a.rem.n && is_removed_call(a.rem.sorted, a.rem.n, v[r]))) keep |= 1u << r;
       }
-      const uint32_t mine = warp_sum(__popc(keep));
-      if (lane == 0) s_cnt[w] = mine;
+      uint32_t up = __shfl_up_sync(0xffffffffu, v[MED_V - 1], 1);  // the value before v[0]
+      if (lane == 0 && w > 0) up = s_last[w - 1];
+      if (!single) {
+        if (e_l > 0 && up == v[0]) keep &= ~1u;
+#pragma unroll
+        for (int r = 1; r < MED_V; r++)
+          if (v[r] == v[r - 1]) keep &= ~(1u << r);
+      }
+      const uint32_t cnt = __popc(keep);
+      const uint32_t inc = warp_inclusive_scan(cnt);
+      if (lane == 31) s_cnt[w] = inc;
       __syncthreads();
-      uint32_t at = 0, tot = 0;
+      uint32_t at = inc - cnt, tot = 0;
 #pragma unroll
       for (int q = 0; q < MED_THREADS / 32; q++) {
         const uint32_t cq = s_cnt[q];
@@ -1322,15 +1327,16 @@ __global__ void __launch_bounds__(MED_THREADS) k2_medium_kernel(const MedArgs a)
         tot += cq;
       }
       outn = tot;
-      const uint32_t lt = (1u << lane) - 1u;
-      for (uint32_t i = 0; i * 32 < seg; i++) {
-        const bool k = (keep >> i) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, k);
-        if (k) oth[at + __popc(bal & lt)] = fin[e_w + i * 32 + lane];
-        at += __popc(bal);
+      uint32_t* dst = s_v + at;
+#pragma unroll
+      for (int r = 0; r < MED_V; r++) {
+        const bool k = (keep >> r) & 1u;
+        if (k) *dst = v[r];
+        dst += k ? 1 : 0;
       }
     }
     __syncthreads();
+    uint32_t* const oth = s_v;
     // ---- output space, then the stream and the values
     if (tid == 0) {
       s_pos[0] = atomicAdd(&a.out_cursor[0], (unsigned long long)outn);
@@ -1938,7 +1944,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       w2.out_post = u.med_post.p;
       w2.out_enc = u.med_enc.p;
       w2.out_cursor = med_cursor.p;
-      k2_mwarp_kernel<<<kNumSMs * 4, MW_WARPS * 32, 0, s>>>(w2);
+      k2_mwarp_kernel<<<kNumSMs * (MW_MIN_CTAS < 4 ? 4 : MW_MIN_CTAS), MW_WARPS * 32, 0, s>>>(w2);
       II2_LAUNCHED();
       MedArgs m;
       m.n_large = n_mid;

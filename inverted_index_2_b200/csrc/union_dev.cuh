@@ -152,6 +152,22 @@ __device__ __forceinline__ void sort_warp_v(uint32_t (&v)[V], unsigned lane, uin
   }
 }
 
+// The part of a merge level that stays inside a warp once the cross-warp stages are done
+// (k12_union.cu, k2_medium_kernel): half-cleaners at lane distances 16 .. 1, then the local ones.
+template <int V>
+__device__ __forceinline__ void clean_warp_v(uint32_t (&v)[V], unsigned lane) {
+#pragma unroll 1
+  for (unsigned dist = 16; dist >= 1; dist >>= 1) {
+    const bool lower = (lane & dist) == 0;
+#pragma unroll
+    for (int r = 0; r < V; r++) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], dist);
+      v[r] = ((v[r] < o) == lower) ? v[r] : o;
+    }
+  }
+  clean_local_v<V>(v);
+}
+
 // Union of the term of this lane's group: L gathered values at `slot` (global) -> sorted
 // (slices.Sort) and deduped (slices.Compact) when the term has >= 2 sources (a single-source
 // term passes through in source order, duplicates kept: survey Q4) -> removed filter ->
