@@ -1085,7 +1085,7 @@ __global__ void __launch_bounds__(MW_WARPS * 32, MW_MIN_CTAS) k2_mwarp_kernel(co
 }
 
 // ---------------------------------------------------------------- medium terms (one CTA each)
-// Terms of REG_CAP < L <= MED_CAP values — every term of an index with ~1000 postings per term,
+// Terms of REG_CAP < L <= 4096 values — every term of an index with ~1000 postings per term,
 // the head of a Zipf distribution — used to take the multi-kernel global-memory path below: a
 // host round trip for the lengths, a gather pass, a tile sort pass and a finish pass over the
 // same values.  Here one CTA unions a term entirely in shared memory: sources gathered by
@@ -1096,8 +1096,6 @@ __global__ void __launch_bounds__(MW_WARPS * 32, MW_MIN_CTAS) k2_mwarp_kernel(co
 // list K2b filled (a device-side counter: no host synchronisation); output space comes from two
 // bump cursors over regions sized by the input postings.  Longer terms go on to the `huge`
 // list for the path below.
-constexpr uint32_t MED_CAP = 4096;
-constexpr int MED_THREADS = 256;
 constexpr int MED_V = 16;                 // values per lane of a warp-sorted run
 constexpr uint32_t MED_RUN = 32 * MED_V;  // 512
 // Word of s_o that holds gathered value e: runs of MED_RUN values, one pad word per 16.
@@ -1124,7 +1122,10 @@ struct MedArgs {
   unsigned long long* out_cursor;  // [0] postings, [1] words
 };
 
-__global__ void __launch_bounds__(MED_THREADS, 5) k2_medium_kernel(const MedArgs a) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 8 : 5) k2_medium_kernel(const MedArgs a) {
+  constexpr int MED_THREADS = NW * 32;
+  constexpr uint32_t MED_CAP = NW * MED_RUN;  // values one CTA of NW warps unions
   __shared__ uint32_t s_v[MED_CAP];                 // sorted runs / merge ping-pong / survivors
   __shared__ uint32_t s_o[MED_CAP + MED_CAP / 16];  // gathered (padded runs) / ping-pong / survivors
   __shared__ uint32_t s_moff[kMaxSegs + 1];    // prefix of the source lengths
@@ -1830,14 +1831,17 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   // gather slots of the light terms (K1b -> K2b); the decoded union replaces them in place
   II2_TRY(u.tmp_post.alloc_scratch(n_in, s, 16));
   const uint32_t large_cap = (uint32_t)std::min<uint64_t>(N, n_in / REG_CAP + 1);
-  // [6][large_cap]: K2b's list (rec, bucket), the list the warp kernel passes on, the huge list
+  // [8][large_cap]: K2b's list (rec, bucket), the huge list, the lists the warp kernel and the
+  // four-warp CTA kernel pass on
   DevBuf<uint32_t> large_u32;
-  II2_TRY(large_u32.alloc_scratch(6 * (size_t)large_cap, s));
+  II2_TRY(large_u32.alloc_scratch(8 * (size_t)large_cap, s));
   // mid / medium terms (k2_mwarp_kernel, k2_medium_kernel): unions and streams bump-allocated
-  // [0] postings, [1] words, [2] work cursors (2 x u32), [3] terms passed on by the warp kernel
+  // [0] postings, [1] words, [2] work cursors (2 x u32: eight-warp CTA kernel, warp kernel),
+  // [3] terms passed on (2 x u32: by the warp kernel, by the four-warp CTA kernel),
+  // [4] work cursor of the four-warp CTA kernel
   DevBuf<unsigned long long> med_cursor;
-  II2_TRY(med_cursor.alloc_scratch(4, s));
-  II2_CUDA_TRY(cudaMemsetAsync(med_cursor.p, 0, 32, s));
+  II2_TRY(med_cursor.alloc_scratch(8, s));
+  II2_CUDA_TRY(cudaMemsetAsync(med_cursor.p, 0, 64, s));
   II2_TRY(u.med_post.alloc_scratch(n_in, s, 16));
   if (want_enc) II2_TRY(u.med_enc.alloc_scratch(n_in + n_in / 4 + 16ull * large_cap + 64, s, 16));
   II2_CUDA_TRY(cudaMemsetAsync(u.totals.p, 0, 64, s));
@@ -1918,7 +1922,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
         k2b_union_kernel<false><<<grid, K2B_THREADS, 0, s>>>(a2);
       II2_LAUNCHED();
     }
-    {  // the terms K2b deferred: up to MW_CAP values one warp each, up to MED_CAP one CTA each;
+    {  // the terms K2b deferred: up to MW_CAP values one warp each, up to 4096 one CTA each;
        // device-side work lists, no host round trip
       ProfScope scope("k2_medium", s);
       uint32_t* const mid_rec = large_u32.p + 4 * (size_t)large_cap;
@@ -1946,6 +1950,11 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       w2.out_cursor = med_cursor.p;
       k2_mwarp_kernel<<<kNumSMs * (MW_MIN_CTAS < 4 ? 4 : MW_MIN_CTAS), MW_WARPS * 32, 0, s>>>(w2);
       II2_LAUNCHED();
+      // one CTA per term: four warps up to 2048 values (eight CTAs per SM), eight warps up to
+      // 4096 (five per SM); each passes the longer terms on through its own list
+      uint32_t* const mid2_rec = large_u32.p + 6 * (size_t)large_cap;
+      uint32_t* const mid2_bucket = large_u32.p + 7 * (size_t)large_cap;
+      uint32_t* const n_mid2 = reinterpret_cast<uint32_t*>(med_cursor.p + 3) + 1;
       MedArgs m;
       m.n_large = n_mid;
       m.large_rec = mid_rec;
@@ -1959,14 +1968,23 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       m.keep_empty = keep_empty ? 1 : 0;
       m.bk_raw = u.bk_raw.p;
       m.nb1 = B + 1;
+      m.cursor = reinterpret_cast<uint32_t*>(med_cursor.p + 4);
+      m.n_huge = n_mid2;
+      m.huge_rec = mid2_rec;
+      m.huge_bucket = mid2_bucket;
+      m.out_post = u.med_post.p;
+      m.out_enc = u.med_enc.p;
+      m.out_cursor = med_cursor.p;
+      k2_medium_kernel<4><<<kNumSMs * 8, 4 * 32, 0, s>>>(m);
+      II2_LAUNCHED();
+      m.n_large = n_mid2;
+      m.large_rec = mid2_rec;
+      m.large_bucket = mid2_bucket;
       m.cursor = reinterpret_cast<uint32_t*>(med_cursor.p + 2);
       m.n_huge = a2.n_large + 1;  // the high half of totals[6]
       m.huge_rec = large_u32.p + 2 * (size_t)large_cap;
       m.huge_bucket = large_u32.p + 3 * (size_t)large_cap;
-      m.out_post = u.med_post.p;
-      m.out_enc = u.med_enc.p;
-      m.out_cursor = med_cursor.p;
-      k2_medium_kernel<<<kNumSMs * 5, MED_THREADS, 0, s>>>(m);
+      k2_medium_kernel<8><<<kNumSMs * 5, 8 * 32, 0, s>>>(m);
       II2_LAUNCHED();
     }
     return II2_OK;
@@ -2028,7 +2046,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     II2_TRY(general(B, nullptr));
     II2_TRY(totals());
   }
-  const uint32_t h_nl = (uint32_t)(h_tot[6] >> 32);  // terms the medium kernel passed on (> MED_CAP values)
+  const uint32_t h_nl = (uint32_t)(h_tot[6] >> 32);  // terms the CTA kernels passed on (> 4096 values)
   if (h_nl > 0) {
     ProfScope scope("k2_large", s);
     LargeArgs la;
