@@ -543,10 +543,10 @@ def run_ours(a):
         "k6_emit": 32 * n_groups + val_size + t_out_bytes + val_size + t_out_bytes + 12 * t_out,
     }
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture
-    # of this command (profiles/r02t_ncu_full_metrics.csv; the fused kernel:
+    # of this command (profiles/r03_ncu_full_metrics.csv; the fused kernel:
     # profiles/r02_ncu_k12f_2cta_metrics.csv); only valid for the default workload
-    ncu_traffic = {"k12f_bucket": 1230.4e6 + 253.7e6, "k1b_group": 1279.2e6 + 457.7e6,
-                   "k2b_union": 493.7e6 + 306.9e6, "k6_emit": 521.5e6 + 298.7e6}
+    ncu_traffic = {"k12f_bucket": 1230.4e6 + 253.7e6, "k1b_group": 1278.1e6 + 456.8e6,
+                   "k2b_union": 493.7e6 + 308.4e6, "k6_emit": 521.4e6 + 297.9e6}
     traffic_src = {"k12f_bucket": "ncu --set full, profiles/r02_ncu_k12f_2cta_metrics.csv"}
     default_workload = (a.terms, a.segments, a.postings, a.removed_frac) == \
         (1_000_000, 64, 100_000_000, 0.05) and world == 1
@@ -562,7 +562,7 @@ def run_ours(a):
                     "unit": "GB/s", "frac": ach / peak,
                     "traffic": ncu_traffic.get(top["name"]) if default_workload else None,
                     "traffic_source": traffic_src.get(top["name"],
-                                                      "ncu --set full, profiles/r02t_ncu_full_metrics.csv"),
+                                                      "ncu --set full, profiles/r03_ncu_full_metrics.csv"),
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms}
     pipeline_bytes = synth.algorithmic_bytes(n_in, n_out, t_in, t_in_bytes, a.segments, t_out,
