@@ -223,59 +223,62 @@ k_removed_check(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t* __res
 // One WARP per segment searches 32 ways at a time (warp_partition_point: 4 rounds for 500 k
 // terms instead of the 19 dependent probes of a binary search — a small read spent 50 of its
 // 270 us there).  The last CTA to finish turns the window widths into instance bases.
+// The kernel is the whole host <-> device exchange of the step (a small read is bound by the
+// number of launches, not by their work): it reads the segment table and the bounds straight
+// from the caller's pinned block, writes the device copy of the table the later kernels use,
+// and puts the windows and the postings inside them back into the pinned block.
+constexpr uint32_t kBoundsSmem = 4096;
 __global__ void __launch_bounds__(256)
-k4_windows(SegDesc* segs, int k, const uint8_t* __restrict__ bounds, uint32_t minlen,
-           int has_min, uint32_t maxlen, int has_max, uint32_t* n_total) {
+k4_windows(const SegDesc* h_segs, SegDesc* d_segs, SegDesc* h_out,
+           uint64_t* __restrict__ h_post, int k, const uint8_t* __restrict__ bounds,
+           uint32_t minlen, int has_min, uint32_t maxlen, int has_max, uint32_t* ticket) {
+  pdl_enter();
   __shared__ uint32_t ws[256 / 32 + 2];
-  __shared__ uint64_t ws64[256 / 32 + 2];
+  __shared__ __align__(16) uint8_t s_bounds[kBoundsSmem];
   __shared__ bool s_last;
+  const uint8_t* bnd = bounds;
+  if (minlen + maxlen <= kBoundsSmem) {  // (longer bounds were uploaded: read them in place)
+    for (uint32_t i = threadIdx.x; i < minlen + maxlen; i += 256) s_bounds[i] = bounds[i];
+    bnd = s_bounds;
+    __syncthreads();
+  }
   const int s = blockIdx.x * 8 + warp_id();
   if (s < k) {
-    const SegDesc sd = segs[s];
+    SegDesc sd = h_segs[s];
     auto term_vs = [&](uint32_t i, const uint8_t* t, uint32_t nt) {
       const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
       return term_compare(sd.tb + o, n, t, nt);
     };
     const uint32_t lo = has_min ? warp_partition_point(0u, sd.n, [&](uint32_t i) {
-      return term_vs(i, bounds, minlen) < 0; }) : 0u;
+      return term_vs(i, bnd, minlen) < 0; }) : 0u;
     const uint32_t hi = has_max ? warp_partition_point(lo, sd.n, [&](uint32_t i) {
-      return term_vs(i, bounds + minlen, maxlen) <= 0; }) : sd.n;
+      return term_vs(i, bnd + minlen, maxlen) <= 0; }) : sd.n;
     if (lane_id() == 0) {
-      segs[s].lo = lo;
-      segs[s].hi = hi;
+      sd.lo = lo;
+      sd.hi = hi;
+      d_segs[s] = sd;  // .base follows below
+      h_out[s].lo = lo;
+      h_out[s].hi = hi;
+      h_post[s] = __ldg(sd.poff + hi) - __ldg(sd.poff + lo);  // sizes the union buffers
     }
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&n_total[1], 1u) == gridDim.x - 1;  // n_total[1]: zeroed
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   uint32_t run = 0;
-  uint64_t post = 0;  // Σ input postings inside the windows: sizes the union buffers
   for (int base = 0; base < k; base += 256) {
     const int x = base + threadIdx.x;
-    const volatile SegDesc* v = segs;
-    uint32_t w = 0;
-    uint64_t p = 0;
-    if (x < k) {
-      const uint32_t lo = v[x].lo, hi = v[x].hi;
-      w = hi - lo;
-      p = __ldg(v[x].poff + hi) - __ldg(v[x].poff + lo);
-    }
+    const volatile SegDesc* v = d_segs;
+    const uint32_t w = x < k ? v[x].hi - v[x].lo : 0u;
     uint32_t tot;
-    uint64_t ptot;
     const uint32_t ex = block_exclusive_scan(w, ws, tot);
-    block_exclusive_scan(p, ws64, ptot);
-    if (x < k) segs[x].base = run + ex;
+    if (x < k) d_segs[x].base = run + ex;
     run += tot;
-    post += ptot;
   }
-  if (threadIdx.x == 0) {
-    n_total[0] = run;
-    n_total[2] = (uint32_t)post;
-    n_total[3] = (uint32_t)(post >> 32);
-  }
+  if (threadIdx.x == 0) *ticket = 0;  // the next launch finds it zero
 }
 
 // ------------------------------------------------------------------ the device pipeline
@@ -300,11 +303,12 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     ~PinnedBlock() { pinned_free(p); }
   } stage;
   const size_t nsegx = nseg ? nseg : 1;
-  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 8 * (nsegx + 1) + minlen + maxlen + 64;
+  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 8 * nsegx + 8 * (nsegx + 1) + minlen + maxlen + 64;
   stage.p = pinned_alloc(stage_bytes);
   if (!stage.p) return II2_ERR_NOMEM;
   SegDesc* h = static_cast<SegDesc*>(stage.p);
-  uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h + nsegx);
+  uint64_t* h_post = reinterpret_cast<uint64_t*>(h + nsegx);  // postings inside every window
+  uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h_post + nsegx);
   uint8_t* h_bounds = reinterpret_cast<uint8_t*>(h_sbase + 2 * (nsegx + 1));
   uint64_t n_total64 = 0, n_in = 0, tb_in = 0;
   for (int i = 0; i < nseg; i++) {
@@ -328,33 +332,34 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   }
   DevBuf<SegDesc> d_segs;
   II2_TRY(d_segs.alloc_scratch(nsegx, s));
-  if (nseg)
-    II2_TRY(small_copy(d_segs.p, h, sizeof(SegDesc) * nseg, s));
   uint32_t n_total = (uint32_t)n_total64;
   const bool ranged = has_min || has_max;
   if (ranged && nseg) {
     ProfScope win_scope("k4_windows_sync", s);
     DevBuf<uint8_t> d_bounds;
-    DevBuf<uint32_t> d_nt;
-    II2_TRY(d_bounds.alloc_scratch(minlen + maxlen + 8, s));
-    II2_TRY(d_nt.alloc_scratch(4, s));
-    II2_CUDA_TRY(cudaMemsetAsync(d_nt.p, 0, 16, s));
     if (has_min && minlen) memcpy(h_bounds, min, minlen);
     if (has_max && maxlen) memcpy(h_bounds + minlen, max, maxlen);
-    if (minlen + maxlen)
+    const uint8_t* bounds = h_bounds;  // read from the pinned block; long ones are uploaded
+    if (minlen + maxlen > kBoundsSmem) {
+      II2_TRY(d_bounds.alloc_scratch(minlen + maxlen + 8, s));
       II2_TRY(small_copy(d_bounds.p, h_bounds, minlen + maxlen, s));
-    k4_windows<<<div_up(nseg, 8), 256, 0, s>>>(d_segs.p, nseg, d_bounds.p, (uint32_t)minlen, has_min ? 1 : 0,
-                                  (uint32_t)maxlen, has_max ? 1 : 0, d_nt.p);
-    II2_LAUNCHED();
+      bounds = d_bounds.p;
+    }
+    uint32_t* const ticket = device_tickets();
+    if (!ticket) return II2_ERR_NOMEM;
+    II2_LAUNCH_CHAIN(k4_windows, div_up(nseg, 8), 256, 0, s, h, d_segs.p, h, h_post, nseg, bounds,
+                     (uint32_t)minlen, has_min ? 1 : 0, (uint32_t)maxlen, has_max ? 1 : 0, ticket);
     // the windows come back: the planner spreads its samples over them
-    II2_TRY(small_copy(h, d_segs.p, sizeof(SegDesc) * nseg, s));
-    uint32_t* h_nt = reinterpret_cast<uint32_t*>(pinned_scratch() + 16);
-    II2_TRY(small_copy(h_nt, d_nt.p, 16, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
     n_total64 = 0;
-    for (int i = 0; i < nseg; i++) n_total64 += h[i].hi - h[i].lo;
+    n_in = 0;
+    for (int i = 0; i < nseg; i++) {
+      n_total64 += h[i].hi - h[i].lo;
+      n_in += h_post[i];
+    }
     n_total = (uint32_t)n_total64;
-    n_in = (uint64_t)h_nt[2] | ((uint64_t)h_nt[3] << 32);
+  } else if (nseg) {
+    II2_TRY(small_copy(d_segs.p, h, sizeof(SegDesc) * nseg, s));
   }
 
   EmitOut& out = res->out;

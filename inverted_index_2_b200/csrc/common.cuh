@@ -39,6 +39,37 @@ void set_last_error(const char* fmt, ...);
     II2_CUDA_TRY(cudaGetLastError());                    \
   } while (0)
 
+// ---- chained launches (programmatic dependent launch) -------------------------------------
+// A range read of a thousand terms is ~20 dependent kernels of a few microseconds each: the
+// launch gaps, not the kernels, are most of its latency.  Kernels of the merge / read chain
+// start with pdl_enter() and are launched with II2_LAUNCH_CHAIN: the grid is set up and its
+// CTAs become resident while the previous kernel still runs, `griddepcontrol.wait` holds them
+// until that kernel has completed and its writes are visible, so only the gap disappears —
+// ordering and visibility are those of a plain stream.  A kernel WITHOUT pdl_enter() must never
+// be launched this way (it would run next to its producer).  II2_PDL=0 launches plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define II2_LAUNCH_CHAIN(kern, grid, block, smem, s, ...)                                  \
+  do {                                                                                     \
+    const cudaError_t _le = ::ii2::launch_chain(kern, grid, block, smem, s, __VA_ARGS__);  \
+    ::ii2::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                      \
+    II2_CUDA_TRY(_le);                                                                     \
+  } while (0)
+
 constexpr int kNumSMs = 148;  // B200
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -67,6 +98,12 @@ constexpr int kMaxSamples = 8192;  // splitter samples (one CTA sorts them in sm
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device side
+// First statement of every kernel launched with II2_LAUNCH_CHAIN: wait for the producer grid,
+// then let the consumer grid be set up behind this one.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 

@@ -109,6 +109,7 @@ __device__ __forceinline__ void smem_key16_at(const uint8_t* smem, uint32_t t0, 
 }
 
 __global__ void __launch_bounds__(F_THREADS, K12F_MIN_CTAS) k12f_bucket_kernel(const K12fArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint64_t s_p1[8], s_p2[8];
   __shared__ uint64_t s_ws64[F_WARPS + 2];
@@ -638,8 +639,7 @@ int k12f_launch(const K12fArgs& a, uint32_t n_buckets, cudaStream_t s) {
                                       (int)want));
     attr = want;
   }
-  k12f_bucket_kernel<<<n_buckets, F_THREADS, smem, s>>>(a);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k12f_bucket_kernel, n_buckets, F_THREADS, smem, s, a);
   return II2_OK;
 }
 

@@ -124,6 +124,7 @@ __device__ unsigned long long g_k1b_clk[10];
 // instantiation, because one more live pointer in the default one costs spills (64 registers).
 template <bool LIST>
 __global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) k1b_group_kernel(const K1bArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t s_ws64[K1B_WARPS + 2];
   __shared__ uint32_t s_ws32[K1B_WARPS + 2];
@@ -745,6 +746,7 @@ struct K2bArgs {
 #endif
 template <bool LIST>
 __global__ void __launch_bounds__(K2B_THREADS, K2B_MIN_CTAS) k2b_union_kernel(const K2bArgs a) {
+  pdl_enter();
   __shared__ __align__(16) uint32_t s_buf[K2B_WARPS][REG_CAP];
   __shared__ __align__(16) uint32_t s_enc[K2B_WARPS][K2B_EBUF];
   const unsigned lane = lane_id(), warp = warp_id();
@@ -916,6 +918,7 @@ struct MwArgs {
 };
 
 __global__ void __launch_bounds__(MW_WARPS * 32, MW_MIN_CTAS) k2_mwarp_kernel(const MwArgs a) {
+  pdl_enter();
   __shared__ __align__(16) uint32_t s_buf[MW_WARPS][MW_BUF];
   __shared__ __align__(16) uint32_t s_enc[MW_WARPS][MW_EBUF];
   const unsigned lane = lane_id(), warp = warp_id();
@@ -1124,6 +1127,7 @@ struct MedArgs {
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 8 : 5) k2_medium_kernel(const MedArgs a) {
+  pdl_enter();
   constexpr int MED_THREADS = NW * 32;
   constexpr uint32_t MED_CAP = NW * MED_RUN;  // values one CTA of NW warps unions
   __shared__ uint32_t s_v[MED_CAP];                 // sorted runs / merge ping-pong / survivors
@@ -1631,17 +1635,6 @@ __global__ void __launch_bounds__(1024) k2_large_finish(const LargeArgs a) {
   }
 }
 
-// Σ bk_D (terms_merged)
-__global__ void __launch_bounds__(1024)
-k12_sum_D(const uint32_t* __restrict__ d, uint32_t n, uint64_t* __restrict__ out) {
-  __shared__ uint64_t ws[1024 / 32 + 2];
-  uint64_t acc = 0;
-  for (uint32_t i = threadIdx.x; i < n; i += 1024) acc += d[i];
-  uint64_t tot;
-  block_exclusive_scan(acc, ws, tot);
-  if (threadIdx.x == 0) *out = tot;
-}
-
 // The multi-CTA union of `h_nl` heavy groups (also the per-prefix union of k5_prefix.cu).  The
 // caller fills rec / bucket / gin / src_ptr / src_len / recs / rem / flags / bk_raw; sizes,
 // offsets and the sort space are set up here.  Synchronises the stream.
@@ -1908,19 +1901,19 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
     a1.list = a2.list = list;
     {
       ProfScope scope("k1b_group", s);
-      if (list)
-        k1b_group_kernel<true><<<grid, K1B_THREADS, smem, s>>>(a1);
-      else
-        k1b_group_kernel<false><<<grid, K1B_THREADS, smem, s>>>(a1);
-      II2_LAUNCHED();
+      if (list) {
+        II2_LAUNCH_CHAIN(k1b_group_kernel<true>, grid, K1B_THREADS, smem, s, a1);
+      } else {
+        II2_LAUNCH_CHAIN(k1b_group_kernel<false>, grid, K1B_THREADS, smem, s, a1);
+      }
     }
     {
       ProfScope scope("k2b_union", s);
-      if (list)
-        k2b_union_kernel<true><<<grid, K2B_THREADS, 0, s>>>(a2);
-      else
-        k2b_union_kernel<false><<<grid, K2B_THREADS, 0, s>>>(a2);
-      II2_LAUNCHED();
+      if (list) {
+        II2_LAUNCH_CHAIN(k2b_union_kernel<true>, grid, K2B_THREADS, 0, s, a2);
+      } else {
+        II2_LAUNCH_CHAIN(k2b_union_kernel<false>, grid, K2B_THREADS, 0, s, a2);
+      }
     }
     {  // the terms K2b deferred: up to MW_CAP values one warp each, up to 4096 one CTA each;
        // device-side work lists, no host round trip
@@ -1948,8 +1941,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       w2.out_post = u.med_post.p;
       w2.out_enc = u.med_enc.p;
       w2.out_cursor = med_cursor.p;
-      k2_mwarp_kernel<<<kNumSMs * (MW_MIN_CTAS < 4 ? 4 : MW_MIN_CTAS), MW_WARPS * 32, 0, s>>>(w2);
-      II2_LAUNCHED();
+      II2_LAUNCH_CHAIN(k2_mwarp_kernel, kNumSMs * (MW_MIN_CTAS < 4 ? 4 : MW_MIN_CTAS), MW_WARPS * 32, 0, s, w2);
       // one CTA per term: four warps up to 2048 values (eight CTAs per SM), eight warps up to
       // 4096 (five per SM); each passes the longer terms on through its own list
       uint32_t* const mid2_rec = large_u32.p + 6 * (size_t)large_cap;
@@ -1975,8 +1967,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       m.out_post = u.med_post.p;
       m.out_enc = u.med_enc.p;
       m.out_cursor = med_cursor.p;
-      k2_medium_kernel<4><<<kNumSMs * 8, 4 * 32, 0, s>>>(m);
-      II2_LAUNCHED();
+      II2_LAUNCH_CHAIN(k2_medium_kernel<4>, kNumSMs * 8, 4 * 32, 0, s, m);
       m.n_large = n_mid2;
       m.large_rec = mid2_rec;
       m.large_bucket = mid2_bucket;
@@ -1984,8 +1975,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       m.n_huge = a2.n_large + 1;  // the high half of totals[6]
       m.huge_rec = large_u32.p + 2 * (size_t)large_cap;
       m.huge_bucket = large_u32.p + 3 * (size_t)large_cap;
-      k2_medium_kernel<8><<<kNumSMs * 5, 8 * 32, 0, s>>>(m);
-      II2_LAUNCHED();
+      II2_LAUNCH_CHAIN(k2_medium_kernel<8>, kNumSMs * 5, 8 * 32, 0, s, m);
     }
     return II2_OK;
   };
@@ -1994,10 +1984,9 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   // bucket totals -> prefixes -> host (synchronises the stream)
   auto totals = [&]() -> int {
     ProfScope scope("k12_scan_sync", s);
-    k12_sum_D<<<1, 1024, 0, s>>>(u.bk_D.p, B, u.totals.p + 4);
-    II2_LAUNCHED();
-    II2_TRY(exclusive_scan_multi_u64(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, s));
-    II2_TRY(small_copy(h_tot, u.totals.p, 64, s));
+    // four scans, Σ bk_D (terms_merged) and the copy of the eight totals to the host: one launch
+    II2_TRY(exclusive_scan_multi_sum_to_host(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, u.bk_D.p, B,
+                                             4, h_tot, 8, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
     return II2_OK;
   };

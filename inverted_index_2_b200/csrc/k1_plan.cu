@@ -45,6 +45,7 @@ struct SampleArrays {
 __global__ void __launch_bounds__(256)
 k1_sample_keys(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ sbase,
                uint32_t S, SampleArrays sa) {
+  pdl_enter();
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= S) return;
   int lo = 0, hi = k;  // segment of sample x: last s with sbase[s] <= x
@@ -91,6 +92,7 @@ __device__ __forceinline__ KeyedTerm sample_term(const SampleArrays& sa, uint32_
 __global__ void __launch_bounds__(256)
 k1_rank_samples(int k, const uint32_t* __restrict__ sbase, uint32_t S, SampleArrays sa,
                 SampleArrays sorted) {
+  pdl_enter();
   const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = lane_id();
   if (x >= S) return;
@@ -136,6 +138,7 @@ constexpr uint32_t K1_CHUNK = K1_CHUNK_TERMS;
 __global__ void __launch_bounds__(256)
 k1_chunk_ranks(const SegDesc* __restrict__ segs, int k, const uint32_t* __restrict__ cbase,
                uint32_t n_chunks, uint32_t S, SampleArrays sp, uint32_t* __restrict__ crank) {
+  pdl_enter();
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chunks) return;
   int lo = 0, hi = k;  // segment of chunk c: last s with cbase[s] <= c
@@ -202,6 +205,7 @@ k1_partition_chunks_raw(const SegDesc* __restrict__ segs, int k, const uint32_t*
                         uint32_t S, SampleArrays sp, const uint32_t* __restrict__ crank,
                         uint32_t* __restrict__ part, uint32_t* __restrict__ btb,
                         uint64_t* __restrict__ bpo) {
+  pdl_enter();
   extern __shared__ __align__(16) uint32_t k1_smem[];
   uint32_t* s_off = k1_smem;                  // [K1_CHUNK + 1] term offsets of the chunk
   uint32_t* s_raw = k1_smem + K1_CHUNK + 4;   // staged term bytes (+ 8 words of slack)
@@ -318,6 +322,7 @@ k1_bucket_stats(int k, uint32_t S, SampleArrays sp, const uint32_t* __restrict__
                 const uint32_t* __restrict__ btb, const uint64_t* __restrict__ bpo,
                 uint64_t* __restrict__ raw, uint32_t* __restrict__ bk_cpl,
                 const uint32_t* __restrict__ sel, uint32_t S_fine) {
+  pdl_enter();
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t B = S + 1;
   if (b > B) return;
@@ -368,6 +373,7 @@ k1_bucket_stats(int k, uint32_t S, SampleArrays sp, const uint32_t* __restrict__
 __global__ void __launch_bounds__(256)
 k1_fine_sizes(const uint32_t* __restrict__ part, int k, uint32_t rows /* S_fine + 2 */,
               uint64_t* __restrict__ cum) {
+  pdl_enter();
   const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // instances before row r
   if (r >= rows) return;
   uint64_t w = 0;
@@ -379,6 +385,7 @@ k1_fine_sizes(const uint32_t* __restrict__ part, int k, uint32_t rows /* S_fine 
 __global__ void __launch_bounds__(256)
 k1_select_rows(const uint64_t* __restrict__ cum, uint32_t rows, uint32_t target,
                uint64_t* __restrict__ flag) {
+  pdl_enter();
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > rows) return;
   uint64_t f = 0;
@@ -392,6 +399,7 @@ k1_select_rows(const uint64_t* __restrict__ cum, uint32_t rows, uint32_t target,
 __global__ void __launch_bounds__(256)
 k1_mark_rows(const uint64_t* __restrict__ idx, const uint64_t* __restrict__ cum, uint32_t rows,
              uint32_t target, uint32_t* __restrict__ sel, uint32_t out_rows) {
+  pdl_enter();
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows - 1) {
     const bool kept = r == 0 || cum[r] / target > cum[r - 1] / target;
@@ -407,6 +415,7 @@ k1_compact_rows(const uint32_t* __restrict__ sel, int k, uint32_t out_rows,
                 const uint32_t* __restrict__ part_f, const uint32_t* __restrict__ btb_f,
                 const uint64_t* __restrict__ bpo_f, uint32_t* __restrict__ part,
                 uint32_t* __restrict__ btb, uint64_t* __restrict__ bpo) {
+  pdl_enter();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (uint64_t)out_rows * k) return;
   const uint32_t j = (uint32_t)(i / k), s = (uint32_t)(i % k);
@@ -533,10 +542,8 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   SampleArrays sa{d_u64.p, d_u64.p + Sx, d_u64.p + 2 * Sx, d_u32.p, d_u32.p + Sx, d_u32.p + 2 * Sx};
   SampleArrays sp{d_u64.p + 3 * Sx, d_u64.p + 4 * Sx, d_u64.p + 5 * Sx, d_u32.p + 3 * Sx, nullptr, nullptr};
   if (S) {
-    k1_sample_keys<<<div_up(S, 256), 256, 0, s>>>(plan.segs, k, d_sbase, S, sa);
-    II2_LAUNCHED();
-    k1_rank_samples<<<div_up((uint64_t)S * 32, 256), 256, 0, s>>>(k, d_sbase, S, sa, sp);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k1_sample_keys, div_up(S, 256), 256, 0, s, plan.segs, k, d_sbase, S, sa);
+    II2_LAUNCH_CHAIN(k1_rank_samples, div_up((uint64_t)S * 32, 256), 256, 0, s, k, d_sbase, S, sa, sp);
   }
   {
     constexpr size_t smem = (K1_CHUNK + 4 + 8) * 4 + K1_RAW_BYTES;
@@ -548,31 +555,18 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     }
     DevBuf<uint32_t> crank;
     II2_TRY(crank.alloc_scratch((size_t)n_chunks + 1, s));
-    k1_chunk_ranks<<<div_up(n_chunks, 256), 256, 0, s>>>(plan.segs, k, d_cbase, n_chunks, S, sp,
-                                                          crank.p);
-    II2_LAUNCHED();
-    k1_partition_chunks_raw<<<n_chunks, 256, smem, s>>>(plan.segs, k, d_cbase, S, sp, crank.p,
-                                                        p_part, p_btb, p_bpo);
+    II2_LAUNCH_CHAIN(k1_chunk_ranks, div_up(n_chunks, 256), 256, 0, s, plan.segs, k, d_cbase, n_chunks, S, sp, crank.p);
+    II2_LAUNCH_CHAIN(k1_partition_chunks_raw, n_chunks, 256, smem, s, plan.segs, k, d_cbase, S, sp, crank.p, p_part, p_btb, p_bpo);
   }
-  II2_LAUNCHED();
   if (fine > 1) {
     const uint32_t rows = S + 2;
-    k1_fine_sizes<<<div_up((uint64_t)rows * 32, 256), 256, 0, s>>>(p_part, k, rows, d_cum.p);
-    II2_LAUNCHED();
-    k1_select_rows<<<div_up((uint64_t)rows + 1, 256), 256, 0, s>>>(d_cum.p, rows, target, d_idx.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k1_fine_sizes, div_up((uint64_t)rows * 32, 256), 256, 0, s, p_part, k, rows, d_cum.p);
+    II2_LAUNCH_CHAIN(k1_select_rows, div_up((uint64_t)rows + 1, 256), 256, 0, s, d_cum.p, rows, target, d_idx.p);
     II2_TRY(exclusive_scan_u64(d_idx.p, (uint64_t)rows + 1, nullptr, s));
-    k1_mark_rows<<<div_up(std::max<uint64_t>(rows, (uint64_t)B + 1), 256), 256, 0, s>>>(
-        d_idx.p, d_cum.p, rows, target, d_sel.p, B + 1);
-    II2_LAUNCHED();
-    k1_compact_rows<<<div_up((uint64_t)(B + 1) * k, 256), 256, 0, s>>>(
-        d_sel.p, k, B + 1, p_part, p_btb, p_bpo, plan.part.p, plan.btb.p, plan.bpo.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k1_mark_rows, div_up(std::max<uint64_t>(rows, (uint64_t)B + 1), 256), 256, 0, s, d_idx.p, d_cum.p, rows, target, d_sel.p, B + 1);
+    II2_LAUNCH_CHAIN(k1_compact_rows, div_up((uint64_t)(B + 1) * k, 256), 256, 0, s, d_sel.p, k, B + 1, p_part, p_btb, p_bpo, plan.part.p, plan.btb.p, plan.bpo.p);
   }
-  k1_bucket_stats<<<div_up((uint64_t)(B + 1) * 32, 256), 256, 0, s>>>(
-      k, B - 1, sp, plan.part.p, plan.btb.p, plan.bpo.p, plan.bk_WP.p, plan.bk_cpl.p,
-      fine > 1 ? d_sel.p : nullptr, S);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k1_bucket_stats, div_up((uint64_t)(B + 1) * 32, 256), 256, 0, s, k, B - 1, sp, plan.part.p, plan.btb.p, plan.bpo.p, plan.bk_WP.p, plan.bk_cpl.p, fine > 1 ? d_sel.p : nullptr, S);
   II2_TRY(exclusive_scan_multi_u64(plan.bk_WP.p, plan.bk_WP.p, B + 1, 4, plan.totals.p, s));
   return II2_OK;
 }

@@ -60,6 +60,7 @@ constexpr uint32_t K6_MAX_GROUP = 32;  // buckets per CTA
 #endif
 __global__ void __launch_bounds__(K6_THREADS, K6_MIN_CTAS) k6_emit_kernel(const K6Args a, uint32_t group,
                                                              uint32_t n_buckets) {
+  pdl_enter();
   __shared__ K6Work s_work[K6_THREADS];
   __shared__ uint64_t s_ws64[K6_WARPS + 2];
   __shared__ uint32_t s_pref[K6_MAX_GROUP + 1];
@@ -277,6 +278,7 @@ __device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst,
 }
 
 __global__ void __launch_bounds__(K6_THREADS) k6_dense_kernel(const K6DenseArgs a, uint32_t n_buckets) {
+  pdl_enter();
   const uint32_t b = blockIdx.x * K6_WARPS + warp_id();
   if (b >= n_buckets) return;
   const unsigned lane = lane_id();
@@ -364,12 +366,10 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
     d.o_post_off = out.post_off.p;
     d.o_val_words = out.val_words.p;
     d.o_val_off = out.val_off.p;
-    k6_dense_kernel<<<div_up(plan.n_buckets, K6_WARPS), K6_THREADS, 0, s>>>(d, plan.n_buckets);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k6_dense_kernel, div_up(plan.n_buckets, K6_WARPS), K6_THREADS, 0, s, d, plan.n_buckets);
     if (u.n_def) {  // the buckets the general kernels ran: one CTA each, from their records
       a.list = u.def_list.p;
-      k6_emit_kernel<<<u.n_def, K6_THREADS, 0, s>>>(a, 1, plan.n_buckets);
-      II2_LAUNCHED();
+      II2_LAUNCH_CHAIN(k6_emit_kernel, u.n_def, K6_THREADS, 0, s, a, 1, plan.n_buckets);
     }
     return II2_OK;
   }
@@ -380,8 +380,7 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   // a small result (a narrow range read) must not end up on a handful of CTAs whose warps walk
   // dozens of terms one after the other: at least ~two CTAs per SM while the buckets last
   group = (uint32_t)std::min<uint64_t>(group, std::max<uint64_t>(1, plan.n_buckets / 296));
-  k6_emit_kernel<<<div_up(plan.n_buckets, group), K6_THREADS, 0, s>>>(a, group, plan.n_buckets);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k6_emit_kernel, div_up(plan.n_buckets, group), K6_THREADS, 0, s, a, group, plan.n_buckets);
   return II2_OK;
 }
 
@@ -389,6 +388,7 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
 // and the largest last term over the segments' windows.  One warp.
 __global__ void __launch_bounds__(32)
 k6_minmax_kernel(const SegDesc* __restrict__ segs, int k, uint8_t* __restrict__ out) {
+  pdl_enter();
   const unsigned lane = lane_id();
   int best[2] = {-1, -1};
   for (int s = lane; s < k; s += 32) {
@@ -431,8 +431,7 @@ k6_minmax_kernel(const SegDesc* __restrict__ segs, int k, uint8_t* __restrict__ 
 
 int k6_minmax(const MergePlan& plan, const UnionOut& u, uint8_t* d_out, cudaStream_t s) {
   (void)u;
-  k6_minmax_kernel<<<1, 32, 0, s>>>(plan.segs, plan.k, d_out);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k6_minmax_kernel, 1, 32, 0, s, plan.segs, plan.k, d_out);
   return II2_OK;
 }
 

@@ -11,6 +11,11 @@ namespace ii2 {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 
+bool pdl_enabled() {  // read per launch (tuning runs flip it inside one process)
+  const char* e = getenv("II2_PDL");
+  return !(e && e[0] == '0');
+}
+
 static thread_local char t_last_error[512] = "";
 
 void set_last_error(const char* fmt, ...) {
@@ -102,6 +107,7 @@ static size_t size_class(size_t bytes) {
 
 __global__ void __launch_bounds__(256)
 k_small_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+  pdl_enter();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nw = bytes >> 2;
   const bool aligned = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3) == 0;
@@ -115,9 +121,8 @@ k_small_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t 
 
 int small_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return II2_OK;
-  k_small_copy<<<div_up((bytes + 3) / 4, 256), 256, 0, s>>>(static_cast<uint8_t*>(dst),
-                                                            static_cast<const uint8_t*>(src), bytes);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k_small_copy, div_up((bytes + 3) / 4, 256), 256, 0, s, static_cast<uint8_t*>(dst),
+                   static_cast<const uint8_t*>(src), bytes);
   return II2_OK;
 }
 
@@ -127,6 +132,20 @@ uint64_t* pinned_scratch() {
     void* q = nullptr;
     if (cudaHostAlloc(&q, 256, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     p = static_cast<uint64_t*>(q);
+  }
+  return p;
+}
+
+uint32_t* device_tickets() {
+  static thread_local uint32_t* p = nullptr;
+  if (!p) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, 256) != cudaSuccess) return nullptr;
+    if (cudaMemset(q, 0, 256) != cudaSuccess) {
+      cudaFree(q);
+      return nullptr;
+    }
+    p = static_cast<uint32_t*>(q);
   }
   return p;
 }
@@ -317,6 +336,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint64_t* __restrict__ d,
                                                               uint64_t n,
                                                               uint64_t* __restrict__ bsum) {
+  pdl_enter();
   __shared__ uint64_t ws[kScanThreads / 32 + 2];
   uint64_t base = (uint64_t)blockIdx.x * kScanTile;
   uint64_t acc = 0;
@@ -333,6 +353,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint64_t* __
 // single CTA: exclusive scan of bsum[0..nb) in place, total -> *d_total
 __global__ void __launch_bounds__(1024) k_scan_single(uint64_t* __restrict__ a, uint64_t nb,
                                                       uint64_t* __restrict__ d_total) {
+  pdl_enter();
   __shared__ uint64_t ws[1024 / 32 + 2];
   uint64_t carry = 0;
   for (uint64_t base = 0; base < nb; base += 1024) {
@@ -348,6 +369,7 @@ __global__ void __launch_bounds__(1024) k_scan_single(uint64_t* __restrict__ a, 
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(uint64_t* __restrict__ d, uint64_t n,
                                                              const uint64_t* __restrict__ bsum) {
+  pdl_enter();
   __shared__ uint64_t ws[kScanThreads / 32 + 2];
   uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
   uint64_t v[kScanItems];
@@ -372,9 +394,44 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(uint64_t* __restric
 // barrier inside the loops); the 32 warp totals are scanned once, then each warp adds its base.
 // (The first version gave every thread a contiguous chunk: 2 x 41 strided dependent loads per
 // thread, 48 us per launch at n = 41 k.)
+// Optional extras (ScanExtra): CTA m sums a u32 array into totals[sum_slot]; the last CTA to
+// finish copies totals[0 .. n_copy) to `host_copy` (pinned) — the totals of a pipeline stage
+// reach the host with this launch alone.
+struct ScanExtra {
+  const uint32_t* sum_in;
+  uint32_t sum_n, sum_slot;
+  uint64_t* host_copy;
+  uint32_t n_copy;
+  uint32_t* ticket;  // zero between launches (device_tickets)
+};
+
+__device__ __forceinline__ void scan_multi_finish(const ScanExtra& x, uint64_t* totals) {
+  if (!x.host_copy) return;
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(x.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < x.n_copy) x.host_copy[threadIdx.x] = *(volatile uint64_t*)(totals + threadIdx.x);
+  if (threadIdx.x == 0) *x.ticket = 0;
+}
+
 __global__ void __launch_bounds__(1024) k_scan_multi(const uint64_t* a, uint64_t* out, uint64_t n,
-                                                     uint64_t* __restrict__ totals) {
+                                                     uint64_t* __restrict__ totals, int m,
+                                                     const ScanExtra x) {
+  pdl_enter();
   __shared__ uint64_t ws[1024 / 32 + 2];
+  if ((int)blockIdx.x >= m) {  // the extra CTA: a plain sum
+    uint64_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < x.sum_n; i += 1024) acc += x.sum_in[i];
+    uint64_t tot;
+    block_exclusive_scan(acc, ws, tot);
+    if (threadIdx.x == 0) totals[x.sum_slot] = tot;
+    scan_multi_finish(x, totals);
+    return;
+  }
   const uint64_t* arr = a + (uint64_t)blockIdx.x * n;
   uint64_t* dst = out + (uint64_t)blockIdx.x * n;
   const unsigned lane = lane_id(), w = warp_id();
@@ -402,12 +459,24 @@ __global__ void __launch_bounds__(1024) k_scan_multi(const uint64_t* a, uint64_t
   if (add)
     for (uint64_t i = lo + lane; i < hi; i += 32) dst[i] += add;
   if (threadIdx.x == 0 && totals) totals[blockIdx.x] = total;
+  scan_multi_finish(x, totals);
 }
 
 int exclusive_scan_multi_u64(const uint64_t* in, uint64_t* out, uint64_t n, int m,
                              uint64_t* d_totals, cudaStream_t s) {
-  k_scan_multi<<<m, 1024, 0, s>>>(in, out, n, d_totals);
-  II2_LAUNCHED();
+  const ScanExtra none = {nullptr, 0, 0, nullptr, 0, nullptr};
+  II2_LAUNCH_CHAIN(k_scan_multi, m, 1024, 0, s, in, out, n, d_totals, m, none);
+  return II2_OK;
+}
+
+int exclusive_scan_multi_sum_to_host(const uint64_t* in, uint64_t* out, uint64_t n, int m,
+                                     uint64_t* d_totals, const uint32_t* sum_in, uint32_t sum_n,
+                                     uint32_t sum_slot, uint64_t* host_copy, uint32_t n_copy,
+                                     cudaStream_t s) {
+  uint32_t* const tickets = device_tickets();
+  if (!tickets || n_copy > 1024) return II2_ERR_NOMEM;
+  const ScanExtra x = {sum_in, sum_n, sum_slot, host_copy, n_copy, tickets + 1};
+  II2_LAUNCH_CHAIN(k_scan_multi, m + 1, 1024, 0, s, in, out, n, d_totals, m, x);
   return II2_OK;
 }
 
@@ -417,20 +486,16 @@ int exclusive_scan_u64(uint64_t* d, uint64_t n, uint64_t* d_total, cudaStream_t 
     return II2_OK;
   }
   if (n <= 16384) {
-    k_scan_single<<<1, 1024, 0, s>>>(d, n, d_total);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_scan_single, 1, 1024, 0, s, d, n, d_total);
     return II2_OK;
   }
   uint64_t nb = (n + kScanTile - 1) / kScanTile;
   DevBuf<uint64_t> bsum;
   II2_TRY(bsum.alloc(nb, s));
   // k_scan_reduce reads strided (coalesced), k_scan_apply reads blocked per thread
-  k_scan_reduce<<<(unsigned)nb, kScanThreads, 0, s>>>(d, n, bsum.p);
-  II2_LAUNCHED();
-  k_scan_single<<<1, 1024, 0, s>>>(bsum.p, nb, d_total);
-  II2_LAUNCHED();
-  k_scan_apply<<<(unsigned)nb, kScanThreads, 0, s>>>(d, n, bsum.p);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k_scan_reduce, (unsigned)nb, kScanThreads, 0, s, d, n, bsum.p);
+  II2_LAUNCH_CHAIN(k_scan_single, 1, 1024, 0, s, bsum.p, nb, d_total);
+  II2_LAUNCH_CHAIN(k_scan_apply, (unsigned)nb, kScanThreads, 0, s, d, n, bsum.p);
   return II2_OK;
 }
 

@@ -94,6 +94,9 @@ void pinned_free(void* p);  // also accepts nullptr
 // device->host readbacks (totals, flags).  A pageable destination would make the copy wait for
 // every other transfer in flight, including the next range's staging on the second stream.
 uint64_t* pinned_scratch();
+// 64 device words that are zero between kernels (per host thread): "last CTA" tickets; a kernel
+// that takes one puts the zero back before it ends, so no launch needs a memset in front of it.
+uint32_t* device_tickets();
 
 // Copy a few bytes between PINNED host memory and device memory (either direction) with a
 // kernel instead of a copy engine.  The copy engines serve requests in order: a 64-byte
@@ -108,5 +111,12 @@ int exclusive_scan_u64(uint64_t* d, uint64_t n, uint64_t* d_total, cudaStream_t 
 // (in == out is allowed.)
 int exclusive_scan_multi_u64(const uint64_t* in, uint64_t* out, uint64_t n, int m,
                              uint64_t* d_totals, cudaStream_t s);
+// The same with one more CTA that sums `sum_in[0 .. sum_n)` into d_totals[sum_slot]; the last CTA
+// copies d_totals[0 .. n_copy) into `host_copy` (pinned memory): scan + sum + the copy of the
+// totals to the host as ONE launch.  The caller synchronises the stream before reading.
+int exclusive_scan_multi_sum_to_host(const uint64_t* in, uint64_t* out, uint64_t n, int m,
+                                     uint64_t* d_totals, const uint32_t* sum_in, uint32_t sum_n,
+                                     uint32_t sum_slot, uint64_t* host_copy, uint32_t n_copy,
+                                     cudaStream_t s);
 
 }  // namespace ii2
