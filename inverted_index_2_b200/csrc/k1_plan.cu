@@ -362,6 +362,48 @@ k1_bucket_stats(int k, uint32_t S, SampleArrays sp, const uint32_t* __restrict__
   }
 }
 
+// ---- a window small enough for ONE bucket ------------------------------------------------------
+// (a point read, a handful of terms): no splitter exists, so the plan is the two boundary rows,
+// the bucket's sizes and their trivial prefixes — one CTA instead of the five launches of the
+// general path (copy of the bases, chunk ranks, partition, stats, scan); a read of this size is
+// bound by the number of launches.
+__global__ void __launch_bounds__(256)
+k1_plan_single(const SegDesc* __restrict__ segs, int k, uint32_t* __restrict__ part,
+               uint32_t* __restrict__ btb, uint64_t* __restrict__ bpo, uint64_t* __restrict__ bk_WP,
+               uint32_t* __restrict__ bk_cpl, uint64_t* __restrict__ totals) {
+  pdl_enter();
+  __shared__ uint64_t ws[256 / 32 + 2];
+  uint64_t w = 0, p = 0, t = 0;
+  for (int s = threadIdx.x; s < k; s += 256) {
+    const SegDesc sd = segs[s];
+    const uint32_t t0 = __ldg(sd.toff + sd.lo), t1 = __ldg(sd.toff + sd.hi);
+    const uint64_t p0 = __ldg(sd.poff + sd.lo), p1 = __ldg(sd.poff + sd.hi);
+    part[s] = sd.lo;
+    part[k + s] = sd.hi;
+    btb[s] = t0;
+    btb[k + s] = t1;
+    bpo[s] = p0;
+    bpo[k + s] = p1;
+    w += sd.hi - sd.lo;
+    p += p1 - p0;
+    t += t1 - t0;
+  }
+  uint64_t tw, tp, tt;
+  block_exclusive_scan(w, ws, tw);
+  block_exclusive_scan(p, ws, tp);
+  block_exclusive_scan(t, ws, tt);
+  if (threadIdx.x == 0) {
+    const uint64_t v[4] = {tw, tp, tp + (tp >> 2) + 6 * tw, tt};  // as k1_bucket_stats
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      bk_WP[2 * j] = 0;
+      bk_WP[2 * j + 1] = v[j];
+      totals[j] = v[j];
+    }
+    bk_cpl[0] = 0;
+  }
+}
+
 // ---- coalescing of a fine partition -----------------------------------------------------------
 // Evenly spaced terms of one segment are NOT evenly spaced in the merged order (the number of
 // other terms between two of them is negative-binomial: CV 0.2 at 64 segments), and a bucket
@@ -453,6 +495,14 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   }();
   if (small_bucket && want < small_want && N / small_bucket > want)
     want = std::min<uint64_t>(small_want, N / small_bucket);
+  // ... and a window of a few hundred instances (a point read) is ONE bucket: planning it costs
+  // more launches than the bucket takes (k1_plan_single; II2_SINGLE_BUCKET=<max instances>, 0 = off)
+  const uint32_t single_max = [] {
+    const char* e = getenv("II2_SINGLE_BUCKET");
+    const long v = e ? atol(e) : 768;
+    return (v >= 0 && v <= 1024) ? (uint32_t)v : 768u;
+  }();
+  if (N <= single_max) want = 0;
   // II2_COALESCE=<fine> (default 1 = off): a partition `fine` times finer, coalesced afterwards.
   // Measured on B200 (C2, profiles/r02_experiments.md): fine = 4 takes the buckets above 1024
   // instances from 9.6 % to 2 %, but the finer partition costs +0.5 ms of plan time (0.38 ->
@@ -529,6 +579,11 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     p_part = part_f.p;
     p_btb = btb_f.p;
     p_bpo = bpo_f.p;
+  }
+  if (S == 0 && fine == 1) {
+    II2_LAUNCH_CHAIN(k1_plan_single, 1, 256, 0, s, plan.segs, k, plan.part.p, plan.btb.p, plan.bpo.p,
+                     plan.bk_WP.p, plan.bk_cpl.p, plan.totals.p);
+    return II2_OK;
   }
   DevBuf<uint32_t> d_base, d_u32;
   DevBuf<uint64_t> d_u64;

@@ -13,6 +13,7 @@ ap.add_argument("--fracs", default="0.001,0.01")
 ap.add_argument("--reps", type=int, default=50)
 ap.add_argument("--terms", type=int, default=1_000_000)
 ap.add_argument("--postings", type=int, default=100_000_000)
+ap.add_argument("--prof", action="store_true")
 ap.add_argument("--env", default="", help="A=1;A=0 settings swept")
 a = ap.parse_args()
 w = synth.make_workload(a.terms, 256, a.postings, seed=0xC3, presence=0.125)
@@ -41,6 +42,16 @@ for env in (a.env.split(";") if a.env else [""]):
             if i >= 5:
                 lat.append(t1 - t0)
             sig = (int(info.terms_count), int(info.postings_in), int(info.postings_out))
-        print(json.dumps({"env": env, "frac": frac, "median_us": round(1e6 * float(np.median(lat)), 1),
+        phases = host = None
+        if a.prof:
+            eng.prof_enable(True)
+            r = eng.read_range_dev(dsegs, tlo, thi, drem)
+            r.info()
+            r.release()
+            pr = eng.prof_read()
+            phases = {p["name"]: round(1e3 * p["ms"] / max(1, p["count"]), 1) for p in pr}
+            host = {p["name"]: round(1e3 * p["host_ms"] / max(1, p["count"]), 1) for p in pr}
+            eng.prof_enable(False)
+        print(json.dumps({"env": env, "frac": frac, "phase_us": phases, "host_us": host, "median_us": round(1e6 * float(np.median(lat)), 1),
                           "min_us": round(1e6 * float(np.min(lat)), 1),
                           "p90_us": round(1e6 * float(np.percentile(lat, 90)), 1), "last_sig": sig}), flush=True)
