@@ -268,8 +268,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------- extra legs
 def range_read_leg(eng, a):
     """BASELINE configs[2]: term-range reads over 256 resident segments, 5 % of the id universe
-    removed (read + merge-style filter, quirk Q2), ranges of 0.1 / 1 / 10 / 100 % of the term
-    space at 16 random positions (4 for the full range); wall clock per call, microseconds."""
+    removed (read + merge-style filter, quirk Q2), a single term and ranges of 0.1 / 1 / 10 / 100 %
+    of the term space at 16 random positions (4 for the full range); wall clock per call,
+    microseconds."""
     import torch
     w = synth.make_workload(a.terms, 256, a.postings, seed=0xC3, presence=0.125,
                             removed_frac=a.removed_frac)
@@ -278,7 +279,7 @@ def range_read_leg(eng, a):
     n = len(w.term_off) - 1
     rng = np.random.default_rng(3)
     out = {}
-    for frac in (0.001, 0.01, 0.1, 1.0):
+    for frac in (0.0, 0.001, 0.01, 0.1, 1.0):  # 0 = a single term (min == max)
         span = max(1, int(n * frac))
         lat, info = [], None
         for _ in range(16 if frac < 1 else 4):
@@ -296,7 +297,7 @@ def range_read_leg(eng, a):
                 info = r.info()
                 r.release()
             lat.append(float(np.median(ts)))
-        out[f"{frac:g}"] = {"median_us": 1e6 * float(np.median(lat)), "p99_us": 1e6 * float(np.max(lat)),
+        out["one_term" if frac == 0 else f"{frac:g}"] = {"median_us": 1e6 * float(np.median(lat)), "p99_us": 1e6 * float(np.max(lat)),
                             "terms": int(info.terms_count), "postings_in": int(info.postings_in),
                             "postings_out": int(info.postings_out)}
     for d in dsegs:

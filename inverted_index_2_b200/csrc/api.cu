@@ -220,7 +220,7 @@ k_removed_check(const uint32_t* __restrict__ sorted, uint64_t n, uint32_t* __res
 
 // Range windows (K4): lo = first term >= min (vellum Iterator(min) seek, file/reader.go:147),
 // hi = first term > max (inclusive right bound, :54-58 and :151-155); then bases.
-// One WARP per segment searches 32 ways at a time (warp_partition_point: 4 rounds for 500 k
+// A WARP searches 32 ways at a time (warp_partition_point: 4 rounds for 500 k
 // terms instead of the 19 dependent probes of a binary search — a small read spent 50 of its
 // 270 us there).  The last CTA to finish turns the window widths into instance bases.
 // The kernel is the whole host <-> device exchange of the step (a small read is bound by the
@@ -242,25 +242,36 @@ k4_windows(const SegDesc* h_segs, SegDesc* d_segs, SegDesc* h_out,
     bnd = s_bounds;
     __syncthreads();
   }
-  const int s = blockIdx.x * 8 + warp_id();
+  // two warps per segment: one finds the start of the window, the other its end, at the same
+  // time (each search is a chain of ~8 dependent loads, which is what this kernel's time is)
+  __shared__ uint32_t s_hi[4];
+  const int s = blockIdx.x * 4 + (warp_id() >> 1);
+  const bool upper = warp_id() & 1u;
+  SegDesc sd = {};
+  uint32_t found = 0;
   if (s < k) {
-    SegDesc sd = h_segs[s];
+    sd = h_segs[s];
     auto term_vs = [&](uint32_t i, const uint8_t* t, uint32_t nt) {
       const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
       return term_compare(sd.tb + o, n, t, nt);
     };
-    const uint32_t lo = has_min ? warp_partition_point(0u, sd.n, [&](uint32_t i) {
-      return term_vs(i, bnd, minlen) < 0; }) : 0u;
-    const uint32_t hi = has_max ? warp_partition_point(lo, sd.n, [&](uint32_t i) {
-      return term_vs(i, bnd + minlen, maxlen) <= 0; }) : sd.n;
-    if (lane_id() == 0) {
-      sd.lo = lo;
-      sd.hi = hi;
-      d_segs[s] = sd;  // .base follows below
-      h_out[s].lo = lo;
-      h_out[s].hi = hi;
-      h_post[s] = __ldg(sd.poff + hi) - __ldg(sd.poff + lo);  // sizes the union buffers
-    }
+    if (!upper)
+      found = has_min ? warp_partition_point(0u, sd.n, [&](uint32_t i) {
+        return term_vs(i, bnd, minlen) < 0; }) : 0u;
+    else
+      found = has_max ? warp_partition_point(0u, sd.n, [&](uint32_t i) {
+        return term_vs(i, bnd + minlen, maxlen) <= 0; }) : sd.n;
+    if (upper && lane_id() == 0) s_hi[warp_id() >> 1] = found;
+  }
+  __syncthreads();
+  if (s < k && !upper && lane_id() == 0) {
+    const uint32_t lo = found, hi = max(s_hi[warp_id() >> 1], lo);  // min > max: empty at lo
+    sd.lo = lo;
+    sd.hi = hi;
+    d_segs[s] = sd;  // .base follows below
+    h_out[s].lo = lo;
+    h_out[s].hi = hi;
+    h_post[s] = __ldg(sd.poff + hi) - __ldg(sd.poff + lo);  // sizes the union buffers
   }
   __threadfence();
   __syncthreads();
@@ -347,7 +358,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     }
     uint32_t* const ticket = device_tickets();
     if (!ticket) return II2_ERR_NOMEM;
-    II2_LAUNCH_CHAIN(k4_windows, div_up(nseg, 8), 256, 0, s, h, d_segs.p, h, h_post, nseg, bounds,
+    II2_LAUNCH_CHAIN(k4_windows, div_up(nseg, 4), 256, 0, s, h, d_segs.p, h, h_post, nseg, bounds,
                      (uint32_t)minlen, has_min ? 1 : 0, (uint32_t)maxlen, has_max ? 1 : 0, ticket);
     // the windows come back: the planner spreads its samples over them
     II2_CUDA_TRY(cudaStreamSynchronize(s));
