@@ -271,7 +271,8 @@ k4_windows(const SegDesc* h_segs, SegDesc* d_segs, SegDesc* h_out,
     d_segs[s] = sd;  // .base follows below
     h_out[s].lo = lo;
     h_out[s].hi = hi;
-    h_post[s] = __ldg(sd.poff + hi) - __ldg(sd.poff + lo);  // sizes the union buffers
+    h_post[2 * s] = __ldg(sd.poff + hi) - __ldg(sd.poff + lo);  // sizes the union buffers
+    h_post[2 * s + 1] = __ldg(sd.toff + hi) - __ldg(sd.toff + lo);  // and the term bytes
   }
   __threadfence();
   __syncthreads();
@@ -314,12 +315,12 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     ~PinnedBlock() { pinned_free(p); }
   } stage;
   const size_t nsegx = nseg ? nseg : 1;
-  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 8 * nsegx + 8 * (nsegx + 1) + minlen + maxlen + 64;
+  const size_t stage_bytes = sizeof(SegDesc) * nsegx + 16 * nsegx + 8 * (nsegx + 1) + minlen + maxlen + 64;
   stage.p = pinned_alloc(stage_bytes);
   if (!stage.p) return II2_ERR_NOMEM;
   SegDesc* h = static_cast<SegDesc*>(stage.p);
-  uint64_t* h_post = reinterpret_cast<uint64_t*>(h + nsegx);  // postings inside every window
-  uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h_post + nsegx);
+  uint64_t* h_post = reinterpret_cast<uint64_t*>(h + nsegx);  // (postings, term bytes) inside every window
+  uint32_t* h_sbase = reinterpret_cast<uint32_t*>(h_post + 2 * nsegx);
   uint8_t* h_bounds = reinterpret_cast<uint8_t*>(h_sbase + 2 * (nsegx + 1));
   uint64_t n_total64 = 0, n_in = 0, tb_in = 0;
   for (int i = 0; i < nseg; i++) {
@@ -363,10 +364,11 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     // the windows come back: the planner spreads its samples over them
     II2_CUDA_TRY(cudaStreamSynchronize(s));
     n_total64 = 0;
-    n_in = 0;
+    n_in = tb_in = 0;
     for (int i = 0; i < nseg; i++) {
       n_total64 += h[i].hi - h[i].lo;
-      n_in += h_post[i];
+      n_in += h_post[2 * i];
+      tb_in += h_post[2 * i + 1];
     }
     n_total = (uint32_t)n_total64;
   } else if (nseg) {
@@ -407,6 +409,9 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     rs.bitmap_bits = 0;
   }
   UnionOut u;
+  // a small read: its result is placed before the host waits for the totals (one round trip
+  // less); the arrays are sized by the window's own upper bounds, so only where those are small
+  if (ranged && n_total <= 65536 && n_in <= (4u << 20) && tb_in <= (16u << 20)) u.early_out = &out;
   II2_TRY(k12_union(plan, rs, want_dec, want_enc, keep_empty, n_in, tb_in, u, s));
   res->T = u.h_totals[0];
   res->TB = u.h_totals[1];

@@ -1982,11 +1982,12 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   uint64_t* h_tot = pinned_scratch();  // 8 words
   if (!h_tot) return II2_ERR_NOMEM;
   // bucket totals -> prefixes -> host (synchronises the stream)
-  auto totals = [&]() -> int {
+  auto totals = [&](bool emit_early = false) -> int {
     ProfScope scope("k12_scan_sync", s);
     // four scans, Σ bk_D (terms_merged) and the copy of the eight totals to the host: one launch
     II2_TRY(exclusive_scan_multi_sum_to_host(u.bk_raw.p, u.bk_out.p, B + 1, 4, u.totals.p, u.bk_D.p, B,
                                              4, h_tot, 8, s));
+    if (emit_early) II2_TRY(k6_emit_early(plan, u, n_in, tb_in, *u.early_out, s));
     II2_CUDA_TRY(cudaStreamSynchronize(s));
     return II2_OK;
   };
@@ -2022,8 +2023,9 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
       ProfScope scope("k12f_bucket", s);
       II2_TRY(k12f_launch(f, B, s));
     }
-    // optimistic: scan right away; redone only if buckets were deferred
-    II2_TRY(totals());
+    // optimistic: scan right away (and, for a small call, place the result before waiting);
+    // redone only if buckets were deferred
+    II2_TRY(totals(u.early_out != nullptr));
     u.n_def = (uint32_t)h_tot[7];
     if (u.n_def) {
       II2_TRY(general(u.n_def, u.def_list.p));

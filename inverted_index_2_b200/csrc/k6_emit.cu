@@ -305,11 +305,71 @@ __global__ void __launch_bounds__(K6_THREADS) k6_dense_kernel(const K6DenseArgs 
   }
 }
 
+static void k6_dense_args(const MergePlan& plan, const UnionOut& u, const EmitOut& out, K6DenseArgs& d) {
+  const uint32_t N = plan.n_total;
+  d.bk_pos = plan.bk_pos();
+  d.bk_P = plan.bk_P();
+  d.bk_E = plan.bk_E();
+  d.bk_TB = plan.bk_TB();
+  d.bk_mode = u.bk_mode.p;
+  d.bk_raw = u.bk_raw.p;
+  d.bk_out = u.bk_out.p;
+  d.nb1 = plan.n_buckets + 1;
+  d.want_dec = u.want_dec ? 1 : 0;
+  d.want_enc = u.want_enc ? 1 : 0;
+  d.st_tb = u.st_tb.p;
+  d.st_toff = u.st_off.p;
+  d.st_eoff = u.st_off.p + N;
+  d.st_poff = u.st_off.p + 2 * (size_t)N;
+  d.st_enc = u.tmp_enc.p;
+  d.st_post = u.tmp_post.p;
+  d.o_term_bytes = out.term_bytes.p;
+  d.o_term_off = out.term_off.p;
+  d.o_post = out.post.p;
+  d.o_post_off = out.post_off.p;
+  d.o_val_words = out.val_words.p;
+  d.o_val_off = out.val_off.p;
+}
+
+int k6_emit_early(const MergePlan& plan, UnionOut& u, uint64_t n_in, uint64_t tb_in, EmitOut& out,
+                  cudaStream_t s) {
+  const uint64_t N = plan.n_total;
+  II2_TRY(out.term_bytes.alloc(tb_in, s, 32));
+  II2_TRY(out.term_off.alloc(N + 1, s, 16));
+  if (u.want_dec) {
+    II2_TRY(out.post.alloc(n_in, s, 16));
+    II2_TRY(out.post_off.alloc(N + 1, s, 16));
+  }
+  if (u.want_enc) {
+    II2_TRY(out.val_words.alloc(n_in + n_in / 4 + 6 * N + 16, s, 16));
+    II2_TRY(out.val_off.alloc(N, s, 16));
+  }
+  K6DenseArgs d;
+  k6_dense_args(plan, u, out, d);
+  ProfScope scope("k6_emit", s);
+  II2_LAUNCH_CHAIN(k6_dense_kernel, div_up(plan.n_buckets, K6_WARPS), K6_THREADS, 0, s, d, plan.n_buckets);
+  u.emitted_early = true;
+  return II2_OK;
+}
+
 int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t s) {
   const uint64_t T = u.h_totals[0], TB = u.h_totals[1], P = u.h_totals[2], E = u.h_totals[3];
   if (TB >= (1ull << 32)) {
     set_last_error("merged term dictionary exceeds 4 GiB of term bytes");
     return II2_ERR_UNSUPPORTED;
+  }
+  if (u.emitted_early && u.n_def == 0) {  // every bucket was placed by k6_emit_early: exact sizes only
+    out.term_bytes.n = TB;
+    out.term_off.n = T + 1;
+    if (u.want_dec) {
+      out.post.n = P;
+      out.post_off.n = T + 1;
+    }
+    if (u.want_enc) {
+      out.val_words.n = E;
+      out.val_off.n = T;
+    }
+    return II2_OK;
   }
   II2_TRY(out.term_bytes.alloc(TB, s, 32));
   II2_TRY(out.term_off.alloc(T + 1, s, 16));
@@ -342,30 +402,8 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
   a.o_val_off = out.val_off.p;
   ProfScope scope("k6_emit", s);
   if (u.fused) {
-    const uint32_t N = plan.n_total;
     K6DenseArgs d;
-    d.bk_pos = plan.bk_pos();
-    d.bk_P = plan.bk_P();
-    d.bk_E = plan.bk_E();
-    d.bk_TB = plan.bk_TB();
-    d.bk_mode = u.bk_mode.p;
-    d.bk_raw = u.bk_raw.p;
-    d.bk_out = u.bk_out.p;
-    d.nb1 = plan.n_buckets + 1;
-    d.want_dec = a.want_dec;
-    d.want_enc = a.want_enc;
-    d.st_tb = u.st_tb.p;
-    d.st_toff = u.st_off.p;
-    d.st_eoff = u.st_off.p + N;
-    d.st_poff = u.st_off.p + 2 * (size_t)N;
-    d.st_enc = u.tmp_enc.p;
-    d.st_post = u.tmp_post.p;
-    d.o_term_bytes = out.term_bytes.p;
-    d.o_term_off = out.term_off.p;
-    d.o_post = out.post.p;
-    d.o_post_off = out.post_off.p;
-    d.o_val_words = out.val_words.p;
-    d.o_val_off = out.val_off.p;
+    k6_dense_args(plan, u, out, d);
     II2_LAUNCH_CHAIN(k6_dense_kernel, div_up(plan.n_buckets, K6_WARPS), K6_THREADS, 0, s, d, plan.n_buckets);
     if (u.n_def) {  // the buckets the general kernels ran: one CTA each, from their records
       a.list = u.def_list.p;

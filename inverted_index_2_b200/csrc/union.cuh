@@ -115,6 +115,12 @@ struct UnionOut {
   uint64_t terms_merged = 0;   // Σ bk_D
   bool keep_empty = false;     // reads without a filter keep terms whose list is empty
   bool want_dec = false, want_enc = false;
+  // Early emit (small fused calls): the caller names the result; K12 launches the dense
+  // placement into arrays sized by the input's upper bounds right behind the bucket kernel and
+  // the totals, BEFORE it waits for the totals — one host round trip instead of two.  If a
+  // bucket had to be deferred the placement is simply redone by k6_emit.
+  struct EmitOut* early_out = nullptr;
+  bool emitted_early = false;
 };
 
 // K12: per bucket, finish the k-way term merge (group equal terms, order the distinct ones) and
@@ -141,6 +147,10 @@ struct EmitOut {
 // bytes/offsets, decoded postings and/or the `_val` stream with running byte offsets
 // (Writer.Append, file/writer.go:43-56).  Pure gather/copy: everything was computed by K12.
 int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t s);
+// The dense placement alone, into arrays sized by upper bounds (T <= instances, term bytes <=
+// tb_in, postings <= n_in); no synchronisation, reads the prefixes on the device.
+int k6_emit_early(const MergePlan& plan, UnionOut& u, uint64_t n_in, uint64_t tb_in, EmitOut& out,
+                  cudaStream_t s);
 
 // First and last term of the merged order (pre-filter min/max, shard.go:176-179).
 // d_out: [0]=len_min [1]=len_max (u32), bytes from +8 (min then max); needs 8 + 2*65536 bytes.

@@ -1,0 +1,4 @@
+#!/bin/bash
+# early emit for small fused reads: parity, latency
+T=r03n
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -x -q -m gpu > gpurun_out/${T}_tests.log 2>&1; tail -4 gpurun_out/${T}_tests.log
