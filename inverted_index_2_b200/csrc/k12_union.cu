@@ -1130,8 +1130,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 8 : 5) k2_medium_kernel(con
   pdl_enter();
   constexpr int MED_THREADS = NW * 32;
   constexpr uint32_t MED_CAP = NW * MED_RUN;  // values one CTA of NW warps unions
-  __shared__ uint32_t s_v[MED_CAP];                 // sorted runs / merge ping-pong / survivors
-  __shared__ uint32_t s_o[MED_CAP + MED_CAP / 16];  // gathered (padded runs) / ping-pong / survivors
+  __shared__ uint32_t s_v[MED_CAP];                 // source pointers / exchange buffer / survivors
+  __shared__ uint32_t s_o[MED_CAP + MED_CAP / 16];  // gathered values (padded runs) / exchange buffer
   __shared__ uint32_t s_moff[kMaxSegs + 1];    // prefix of the source lengths
   __shared__ uint64_t s_ws[MED_THREADS / 32 + 2];
   __shared__ uint32_t s_stage[(MED_THREADS / 32) * intcomp::kStageWords];
@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 8 : 5) k2_medium_kernel(con
       }
     }
     __syncthreads();
-    uint32_t* const oth = s_v;
+    uint32_t* const oth = s_v;  // the survivors
     // ---- output space, then the stream and the values
     if (tid == 0) {
       s_pos[0] = atomicAdd(&a.out_cursor[0], (unsigned long long)outn);
