@@ -294,11 +294,19 @@ k4_windows(const SegDesc* h_segs, SegDesc* d_segs, SegDesc* h_out,
 }
 
 // ------------------------------------------------------------------ the device pipeline
+// Point reads (see run_pipeline_impl): segments and postings the speculation covers.
+constexpr uint32_t kPointMaxSegs = 256;
+constexpr uint64_t kPointMaxPostings = 4096;
+static bool point_reads_enabled() {  // II2_POINT_READ=0: always wait for the windows (tuning / tests)
+  const char* e = getenv("II2_POINT_READ");
+  return !(e && e[0] == '0');
+}
+
 // segs: resident segments; [min,max] optional; rem optional.
 int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t minlen,
                       bool has_min, const uint8_t* max, size_t maxlen, bool has_max,
                       const ii2_removed* rem, bool want_dec, bool want_enc, bool want_minmax,
-                      bool keep_empty, ii2_result** res_out, cudaStream_t s) {
+                      bool keep_empty, ii2_result** res_out, cudaStream_t s, bool allow_spec = true) {
   ProfScope pipe_scope("pipeline_total", s);
   std::unique_ptr<ii2_result> res(new ii2_result());
   res->has_dec = want_dec;
@@ -346,6 +354,17 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   II2_TRY(d_segs.alloc_scratch(nsegx, s));
   uint32_t n_total = (uint32_t)n_total64;
   const bool ranged = has_min || has_max;
+  bool spec = false;
+  auto windows_back = [&]() {  // after a synchronisation: the windows are in the pinned block
+    n_total64 = 0;
+    n_in = tb_in = 0;
+    for (int i = 0; i < nseg; i++) {
+      n_total64 += h[i].hi - h[i].lo;
+      n_in += h_post[2 * i];
+      tb_in += h_post[2 * i + 1];
+    }
+    n_total = (uint32_t)n_total64;
+  };
   if (ranged && nseg) {
     ProfScope win_scope("k4_windows_sync", s);
     DevBuf<uint8_t> d_bounds;
@@ -361,22 +380,28 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     if (!ticket) return II2_ERR_NOMEM;
     II2_LAUNCH_CHAIN(k4_windows, div_up(nseg, 4), 256, 0, s, h, d_segs.p, h, h_post, nseg, bounds,
                      (uint32_t)minlen, has_min ? 1 : 0, (uint32_t)maxlen, has_max ? 1 : 0, ticket);
-    // the windows come back: the planner spreads its samples over them
-    II2_CUDA_TRY(cudaStreamSynchronize(s));
-    n_total64 = 0;
-    n_in = tb_in = 0;
-    for (int i = 0; i < nseg; i++) {
-      n_total64 += h[i].hi - h[i].lo;
-      n_in += h_post[2 * i];
-      tb_in += h_post[2 * i + 1];
+    // A point read (min == max) holds at most one instance per segment, all of the same term:
+    // the rest of the call is queued behind the windows kernel with those bounds, without
+    // waiting for the windows (a round trip less); the plan empties itself on the device if
+    // the postings exceed the speculation, and the call is then run again the ordinary way.
+    spec = allow_spec && point_reads_enabled() && has_min && has_max && minlen == maxlen &&
+           (minlen == 0 || memcmp(min, max, minlen) == 0) && nseg <= (int)kPointMaxSegs &&
+           k12_takes_fused((uint64_t)nseg, nseg);
+    if (spec) {
+      n_total = (uint32_t)nseg;
+      n_in = kPointMaxPostings;
+      tb_in = (uint64_t)nseg * minlen;
+    } else {
+      // the windows come back: the planner spreads its samples over them
+      II2_CUDA_TRY(cudaStreamSynchronize(s));
+      windows_back();
     }
-    n_total = (uint32_t)n_total64;
   } else if (nseg) {
     II2_TRY(small_copy(d_segs.p, h, sizeof(SegDesc) * nseg, s));
   }
 
   EmitOut& out = res->out;
-  if (n_total == 0) {  // nothing in range / no terms at all: empty result
+  if (n_total == 0 && !spec) {  // nothing in range / no terms at all: empty result
     II2_TRY(out.term_bytes.alloc(0, s, 32));
     II2_TRY(out.term_off.alloc(1, s));
     II2_CUDA_TRY(cudaMemsetAsync(out.term_off.p, 0, 4, s));
@@ -398,6 +423,8 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   plan.k = nseg;
   plan.n_total = n_total;
   plan.segs = d_segs.p;
+  plan.speculative = spec;
+  plan.spec_max_postings = kPointMaxPostings;
   II2_TRY(k1_build_plan(plan, h, h_sbase, s));
   RemovedSet rs;
   if (rem) {
@@ -413,6 +440,14 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
   // less); the arrays are sized by the window's own upper bounds, so only where those are small
   if (ranged && n_total <= 65536 && n_in <= (4u << 20) && tb_in <= (16u << 20)) u.early_out = &out;
   II2_TRY(k12_union(plan, rs, want_dec, want_enc, keep_empty, n_in, tb_in, u, s));
+  if (spec) {  // k12_union synchronised: the windows are back
+    windows_back();
+    if (n_total64 > (uint64_t)nseg || n_in > kPointMaxPostings) {  // the plan emptied itself
+      res.reset();
+      return run_pipeline_impl(segs, nseg, min, minlen, has_min, max, maxlen, has_max, rem, want_dec,
+                               want_enc, want_minmax, keep_empty, res_out, s, false);
+    }
+  }
   res->T = u.h_totals[0];
   res->TB = u.h_totals[1];
   res->P = u.h_totals[2];

@@ -1789,6 +1789,12 @@ extern "C" int ii2_debug_k1b_clocks(unsigned long long* out, int reset) {
 #endif
 
 // ---------------------------------------------------------------- host driver
+bool k12_takes_fused(uint64_t N, int k) {
+  const char* fused_env = getenv("II2_FUSED");
+  const bool fused_on = fused_env ? atoi(fused_env) != 0 : N <= 65536;
+  return fused_on && k12f_supported(k);
+}
+
 int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool want_enc,
               bool keep_empty, uint64_t n_in, uint64_t tb_in, UnionOut& u, cudaStream_t s) {
   u.keep_empty = keep_empty;
@@ -1802,9 +1808,7 @@ int k12_union(const MergePlan& plan, const RemovedSet& rem, bool want_dec, bool 
   // general kernels stay the default; the fused path moves 1.6x fewer DRAM bytes per step.
   // Small calls (narrow range reads) are launch-latency bound and the fused path has three
   // launches fewer: 185 vs 219 us for a 0.1 % read of C3; it takes them unless II2_FUSED=0.
-  const char* fused_env = getenv("II2_FUSED");
-  const bool fused_on = fused_env ? atoi(fused_env) != 0 : N <= 65536;
-  u.fused = fused_on && k12f_supported(k);
+  u.fused = k12_takes_fused(N, k);
   DevBuf<GroupIn> gin;
   DevBuf<uint64_t> src_ptr;
   DevBuf<uint32_t> src_len;

@@ -370,7 +370,8 @@ k1_bucket_stats(int k, uint32_t S, SampleArrays sp, const uint32_t* __restrict__
 __global__ void __launch_bounds__(256)
 k1_plan_single(const SegDesc* __restrict__ segs, int k, uint32_t* __restrict__ part,
                uint32_t* __restrict__ btb, uint64_t* __restrict__ bpo, uint64_t* __restrict__ bk_WP,
-               uint32_t* __restrict__ bk_cpl, uint64_t* __restrict__ totals) {
+               uint32_t* __restrict__ bk_cpl, uint64_t* __restrict__ totals, uint64_t max_w,
+               uint64_t max_p) {
   pdl_enter();
   __shared__ uint64_t ws[256 / 32 + 2];
   uint64_t w = 0, p = 0, t = 0;
@@ -393,6 +394,8 @@ k1_plan_single(const SegDesc* __restrict__ segs, int k, uint32_t* __restrict__ p
   block_exclusive_scan(p, ws, tp);
   block_exclusive_scan(t, ws, tt);
   if (threadIdx.x == 0) {
+    const bool fits = tw <= max_w && tp <= max_p;  // a speculative plan: else an empty bucket
+    if (!fits) tw = tp = tt = 0;
     const uint64_t v[4] = {tw, tp, tp + (tp >> 2) + 6 * tw, tt};  // as k1_bucket_stats
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -502,7 +505,7 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
     const long v = e ? atol(e) : 768;
     return (v >= 0 && v <= 1024) ? (uint32_t)v : 768u;
   }();
-  if (N <= single_max) want = 0;
+  if (N <= single_max || plan.speculative) want = 0;
   // II2_COALESCE=<fine> (default 1 = off): a partition `fine` times finer, coalesced afterwards.
   // Measured on B200 (C2, profiles/r02_experiments.md): fine = 4 takes the buckets above 1024
   // instances from 9.6 % to 2 %, but the finer partition costs +0.5 ms of plan time (0.38 ->
@@ -582,8 +585,14 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   }
   if (S == 0 && fine == 1) {
     II2_LAUNCH_CHAIN(k1_plan_single, 1, 256, 0, s, plan.segs, k, plan.part.p, plan.btb.p, plan.bpo.p,
-                     plan.bk_WP.p, plan.bk_cpl.p, plan.totals.p);
+                     plan.bk_WP.p, plan.bk_cpl.p, plan.totals.p,
+                     plan.speculative ? (uint64_t)N : ~0ull,
+                     plan.speculative ? plan.spec_max_postings : ~0ull);
     return II2_OK;
+  }
+  if (plan.speculative) {
+    set_last_error("k1: a speculative plan must be the single bucket");
+    return II2_ERR_INVALID;
   }
   DevBuf<uint32_t> d_base, d_u32;
   DevBuf<uint64_t> d_u64;

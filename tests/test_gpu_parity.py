@@ -489,6 +489,46 @@ def test_read_range_matches_oracle(engine, orc, merge_path):
                           orc.read_range(w.segments, lo, hi, removed=w.removed))
 
 
+def test_point_reads(engine, orc, merge_path, monkeypatch):
+    """min == max: on the fused path the call is queued behind the windows kernel without waiting
+    for the windows (at most one instance per segment, postings speculated <= 4096).  A term that
+    is everywhere, in one segment, nowhere (between terms, before the first, after the last), the
+    empty term; with and without the removed filter; a term whose lists exceed the speculation
+    (the plan empties itself on the device and the call runs again); a term of > 256 values (the
+    bucket is deferred to the general kernels); the same with the speculation switched off."""
+    rng = np.random.default_rng(5)
+    nseg = 9
+    per_seg = [[] for _ in range(nseg)]
+    for s_i in range(nseg):
+        per_seg[s_i].append((b"everywhere", sorted(set(rng.integers(0, 5000, size=20).tolist()))))
+        per_seg[s_i].append((b"filler%02d" % s_i, [s_i, s_i + 100]))
+        per_seg[s_i].append((b"big", sorted(set(rng.integers(0, 1 << 20, size=700).tolist()))))    # 6300 > 4096 in
+        per_seg[s_i].append((b"mid", sorted(set(rng.integers(0, 1 << 20, size=60).tolist()))))     # ~540 values: deferred
+    per_seg[3].append((b"only3", [9, 8, 8, 1]))       # single source: order and duplicates kept
+    per_seg[4].append((b"", [4, 2]))                  # the empty term
+    segs = [FlatSegment.from_items(sorted(x)) for x in per_seg]
+    removed = np.unique(rng.integers(0, 5000, size=800)).astype(np.uint32)
+    terms = [b"everywhere", b"only3", b"", b"big", b"mid", b"filler04", b"absent", b"everywhera", b"zzz",
+             b"\x00", b"filler"]
+    for mode in (None, "0"):
+        if mode is None:
+            monkeypatch.delenv("II2_POINT_READ", raising=False)
+        else:
+            monkeypatch.setenv("II2_POINT_READ", mode)
+        for t in terms:
+            assert_read_equal(engine.read_range(segs, t, t), orc.read_range(segs, t, t))
+            assert_read_equal(engine.read_range(segs, t, t, removed=removed),
+                              orc.read_range(segs, t, t, removed=removed))
+    # resident segments: the same through the device API, results released between calls
+    dsegs = [engine.upload(x) for x in segs]
+    for t in terms:
+        r = engine.read_range_dev(dsegs, t, t, None)
+        assert_read_equal(r.download_read(), orc.read_range(segs, t, t))
+        r.release()
+    for d in dsegs:
+        d.release()
+
+
 def test_window_search_boundaries(engine, orc):
     """The 32-way warp search of the range windows (K4) and of the prefix windows (K5): segment
     sizes around the lane count and its powers (0, 1, 31..34, 1088..1090 = 33^2 +- 1, 36000 >
