@@ -137,7 +137,10 @@ uint64_t* pinned_scratch() {
 }
 
 uint32_t* device_tickets() {
-  static thread_local uint32_t* p = nullptr;
+  static thread_local uint32_t* per_dev[64] = {};  // one block per (host thread, device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  uint32_t*& p = per_dev[dev];
   if (!p) {
     void* q = nullptr;
     if (cudaMalloc(&q, 256) != cudaSuccess) return nullptr;
