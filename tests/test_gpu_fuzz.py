@@ -2,7 +2,7 @@
 generated shard contents — skewed term alphabets with long shared prefixes, empty and very
 uneven segments, empty lists, unsorted single-source lists (survey Q4), duplicates across
 segments, values up to 2^32-1, removed lists with and without a bitmap, open / closed / absent
-range bounds — on both bucket pipelines.  Deterministic (fixed seeds): a failure reproduces."""
+range bounds, point reads — on both bucket pipelines.  Deterministic (fixed seeds): a failure reproduces."""
 import numpy as np
 import pytest
 
@@ -40,7 +40,10 @@ def _segments(rng, vocab, nseg, hi_bits):
     return segs
 
 
-@pytest.mark.parametrize("seed", range(24))
+import os
+
+# II2_FUZZ_SEEDS=<n> widens the run (a one-off before a release; the default stays short)
+@pytest.mark.parametrize("seed", range(int(os.environ.get("II2_FUZZ_SEEDS", "24"))))
 @pytest.mark.parametrize("path", ["0", "1"])
 def test_random_shard_contents(engine, orc, monkeypatch, seed, path):
     monkeypatch.setenv("II2_FUSED", path)
@@ -63,3 +66,9 @@ def test_random_shard_contents(engine, orc, monkeypatch, seed, path):
         assert r.n_terms == e.n_terms
         for f in ("term_bytes", "term_off", "post", "post_off"):
             assert np.array_equal(getattr(r, f), getattr(e, f)), (f, lo, hi)
+    # point reads (min == max): a term of the vocabulary and one that is absent, with the filter
+    for t in (bytes(rng.choice(vocab)), bytes(rng.choice(vocab)) + b"\x01"):
+        r, e = engine.read_range(segs, t, t, removed=removed), orc.read_range(segs, t, t, removed=removed)
+        assert r.n_terms == e.n_terms
+        for f in ("term_bytes", "term_off", "post", "post_off"):
+            assert np.array_equal(getattr(r, f), getattr(e, f)), (f, t)
