@@ -72,3 +72,41 @@ def test_random_shard_contents(engine, orc, monkeypatch, seed, path):
         assert r.n_terms == e.n_terms
         for f in ("term_bytes", "term_off", "post", "post_off"):
             assert np.array_equal(getattr(r, f), getattr(e, f)), (f, t)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("II2_FUZZ_HEAVY_SEEDS", "8"))))
+def test_random_heavy_terms(engine, orc, seed):
+    """Few terms with long lists over many segments: the warp- and CTA-per-term unions (257 ...
+    4096 values, both gathers, both CTA shapes), the multi-CTA path beyond, next to light terms in
+    the same buckets; merge (both outputs) and a range read with the filter."""
+    rng = np.random.default_rng(7000 + seed)
+    hi_bits = [12, 20, 32][seed % 3]
+    vocab = _terms(rng, int(rng.integers(2, 30)), "alpha")
+    nseg = int(rng.integers(2, 48))
+    sizes = [0, 1, 5, 40, 130, 300, 900, 2500]
+    weights = np.array([.05, .15, .15, .2, .15, .15, .1, .05])
+    segs = []
+    for s in range(nseg):
+        frac = rng.choice([0.2, 0.6, 1.0])
+        items = []
+        for t in vocab:
+            if rng.random() >= frac:
+                continue
+            n = int(rng.choice(sizes, p=weights))
+            vals = rng.integers(0, 1 << hi_bits, size=n, dtype=np.int64)
+            if rng.random() < 0.8:
+                vals = np.unique(vals)
+            items.append((t, vals.tolist()))
+        segs.append(FlatSegment.from_items(items))
+    nrem = int(rng.choice([0, 50, 3000]))
+    removed = np.unique(rng.integers(0, 1 << hi_bits, size=nrem, dtype=np.int64)).astype(np.uint32) if nrem else None
+    got, exp = engine.merge(segs, removed, decoded=True), orc.merge(segs, removed, decoded=True)
+    for f in ("terms_count", "val_size", "terms_merged", "postings_in", "postings_out"):
+        assert getattr(got, f) == getattr(exp, f), f
+    for f in ("term_bytes", "term_off", "val_off", "val_bytes", "post", "post_off"):
+        assert np.array_equal(getattr(got, f), getattr(exp, f)), f
+    lo, hi = vocab[len(vocab) // 4], vocab[-1]
+    r, e = engine.read_range(segs, lo, hi, removed=removed), orc.read_range(segs, lo, hi, removed=removed)
+    assert r.n_terms == e.n_terms
+    for f in ("term_bytes", "term_off", "post", "post_off"):
+        assert np.array_equal(getattr(r, f), getattr(e, f)), f
