@@ -30,6 +30,7 @@ k_dec_count(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
             uint64_t* __restrict__ counts, uint32_t* __restrict__ n_work,
             uint32_t* __restrict__ huge_list, uint32_t* __restrict__ huge_gstart,
             uint32_t* __restrict__ huge_tstart, int* __restrict__ err) {
+  pdl_enter();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = woff[i], b = woff[i + 1];
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256)
 k_dec_tile_fill(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
                 const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_tstart,
                 uint32_t* __restrict__ tile_list) {
+  pdl_enter();
   const uint32_t L = blockIdx.x;
   const uint64_t a = woff[huge_list[L]];
   const uint32_t nt = (words[a + 1] - 3 + kTileWords - 1) / kTileWords;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(kWalkThreads)
 k_dec_tile_maps(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff,
                 const uint32_t* __restrict__ huge_list, const uint32_t* __restrict__ huge_tstart,
                 const uint32_t* __restrict__ tile_list, uint32_t* __restrict__ maps) {
+  pdl_enter();
   extern __shared__ __align__(16) uint16_t nxt_dyn[];
   const uint32_t tile = blockIdx.x, L = tile_list[tile];
   const uint32_t* w = words + woff[huge_list[L]];
@@ -115,6 +118,7 @@ k_dec_tile_chain(const uint32_t* __restrict__ words, const uint64_t* __restrict_
                  const uint32_t* __restrict__ huge_tstart, const uint32_t* __restrict__ maps,
                  uint32_t* __restrict__ tile_entry, uint32_t* __restrict__ tile_bbase,
                  uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist, int* __restrict__ err) {
+  pdl_enter();
   __shared__ uint32_t smap[kChainBatch * kTileEntries];
   __shared__ uint32_t s_entry, s_bb;
   const uint32_t L = blockIdx.x;
@@ -165,6 +169,7 @@ k_dec_tile_walk(const uint32_t* __restrict__ words, const uint64_t* __restrict__
                 const uint32_t* __restrict__ huge_tstart, const uint32_t* __restrict__ tile_list,
                 const uint32_t* __restrict__ tile_entry, const uint32_t* __restrict__ tile_bbase,
                 uint64_t* __restrict__ bpos, uint32_t* __restrict__ blist) {
+  pdl_enter();
   extern __shared__ __align__(16) uint16_t nxt_dyn[];
   uint16_t* hdr = nxt_dyn + kTileWords;  // the headers of the tile, in order
   __shared__ uint32_t s_cnt;
@@ -197,6 +202,7 @@ k_dec_blocksum(const uint32_t* __restrict__ words, const uint64_t* __restrict__ 
                const uint32_t* __restrict__ huge_list, const uint64_t* __restrict__ bpos,
                const uint32_t* __restrict__ blist, uint32_t nblocks, uint64_t* __restrict__ bsum,
                int* __restrict__ err) {
+  pdl_enter();
   const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (blk > nblocks) return;
   uint32_t sum = 0;
@@ -218,6 +224,7 @@ k_dec_blocks(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wo
              const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ blist,
              uint32_t nblocks, const uint64_t* __restrict__ bscan,
              const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out) {
+  pdl_enter();
   const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (blk >= nblocks || bpos[blk] == ~0ull) return;
   const uint32_t L = blist[blk], gs = huge_gstart[L], i = huge_list[L];
@@ -236,6 +243,7 @@ k_dec_huge_tail(const uint32_t* __restrict__ words, const uint64_t* __restrict__
                 const uint32_t* __restrict__ huge_list, uint32_t n_huge,
                 const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out,
                 int* __restrict__ err) {
+  pdl_enter();
   const uint32_t L = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (L >= n_huge) return;
   const uint32_t i = huge_list[L];
@@ -251,6 +259,7 @@ k_dec_huge_tail(const uint32_t* __restrict__ words, const uint64_t* __restrict__
 __global__ void __launch_bounds__(kCodecThreads)
 k_valoff_to_woff(const uint64_t* __restrict__ val_off, uint64_t n, uint64_t val_size,
                  uint64_t* __restrict__ woff, int* __restrict__ err) {
+  pdl_enter();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   uint64_t o = i < n ? val_off[i] : val_size;
@@ -263,6 +272,7 @@ k_dec_short(const uint32_t* __restrict__ words, const uint64_t* __restrict__ wof
             const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out,
             uint32_t* __restrict__ worklist, uint32_t* __restrict__ n_work,
             int* __restrict__ err) {
+  pdl_enter();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = woff[i], b = woff[i + 1];
@@ -280,6 +290,7 @@ k_dec_long(const uint32_t* __restrict__ words, const uint64_t* __restrict__ woff
            const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out,
            const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work,
            int* __restrict__ err) {
+  pdl_enter();
   const uint32_t nw = *n_work;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nw; t += warps) {
@@ -317,10 +328,7 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
   II2_CUDA_TRY(cudaMemsetAsync(n_work.p, 0, 4 * sizeof(uint32_t), s));
   II2_CUDA_TRY(cudaMemsetAsync(out_off.p + nlists, 0, sizeof(uint64_t), s));
   if (nlists) {
-    k_dec_count<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_words, d_woff, nlists, out_off.p, n_work.p, huge_list.p, huge_gstart.p, huge_tstart.p,
-        err.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_dec_count, div_up(nlists, kCodecThreads), kCodecThreads, 0, s, d_words, d_woff, nlists, out_off.p, n_work.p, huge_list.p, huge_gstart.p, huge_tstart.p, err.p);
   }
   II2_TRY(exclusive_scan_u64(out_off.p, nlists + 1, d_total.p, s));
   uint64_t total = 0;
@@ -344,12 +352,8 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
     II2_TRY(out.alloc(total, s, 16));
   }
   if (nlists) {
-    k_dec_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_words, d_woff, nlists, out_off.p, out.p, worklist.p, n_work.p, err.p);
-    II2_LAUNCHED();
-    k_dec_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_words, d_woff, out_off.p, out.p, worklist.p,
-                                                     n_work.p, err.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_dec_short, div_up(nlists, kCodecThreads), kCodecThreads, 0, s, d_words, d_woff, nlists, out_off.p, out.p, worklist.p, n_work.p, err.p);
+    II2_LAUNCH_CHAIN(k_dec_long, kNumSMs * 4, kCodecThreads, 0, s, d_words, d_woff, out_off.p, out.p, worklist.p, n_work.p, err.p);
   }
   if (n_huge) {
     DevBuf<uint64_t> bpos, bsum;
@@ -369,35 +373,19 @@ int intcomp_decode_dev(const uint32_t* d_words, const uint64_t* d_woff, uint64_t
                                           (int)(kTileWords * 4)));
         attr_set = true;
       }
-      k_dec_tile_fill<<<n_huge, 256, 0, s>>>(d_words, d_woff, huge_list.p, huge_tstart.p, tile_list.p);
-      II2_LAUNCHED();
+      II2_LAUNCH_CHAIN(k_dec_tile_fill, n_huge, 256, 0, s, d_words, d_woff, huge_list.p, huge_tstart.p, tile_list.p);
       if (n_htiles) {
-        k_dec_tile_maps<<<n_htiles, kWalkThreads, kTileWords * 2, s>>>(
-            d_words, d_woff, huge_list.p, huge_tstart.p, tile_list.p, maps.p);
-        II2_LAUNCHED();
+        II2_LAUNCH_CHAIN(k_dec_tile_maps, n_htiles, kWalkThreads, kTileWords * 2, s, d_words, d_woff, huge_list.p, huge_tstart.p, tile_list.p, maps.p);
       }
-      k_dec_tile_chain<<<n_huge, kWalkThreads, 0, s>>>(d_words, d_woff, huge_list.p, huge_gstart.p,
-                                                       huge_tstart.p, maps.p, tile_entry.p,
-                                                       tile_bbase.p, bpos.p, blist.p, err.p);
-      II2_LAUNCHED();
+      II2_LAUNCH_CHAIN(k_dec_tile_chain, n_huge, kWalkThreads, 0, s, d_words, d_woff, huge_list.p, huge_gstart.p, huge_tstart.p, maps.p, tile_entry.p, tile_bbase.p, bpos.p, blist.p, err.p);
       if (n_htiles) {
-        k_dec_tile_walk<<<n_htiles, kWalkThreads, kTileWords * 4, s>>>(
-            d_words, d_woff, huge_list.p, huge_gstart.p, huge_tstart.p, tile_list.p, tile_entry.p,
-            tile_bbase.p, bpos.p, blist.p);
-        II2_LAUNCHED();
+        II2_LAUNCH_CHAIN(k_dec_tile_walk, n_htiles, kWalkThreads, kTileWords * 4, s, d_words, d_woff, huge_list.p, huge_gstart.p, huge_tstart.p, tile_list.p, tile_entry.p, tile_bbase.p, bpos.p, blist.p);
       }
     }
-    k_dec_blocksum<<<div_up(((uint64_t)n_hblocks + 1) * 32, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_words, d_woff, huge_list.p, bpos.p, blist.p, n_hblocks, bsum.p, err.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_dec_blocksum, div_up(((uint64_t)n_hblocks + 1) * 32, kCodecThreads), kCodecThreads, 0, s, d_words, d_woff, huge_list.p, bpos.p, blist.p, n_hblocks, bsum.p, err.p);
     II2_TRY(exclusive_scan_u64(bsum.p, (uint64_t)n_hblocks + 1, nullptr, s));
-    k_dec_blocks<<<div_up((uint64_t)n_hblocks * 32, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_words, d_woff, huge_list.p, huge_gstart.p, bpos.p, blist.p, n_hblocks, bsum.p, out_off.p,
-        out.p);
-    II2_LAUNCHED();
-    k_dec_huge_tail<<<div_up((uint64_t)n_huge * 32, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_words, d_woff, huge_list.p, n_huge, out_off.p, out.p, err.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_dec_blocks, div_up((uint64_t)n_hblocks * 32, kCodecThreads), kCodecThreads, 0, s, d_words, d_woff, huge_list.p, huge_gstart.p, bpos.p, blist.p, n_hblocks, bsum.p, out_off.p, out.p);
+    II2_LAUNCH_CHAIN(k_dec_huge_tail, div_up((uint64_t)n_huge * 32, kCodecThreads), kCodecThreads, 0, s, d_words, d_woff, huge_list.p, n_huge, out_off.p, out.p, err.p);
   }
   II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 24, err.p, sizeof(herr), cudaMemcpyDeviceToHost, s));
   II2_CUDA_TRY(cudaStreamSynchronize(s));
@@ -416,9 +404,7 @@ int val_offsets_to_word_offsets(const uint64_t* d_val_off, uint64_t n, uint64_t 
   DevBuf<int> err;
   II2_TRY(err.alloc_scratch(1, s));
   II2_CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), s));
-  k_valoff_to_woff<<<div_up(n + 1, kCodecThreads), kCodecThreads, 0, s>>>(d_val_off, n, val_size,
-                                                                          woff.p, err.p);
-  II2_LAUNCHED();
+  II2_LAUNCH_CHAIN(k_valoff_to_woff, div_up(n + 1, kCodecThreads), kCodecThreads, 0, s, d_val_off, n, val_size, woff.p, err.p);
   // (readbacks land in the thread's pinned scratch: a pageable destination would make the copy
   // wait for every transfer in flight on other streams)
   II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 25, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -440,6 +426,7 @@ __global__ void __launch_bounds__(kCodecThreads)
 k_enc_size_short(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
                  uint64_t* __restrict__ sizes, uint32_t* __restrict__ worklist,
                  uint32_t* __restrict__ n_work) {
+  pdl_enter();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = off[i], n = off[i + 1] - a;
@@ -468,6 +455,7 @@ __global__ void __launch_bounds__(1024)
 k_enc_size_huge(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
                 uint32_t* __restrict__ tables, uint64_t* __restrict__ part, uint32_t ymax,
                 const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
+  pdl_enter();
   __shared__ uint64_t ws[1024 / 32 + 2];
   if (blockIdx.x >= n_work[1]) return;
   const uint32_t i = worklist[nlists - 1 - blockIdx.x];
@@ -497,6 +485,7 @@ k_enc_size_huge_fin(const uint32_t* __restrict__ in, const uint64_t* __restrict_
                     uint64_t nlists, uint64_t* __restrict__ sizes,
                     const uint64_t* __restrict__ part, uint32_t ymax,
                     const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
+  pdl_enter();
   const uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (h >= n_work[1]) return;
   const uint32_t i = worklist[nlists - 1 - h];
@@ -522,6 +511,7 @@ k_enc_emit_huge(const uint32_t* __restrict__ in, const uint64_t* __restrict__ of
                 const uint64_t* __restrict__ woff, uint32_t* __restrict__ words,
                 uint32_t* __restrict__ tables, const uint64_t* __restrict__ part, uint32_t ymax,
                 const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
+  pdl_enter();
   __shared__ uint64_t ws[1024 / 32 + 2];
   __shared__ uint32_t stage[32 * intcomp::kStageWords];
   if (blockIdx.x >= n_work[1]) return;
@@ -568,6 +558,7 @@ __global__ void __launch_bounds__(kCodecThreads)
 k_enc_size_long(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off,
                 uint64_t* __restrict__ sizes, const uint32_t* __restrict__ worklist,
                 const uint32_t* __restrict__ n_work) {
+  pdl_enter();
   const uint32_t nw = *n_work;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nw; t += warps) {
@@ -581,6 +572,7 @@ k_enc_size_long(const uint32_t* __restrict__ in, const uint64_t* __restrict__ of
 __global__ void __launch_bounds__(kCodecThreads)
 k_enc_emit_short(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off, uint64_t nlists,
                  const uint64_t* __restrict__ woff, uint32_t* __restrict__ words) {
+  pdl_enter();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlists) return;
   uint64_t a = off[i], n = off[i + 1] - a;
@@ -592,6 +584,7 @@ __global__ void __launch_bounds__(kCodecThreads)
 k_enc_emit_long(const uint32_t* __restrict__ in, const uint64_t* __restrict__ off,
                 const uint64_t* __restrict__ woff, uint32_t* __restrict__ words,
                 const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ n_work) {
+  pdl_enter();
   __shared__ uint32_t stage[kCodecThreads / 32][intcomp::kStageWords];
   const uint32_t nw = *n_work;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -633,18 +626,10 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
   II2_TRY(tables.alloc_scratch((nvals_hint >> 7) + nlists + 1, s));
   II2_TRY(part.alloc_scratch((size_t)huge_grid * ymax + 1, s));
   if (nlists) {
-    k_enc_size_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_in, d_off, nlists, woff.p, worklist.p, n_work.p);
-    II2_LAUNCHED();
-    k_enc_size_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_in, d_off, woff.p, worklist.p,
-                                                          n_work.p);
-    II2_LAUNCHED();
-    k_enc_size_huge<<<huge_dim, 1024, 0, s>>>(d_in, d_off, nlists, tables.p, part.p, ymax,
-                                              worklist.p, n_work.p);
-    II2_LAUNCHED();
-    k_enc_size_huge_fin<<<div_up((uint64_t)huge_grid * 32, kCodecThreads), kCodecThreads, 0, s>>>(
-        d_in, d_off, nlists, woff.p, part.p, ymax, worklist.p, n_work.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_enc_size_short, div_up(nlists, kCodecThreads), kCodecThreads, 0, s, d_in, d_off, nlists, woff.p, worklist.p, n_work.p);
+    II2_LAUNCH_CHAIN(k_enc_size_long, kNumSMs * 4, kCodecThreads, 0, s, d_in, d_off, woff.p, worklist.p, n_work.p);
+    II2_LAUNCH_CHAIN(k_enc_size_huge, huge_dim, 1024, 0, s, d_in, d_off, nlists, tables.p, part.p, ymax, worklist.p, n_work.p);
+    II2_LAUNCH_CHAIN(k_enc_size_huge_fin, div_up((uint64_t)huge_grid * 32, kCodecThreads), kCodecThreads, 0, s, d_in, d_off, nlists, woff.p, part.p, ymax, worklist.p, n_work.p);
   }
   II2_TRY(exclusive_scan_u64(woff.p, nlists + 1, d_total.p, s));
   II2_CUDA_TRY(cudaMemcpyAsync(pinned_scratch() + 26, d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -652,15 +637,9 @@ int intcomp_encode_dev(const uint32_t* d_in, const uint64_t* d_off, uint64_t nli
   const uint64_t total = pinned_scratch()[26];
   II2_TRY(words.alloc_scratch(total, s));
   if (nlists) {
-    k_enc_emit_short<<<div_up(nlists, kCodecThreads), kCodecThreads, 0, s>>>(d_in, d_off, nlists,
-                                                                             woff.p, words.p);
-    II2_LAUNCHED();
-    k_enc_emit_long<<<kNumSMs * 4, kCodecThreads, 0, s>>>(d_in, d_off, woff.p, words.p,
-                                                          worklist.p, n_work.p);
-    II2_LAUNCHED();
-    k_enc_emit_huge<<<huge_dim, 1024, 0, s>>>(d_in, d_off, nlists, woff.p, words.p, tables.p,
-                                              part.p, ymax, worklist.p, n_work.p);
-    II2_LAUNCHED();
+    II2_LAUNCH_CHAIN(k_enc_emit_short, div_up(nlists, kCodecThreads), kCodecThreads, 0, s, d_in, d_off, nlists, woff.p, words.p);
+    II2_LAUNCH_CHAIN(k_enc_emit_long, kNumSMs * 4, kCodecThreads, 0, s, d_in, d_off, woff.p, words.p, worklist.p, n_work.p);
+    II2_LAUNCH_CHAIN(k_enc_emit_huge, huge_dim, 1024, 0, s, d_in, d_off, nlists, woff.p, words.p, tables.p, part.p, ymax, worklist.p, n_work.p);
   }
   if (total_words) *total_words = total;
   return II2_OK;
