@@ -10,7 +10,8 @@ filter + intcomp encode, shard.go:158-212) of all resident segments of this rank
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs measured HBM peak
   cpu_baseline  the CPU oracle (C restatement of the Go path) on a bounded sample, rank 0, N=1
   range_read_us  BASELINE configs[2] (N=1): term-range reads over 256 resident segments with the
-             5 % removed filter, ranges of 0.1 / 1 / 10 / 100 % of the term space, median / p99 us
+             5 % removed filter, a single term and ranges of 0.1 / 1 / 10 / 100 % of the term
+             space, median / p99 us
 Multi-GPU: shards are independent (shard.go:19-20) -> one process per GPU, each compacting its
 own term range, no data-path collective; `value` is weak scaling (every rank its own C2 shard
 range).  `strong` (N > 1, BASELINE configs[4]): ONE synthetic index partitioned by the reference's

@@ -208,7 +208,10 @@ void ii2_removed_release(ii2_removed* rem);
  * in HBM until downloaded.  `flags` selects what a merge produces:
  * II2_RESULT_ENCODED = the intcomp `_val` stream + FST outputs (what Writer.Append
  * writes, file/writer.go:43-56), II2_RESULT_DECODED = decoded postings (needed by
- * ii2_result_to_seg / ii2_result_download_read); 0 means decoded only. */
+ * ii2_result_to_seg / ii2_result_download_read); 0 means decoded only.
+ * The result of a small read (<= 65 536 term instances in range) holds device arrays sized by
+ * the range's input (it is placed before the output sizes are known: one host round trip
+ * less); the counts in ii2_result_info are exact.  Release results you do not keep. */
 #define II2_RESULT_ENCODED 1u
 #define II2_RESULT_DECODED 2u
 int ii2_merge_dev(ii2_seg* const* segs, int nseg, const ii2_removed* rem, uint32_t flags,
