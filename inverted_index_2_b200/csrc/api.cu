@@ -297,9 +297,11 @@ k4_windows(const SegDesc* h_segs, SegDesc* d_segs, SegDesc* h_out,
 // Point reads (see run_pipeline_impl): segments and postings the speculation covers.
 constexpr uint32_t kPointMaxSegs = 256;
 constexpr uint64_t kPointMaxPostings = 4096;
-static bool point_reads_enabled() {  // II2_POINT_READ=0: always wait for the windows (tuning / tests)
+// II2_POINT_READ (tuning / tests): 2 = the one-kernel point read (default), 1 = the general
+// kernels queued behind the windows kernel speculatively, 0 = a read like any other.
+static int point_read_mode() {
   const char* e = getenv("II2_POINT_READ");
-  return !(e && e[0] == '0');
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
 }
 
 // segs: resident segments; [min,max] optional; rem optional.
@@ -350,6 +352,43 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     set_last_error("more than 2^32-1 term instances in one call");
     return II2_ERR_UNSUPPORTED;
   }
+  // ---- Read(min == max), decoded output: the whole call is one kernel
+  if (allow_spec && point_read_mode() == 2 && nseg > 0 && has_min && has_max && minlen == maxlen &&
+      minlen <= kPointMaxTerm && (minlen == 0 || memcmp(min, max, minlen) == 0) && want_dec && !want_enc) {
+    if (minlen) memcpy(h_bounds, min, minlen);
+    uint64_t* const h_res = pinned_scratch() + 32;
+    RemovedSet rs0;
+    if (rem) {
+      rs0 = rem->set();
+    } else {
+      rs0.sorted = nullptr;
+      rs0.n = 0;
+      rs0.bitmap = nullptr;
+      rs0.bitmap_bits = 0;
+    }
+    II2_TRY(k4_point_read(h, nseg, h_bounds, (uint32_t)minlen, rs0, keep_empty, res->out, h_res, s));
+    II2_CUDA_TRY(cudaStreamSynchronize(s));
+    if (h_res[0] == 1) {
+      res->T = h_res[1];
+      res->TB = res->T ? minlen : 0;
+      res->P = h_res[2];
+      res->E = 0;
+      res->postings_in = h_res[3];
+      res->terms_merged = h_res[4] ? 1 : 0;
+      res->out.term_bytes.n = res->TB;
+      res->out.term_off.n = res->T + 1;
+      res->out.post.n = res->P;
+      res->out.post_off.n = res->T + 1;
+      if (want_minmax && res->terms_merged) {  // pre-filter min / max of the merged order: the term
+        res->min_term.assign(reinterpret_cast<const char*>(min), minlen);
+        res->max_term = res->min_term;
+        res->has_minmax = true;
+      }
+      *res_out = res.release();
+      return II2_OK;
+    }
+    // more than 4096 values: the general path below
+  }
   DevBuf<SegDesc> d_segs;
   II2_TRY(d_segs.alloc_scratch(nsegx, s));
   uint32_t n_total = (uint32_t)n_total64;
@@ -384,7 +423,7 @@ int run_pipeline_impl(ii2_seg* const* segs, int nseg, const uint8_t* min, size_t
     // the rest of the call is queued behind the windows kernel with those bounds, without
     // waiting for the windows (a round trip less); the plan empties itself on the device if
     // the postings exceed the speculation, and the call is then run again the ordinary way.
-    spec = allow_spec && point_reads_enabled() && has_min && has_max && minlen == maxlen &&
+    spec = allow_spec && point_read_mode() >= 1 && has_min && has_max && minlen == maxlen &&
            (minlen == 0 || memcmp(min, max, minlen) == 0) && nseg <= (int)kPointMaxSegs &&
            k12_takes_fused((uint64_t)nseg, nseg);
     if (spec) {

@@ -1104,6 +1104,192 @@ constexpr uint32_t MED_RUN = 32 * MED_V;  // 512
 // Word of s_o that holds gathered value e: runs of MED_RUN values, one pad word per 16.
 __device__ __forceinline__ uint32_t med_run_slot(uint32_t e) { return e + (e >> 4); }
 
+// The union of ONE term by a CTA of NW warps (k2_medium_kernel, api.cu's point read): c sources
+// (g_ptr[0 .. c), lengths as the prefix s_moff[0 .. c], L = s_moff[c] <= NW * 512 values) are
+// gathered into shared memory, sorted and deduped when c >= 2 (a single source passes through in
+// its own order, duplicates kept: survey Q4), filtered against the removed set and compacted.
+// Every thread of the CTA calls; returns the number of survivors, which end in s_v[0 .. outn).
+// s_v: NW * 512 words, s_o: NW * 512 * 17 / 16 words, s_cnt / s_last: NW words.
+template <int NW>
+__device__ __forceinline__ uint32_t cta_union_term(const uint64_t* __restrict__ g_ptr, uint32_t c,
+                                                   uint32_t L, const RemovedSet& rem, uint32_t* s_v,
+                                                   uint32_t* s_o, const uint32_t* s_moff,
+                                                   uint32_t* s_cnt, uint32_t* s_last) {
+  constexpr int MED_THREADS = NW * 32;
+  const uint32_t tid = threadIdx.x;
+  // ---- gather.  The term lands in s_o as runs of MED_RUN values (one per warp), every run
+  // padded (one word per 16) so that the blocked register load below is free of bank
+  // conflicts; the tail up to a power-of-two number of runs is the sentinel 0xFFFFFFFF.
+  const bool single = c == 1;  // passes through unsorted, duplicates kept (survey Q4)
+  const uint32_t w = warp_id(), lane = lane_id();
+  uint32_t nrun = 1;
+  while (nrun * MED_RUN < L) nrun <<= 1;
+  const uint32_t Lpad = nrun * MED_RUN;
+  // The source pointers wait in s_v (free until the first exchange) and every thread resolves
+  // eight elements before it stores any: eight value loads in flight instead of a chain of
+  // pointer load -> value load per element.
+  uint64_t* const s_ptr = reinterpret_cast<uint64_t*>(s_v);
+  const uint32_t* const src0 = reinterpret_cast<const uint32_t*>(g_ptr[0]);
+  if (!single) {
+    for (uint32_t i = tid; i < c; i += MED_THREADS) s_ptr[i] = g_ptr[i];
+    __syncthreads();
+  }
+  uint32_t top = 1;  // largest power of two below c
+  while (top * 2 < c) top <<= 1;
+  const bool by_source = !single && c * 8 <= L;  // sources of >= 8 values on average
+  if (by_source) {
+    // a warp per source, two sources (eight loads per lane) in flight; no search at all
+    for (uint32_t e = L + tid; e < Lpad; e += MED_THREADS) s_o[med_run_slot(e)] = 0xFFFFFFFFu;
+    for (uint32_t j0 = 2 * w; j0 < c; j0 += 2 * (MED_THREADS / 32)) {
+      uint32_t x[2][4], o2[2], n2[2];
+      const uint32_t* p2[2];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint32_t j = j0 + q;
+        const bool in = j < c;
+        p2[q] = reinterpret_cast<const uint32_t*>(in ? s_ptr[j] : 0ull);
+        o2[q] = in ? s_moff[j] : 0u;
+        n2[q] = in ? s_moff[j + 1] - o2[q] : 0u;
+#pragma unroll
+        for (int t = 0; t < 4; t++) x[q][t] = t * 32 + lane < n2[q] ? __ldg(p2[q] + t * 32 + lane) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (t * 32 + lane < n2[q]) s_o[med_run_slot(o2[q] + t * 32 + lane)] = x[q][t];
+        for (uint32_t i = 128 + lane; i < n2[q]; i += 32) s_o[med_run_slot(o2[q] + i)] = __ldg(p2[q] + i);
+      }
+    }
+  }
+  for (uint32_t e0 = tid; e0 < (by_source ? 0u : Lpad); e0 += 8 * MED_THREADS) {
+    uint32_t x[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint32_t e = e0 + q * MED_THREADS;
+      x[q] = 0xFFFFFFFFu;
+      if (e < L) {
+        if (single) {
+          x[q] = __ldg(src0 + e);
+        } else {
+          uint32_t lo = 0;  // last source whose first element is <= e (empty sources skipped)
+          for (uint32_t st = top; st; st >>= 1) {
+            const uint32_t m = lo + st;
+            if (m < c && s_moff[m] <= e) lo = m;
+          }
+          x[q] = __ldg(reinterpret_cast<const uint32_t*>(s_ptr[lo]) + (e - s_moff[lo]));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint32_t e = e0 + q * MED_THREADS;
+      if (e < Lpad) s_o[med_run_slot(e)] = x[q];
+    }
+  }
+  __syncthreads();
+  // ---- sort.  From here to the compaction the values live in registers: warp w holds run w,
+  // lane l its values 16 l .. 16 l + 15.  Each run is sorted by its warp (sort_warp_v<16>);
+  // then 1 / 2 / 3 bitonic merge levels double the sorted blocks up to Lpad.  A level starts
+  // with the stages whose partner sits in another warp — the flip (value e against the
+  // mirrored value of the partner run), then half-cleaners at warp distances — exchanged
+  // through shared memory in a transposed, conflict-free layout, alternating between the two
+  // buffers so that one barrier per stage is enough; the rest of the level is shuffles and
+  // register compare-exchanges (clean_warp_v).
+  const bool active = w < nrun;
+  uint32_t v[MED_V];
+#pragma unroll
+  for (int r = 0; r < MED_V; r++)
+    v[r] = active ? s_o[med_run_slot(w * MED_RUN + lane * MED_V + r)] : 0xFFFFFFFFu;
+  if (!single) {
+    {
+      const uint32_t at = w * MED_RUN, n = L > at ? min(L - at, MED_RUN) : 0u;
+      if (n > 1) sort_warp_v<MED_V>(v, lane, n);
+    }
+    uint32_t stage = 0;
+    for (uint32_t nw = 2; nw <= nrun; nw <<= 1) {  // warps per sorted block after this level
+      for (uint32_t dw = nw; dw >= 2; dw >>= 1) {  // dw == nw: the flip; below: half-cleaners
+        const bool flip = dw == nw;
+        uint32_t* const X = (stage++ & 1u) ? s_o : s_v;
+        if (active) {
+#pragma unroll
+          for (int r = 0; r < MED_V; r++) X[w * MED_RUN + r * 32 + lane] = v[r];
+        }
+        __syncthreads();
+        if (active) {
+          const uint32_t pw = flip ? (w ^ (nw - 1)) : (w ^ (dw >> 1));
+          const bool lower = (w & (dw >> 1)) == 0;
+          const uint32_t* const P = X + pw * MED_RUN;
+#pragma unroll
+          for (int r = 0; r < MED_V; r++) {
+            const uint32_t o = flip ? P[(MED_V - 1 - r) * 32 + (31 - lane)] : P[r * 32 + lane];
+            v[r] = ((v[r] < o) == lower) ? v[r] : o;
+          }
+        }
+      }
+      if (active) clean_warp_v<MED_V>(v, lane);
+    }
+  }
+  // ---- dedup + removed filter + compaction, still from the registers: sixteen membership
+  // probes per lane issued eight at a time, keep flags in a register, positions from one warp
+  // scan + the warps' totals; the survivors end in s_v.
+  uint32_t outn;
+  {
+    if (lane == 31) s_last[w] = v[MED_V - 1];
+    __syncthreads();  // (also: every partner has read the last exchange buffer)
+    const uint32_t e_l = w * MED_RUN + lane * MED_V;  // index of v[0]
+    uint32_t keep = 0;
+    if (rem.bitmap) {
+      const uint32_t nbits = (uint32_t)rem.bitmap_bits;
+#pragma unroll
+      for (int r0 = 0; r0 < MED_V; r0 += 8) {
+        uint32_t word[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const bool probe = e_l + r0 + r < L && v[r0 + r] < nbits;
+          word[r] = probe ? __ldg(rem.bitmap + (v[r0 + r] >> 5)) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+          keep |= (e_l + r0 + r < L && !((word[r] >> (v[r0 + r] & 31u)) & 1u)) ? 1u << (r0 + r) : 0u;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < MED_V; r++)
+        if (e_l + r < L && !(rem.n && is_removed_call(rem.sorted, rem.n, v[r]))) keep |= 1u << r;
+    }
+    uint32_t up = __shfl_up_sync(0xffffffffu, v[MED_V - 1], 1);  // the value before v[0]
+    if (lane == 0 && w > 0) up = s_last[w - 1];
+    if (!single) {
+      if (e_l > 0 && up == v[0]) keep &= ~1u;
+#pragma unroll
+      for (int r = 1; r < MED_V; r++)
+        if (v[r] == v[r - 1]) keep &= ~(1u << r);
+    }
+    const uint32_t cnt = __popc(keep);
+    const uint32_t inc = warp_inclusive_scan(cnt);
+    if (lane == 31) s_cnt[w] = inc;
+    __syncthreads();
+    uint32_t at = inc - cnt, tot = 0;
+#pragma unroll
+    for (int q = 0; q < MED_THREADS / 32; q++) {
+      const uint32_t cq = s_cnt[q];
+      at += (uint32_t)q < w ? cq : 0u;
+      tot += cq;
+    }
+    outn = tot;
+    uint32_t* dst = s_v + at;
+#pragma unroll
+    for (int r = 0; r < MED_V; r++) {
+      const bool k = (keep >> r) & 1u;
+      if (k) *dst = v[r];
+      dst += k ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  return outn;
+}
+
 struct MedArgs {
   const uint32_t* n_large;       // terms K2b deferred
   const uint32_t* large_rec;
@@ -1171,176 +1357,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 8 : 5) k2_medium_kernel(con
     const uint32_t L = (uint32_t)run;
     if (tid == 0) s_moff[c] = L;
     __syncthreads();
-    // ---- gather.  The term lands in s_o as runs of MED_RUN values (one per warp), every run
-    // padded (one word per 16) so that the blocked register load below is free of bank
-    // conflicts; the tail up to a power-of-two number of runs is the sentinel 0xFFFFFFFF.
-    const bool single = c == 1;  // passes through unsorted, duplicates kept (survey Q4)
-    const uint32_t w = warp_id(), lane = lane_id();
-    uint32_t nrun = 1;
-    while (nrun * MED_RUN < L) nrun <<= 1;
-    const uint32_t Lpad = nrun * MED_RUN;
-    // The source pointers wait in s_v (free until the first exchange) and every thread resolves
-    // eight elements before it stores any: eight value loads in flight instead of a chain of
-    // pointer load -> value load per element.
-    uint64_t* const s_ptr = reinterpret_cast<uint64_t*>(s_v);
-    const uint32_t* const src0 = reinterpret_cast<const uint32_t*>(a.src_ptr[beg]);
-    if (!single) {
-      for (uint32_t i = tid; i < c; i += MED_THREADS) s_ptr[i] = a.src_ptr[beg + i];
-      __syncthreads();
-    }
-    uint32_t top = 1;  // largest power of two below c
-    while (top * 2 < c) top <<= 1;
-    const bool by_source = !single && c * 8 <= L;  // sources of >= 8 values on average
-    if (by_source) {
-      // a warp per source, two sources (eight loads per lane) in flight; no search at all
-      for (uint32_t e = L + tid; e < Lpad; e += MED_THREADS) s_o[med_run_slot(e)] = 0xFFFFFFFFu;
-      for (uint32_t j0 = 2 * w; j0 < c; j0 += 2 * (MED_THREADS / 32)) {
-        uint32_t x[2][4], o2[2], n2[2];
-        const uint32_t* p2[2];
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const uint32_t j = j0 + q;
-          const bool in = j < c;
-          p2[q] = reinterpret_cast<const uint32_t*>(in ? s_ptr[j] : 0ull);
-          o2[q] = in ? s_moff[j] : 0u;
-          n2[q] = in ? s_moff[j + 1] - o2[q] : 0u;
-#pragma unroll
-          for (int t = 0; t < 4; t++) x[q][t] = t * 32 + lane < n2[q] ? __ldg(p2[q] + t * 32 + lane) : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-#pragma unroll
-          for (int t = 0; t < 4; t++)
-            if (t * 32 + lane < n2[q]) s_o[med_run_slot(o2[q] + t * 32 + lane)] = x[q][t];
-          for (uint32_t i = 128 + lane; i < n2[q]; i += 32) s_o[med_run_slot(o2[q] + i)] = __ldg(p2[q] + i);
-        }
-      }
-    }
-    for (uint32_t e0 = tid; e0 < (by_source ? 0u : Lpad); e0 += 8 * MED_THREADS) {
-      uint32_t x[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const uint32_t e = e0 + q * MED_THREADS;
-        x[q] = 0xFFFFFFFFu;
-        if (e < L) {
-          if (single) {
-            x[q] = __ldg(src0 + e);
-          } else {
-            uint32_t lo = 0;  // last source whose first element is <= e (empty sources skipped)
-            for (uint32_t st = top; st; st >>= 1) {
-              const uint32_t m = lo + st;
-              if (m < c && s_moff[m] <= e) lo = m;
-            }
-            x[q] = __ldg(reinterpret_cast<const uint32_t*>(s_ptr[lo]) + (e - s_moff[lo]));
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const uint32_t e = e0 + q * MED_THREADS;
-        if (e < Lpad) s_o[med_run_slot(e)] = x[q];
-      }
-    }
-    __syncthreads();
-    // ---- sort.  From here to the compaction the values live in registers: warp w holds run w,
-    // lane l its values 16 l .. 16 l + 15.  Each run is sorted by its warp (sort_warp_v<16>);
-    // then 1 / 2 / 3 bitonic merge levels double the sorted blocks up to Lpad.  A level starts
-    // with the stages whose partner sits in another warp — the flip (value e against the
-    // mirrored value of the partner run), then half-cleaners at warp distances — exchanged
-    // through shared memory in a transposed, conflict-free layout, alternating between the two
-    // buffers so that one barrier per stage is enough; the rest of the level is shuffles and
-    // register compare-exchanges (clean_warp_v).
-    const bool active = w < nrun;
-    uint32_t v[MED_V];
-#pragma unroll
-    for (int r = 0; r < MED_V; r++)
-      v[r] = active ? s_o[med_run_slot(w * MED_RUN + lane * MED_V + r)] : 0xFFFFFFFFu;
-    if (!single) {
-      {
-        const uint32_t at = w * MED_RUN, n = L > at ? min(L - at, MED_RUN) : 0u;
-        if (n > 1) sort_warp_v<MED_V>(v, lane, n);
-      }
-      uint32_t stage = 0;
-      for (uint32_t nw = 2; nw <= nrun; nw <<= 1) {  // warps per sorted block after this level
-        for (uint32_t dw = nw; dw >= 2; dw >>= 1) {  // dw == nw: the flip; below: half-cleaners
-          const bool flip = dw == nw;
-          uint32_t* const X = (stage++ & 1u) ? s_o : s_v;
-          if (active) {
-#pragma unroll
-            for (int r = 0; r < MED_V; r++) X[w * MED_RUN + r * 32 + lane] = v[r];
-          }
-          __syncthreads();
-          if (active) {
-            const uint32_t pw = flip ? (w ^ (nw - 1)) : (w ^ (dw >> 1));
-            const bool lower = (w & (dw >> 1)) == 0;
-            const uint32_t* const P = X + pw * MED_RUN;
-#pragma unroll
-            for (int r = 0; r < MED_V; r++) {
-              const uint32_t o = flip ? P[(MED_V - 1 - r) * 32 + (31 - lane)] : P[r * 32 + lane];
-              v[r] = ((v[r] < o) == lower) ? v[r] : o;
-            }
-          }
-        }
-        if (active) clean_warp_v<MED_V>(v, lane);
-      }
-    }
-    // ---- dedup + removed filter + compaction, still from the registers: sixteen membership
-    // probes per lane issued eight at a time, keep flags in a register, positions from one warp
-    // scan + the warps' totals; the survivors end in s_v.
-    uint32_t outn;
-    {
-      if (lane == 31) s_last[w] = v[MED_V - 1];
-      __syncthreads();  // (also: every partner has read the last exchange buffer)
-      const uint32_t e_l = w * MED_RUN + lane * MED_V;  // index of v[0]
-      uint32_t keep = 0;
-      if (a.rem.bitmap) {
-        const uint32_t nbits = (uint32_t)a.rem.bitmap_bits;
-#pragma unroll
-        for (int r0 = 0; r0 < MED_V; r0 += 8) {
-          uint32_t word[8];
-#pragma unroll
-          for (int r = 0; r < 8; r++) {
-            const bool probe = e_l + r0 + r < L && v[r0 + r] < nbits;
-            word[r] = probe ? __ldg(a.rem.bitmap + (v[r0 + r] >> 5)) : 0u;
-          }
-#pragma unroll
-          for (int r = 0; r < 8; r++)
-            keep |= (e_l + r0 + r < L && !((word[r] >> (v[r0 + r] & 31u)) & 1u)) ? 1u << (r0 + r) : 0u;
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < MED_V; r++)
-          if (e_l + r < L && !(a.rem.n && is_removed_call(a.rem.sorted, a.rem.n, v[r]))) keep |= 1u << r;
-      }
-      uint32_t up = __shfl_up_sync(0xffffffffu, v[MED_V - 1], 1);  // the value before v[0]
-      if (lane == 0 && w > 0) up = s_last[w - 1];
-      if (!single) {
-        if (e_l > 0 && up == v[0]) keep &= ~1u;
-#pragma unroll
-        for (int r = 1; r < MED_V; r++)
-          if (v[r] == v[r - 1]) keep &= ~(1u << r);
-      }
-      const uint32_t cnt = __popc(keep);
-      const uint32_t inc = warp_inclusive_scan(cnt);
-      if (lane == 31) s_cnt[w] = inc;
-      __syncthreads();
-      uint32_t at = inc - cnt, tot = 0;
-#pragma unroll
-      for (int q = 0; q < MED_THREADS / 32; q++) {
-        const uint32_t cq = s_cnt[q];
-        at += (uint32_t)q < w ? cq : 0u;
-        tot += cq;
-      }
-      outn = tot;
-      uint32_t* dst = s_v + at;
-#pragma unroll
-      for (int r = 0; r < MED_V; r++) {
-        const bool k = (keep >> r) & 1u;
-        if (k) *dst = v[r];
-        dst += k ? 1 : 0;
-      }
-    }
-    __syncthreads();
+    const uint32_t outn = cta_union_term<NW>(a.src_ptr + beg, c, L, a.rem, s_v, s_o, s_moff, s_cnt, s_last);
     uint32_t* const oth = s_v;  // the survivors
     // ---- output space, then the stream and the values
     if (tid == 0) {
@@ -1377,6 +1394,163 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 8 : 5) k2_medium_kernel(con
       }
     }
   }
+}
+
+// ---------------------------------------------------------------- point read (one term)
+// Read(min == max): the whole call as ONE kernel.  A warp per segment looks the term up (32-way
+// search, one equality check) and records where its list lies; the last CTA to finish unions the
+// <= k lists with cta_union_term (up to 4096 values; sorted + deduped when >= 2 segments hold the
+// term, passed through for one: survey Q4), applies the removed filter and writes the one-term
+// result and its counts — to the result arrays and to pinned host memory.  The general path
+// (windows, plan, bucket kernel, totals, placement: five dependent kernels, ~75 us) remains for
+// anything larger; status 2 tells the host to take it.
+constexpr uint32_t kPointCap = 8 * MED_RUN;  // 4096 values
+enum : uint32_t { kPointAbsent = 0xFFFFFFFFu };
+struct PointArgs {
+  const SegDesc* segs;     // pinned host table (tb / toff / post / poff / n)
+  int k;
+  const uint8_t* term;     // pinned host
+  uint32_t tlen;
+  RemovedSet rem;
+  int keep_empty;
+  uint64_t* src_ptr;       // [2 k] scratch: by segment, then compacted
+  uint32_t* src_len;       // [k]
+  uint8_t* o_term_bytes;
+  uint32_t* o_term_off;    // [2]
+  uint32_t* o_post;        // [kPointCap]
+  uint64_t* o_post_off;    // [2]
+  uint64_t* h_res;         // pinned: status (1 done, 2 too large), T, P, postings in, sources
+  uint32_t* ticket;
+};
+
+__global__ void __launch_bounds__(256) k4_point_kernel(const PointArgs a) {
+  pdl_enter();
+  __shared__ uint32_t s_v[kPointCap];
+  __shared__ uint32_t s_o[kPointCap + kPointCap / 16];
+  __shared__ uint32_t s_moff[kMaxSegs + 1];
+  __shared__ uint64_t s_ws[256 / 32 + 2];
+  __shared__ uint32_t s_ws32[256 / 32 + 2];
+  __shared__ uint32_t s_cnt[8], s_last[8];
+  __shared__ bool s_is_last;
+  const uint32_t tid = threadIdx.x;
+  const unsigned lane = lane_id(), w = warp_id();
+  // the term: staged from the pinned block once per CTA
+  uint8_t* const s_term = reinterpret_cast<uint8_t*>(s_o);
+  for (uint32_t i = tid; i < a.tlen; i += 256) s_term[i] = a.term[i];
+  __syncthreads();
+  const int s = blockIdx.x * 8 + (int)w;
+  if (s < a.k) {
+    const SegDesc sd = a.segs[s];
+    auto term_vs = [&](uint32_t i) {
+      const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
+      return term_compare(sd.tb + o, n, s_term, a.tlen);
+    };
+    const uint32_t lo = warp_partition_point(0u, sd.n, [&](uint32_t i) { return term_vs(i) < 0; });
+    const bool found = lo < sd.n && term_vs(lo) == 0;
+    if (lane == 0) {
+      uint64_t ptr = 0;
+      uint32_t len = kPointAbsent;
+      if (found) {
+        const uint64_t p0 = __ldg(sd.poff + lo), p1 = __ldg(sd.poff + lo + 1);
+        ptr = reinterpret_cast<uint64_t>(sd.post + p0);
+        len = (uint32_t)min(p1 - p0, (uint64_t)kPointCap + 1);
+      }
+      a.src_ptr[s] = ptr;
+      a.src_len[s] = len;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  // ---- the last CTA: the segments that hold the term, in segment order
+  uint64_t* const cptr = a.src_ptr + a.k;
+  uint32_t c = 0;
+  uint64_t L = 0;
+  for (int base = 0; base < a.k; base += 256) {
+    const int x = base + (int)tid;
+    const uint32_t len = x < a.k ? *(volatile uint32_t*)(a.src_len + x) : kPointAbsent;
+    const bool present = len != kPointAbsent;
+    uint32_t ctot;
+    uint64_t ltot;
+    const uint32_t ex_c = block_exclusive_scan<uint32_t>(present ? 1u : 0u, s_ws32, ctot);
+    const uint64_t ex_l = block_exclusive_scan<uint64_t>(present ? (uint64_t)len : 0ull, s_ws, ltot);
+    if (present) {
+      cptr[c + ex_c] = *(volatile uint64_t*)(a.src_ptr + x);
+      s_moff[c + ex_c] = (uint32_t)min(L + ex_l, (uint64_t)kPointCap + 1);
+    }
+    c += ctot;
+    L += ltot;
+  }
+  if (tid == 0) s_moff[c] = (uint32_t)min(L, (uint64_t)kPointCap + 1);
+  __syncthreads();
+  if (c == 0 || L > kPointCap) {  // uniform
+    if (tid == 0) {
+      a.o_term_off[0] = 0;
+      a.o_post_off[0] = 0;
+      a.h_res[1] = 0;
+      a.h_res[2] = 0;
+      a.h_res[3] = L;
+      a.h_res[4] = c;
+      a.h_res[0] = c == 0 ? 1 : 2;
+      *a.ticket = 0;
+    }
+    return;
+  }
+  const uint32_t outn = cta_union_term<8>(cptr, c, (uint32_t)L, a.rem, s_v, s_o, s_moff, s_cnt, s_last);
+  const uint32_t T = (outn || a.keep_empty) ? 1u : 0u;
+  for (uint32_t e = tid; e < outn; e += 256) a.o_post[e] = s_v[e];
+  if (T)
+    for (uint32_t i = tid; i < a.tlen; i += 256) a.o_term_bytes[i] = a.term[i];
+  if (tid == 0) {
+    a.o_term_off[0] = 0;
+    a.o_term_off[1] = a.tlen;
+    a.o_post_off[0] = 0;
+    a.o_post_off[1] = outn;
+    a.h_res[1] = T;
+    a.h_res[2] = T ? outn : 0;
+    a.h_res[3] = L;
+    a.h_res[4] = c;
+    a.h_res[0] = 1;
+    *a.ticket = 0;
+  }
+}
+
+int k4_point_read(const SegDesc* h_segs, int k, const uint8_t* term, uint32_t tlen,
+                  const RemovedSet& rem, bool keep_empty, EmitOut& out, uint64_t* h_res,
+                  cudaStream_t s) {
+  if (k < 1 || k > kMaxSegs || tlen > kPointMaxTerm) return II2_ERR_INVALID;
+  DevBuf<uint64_t> ptrs;
+  DevBuf<uint32_t> lens;
+  II2_TRY(ptrs.alloc_scratch(2 * (size_t)k, s));
+  II2_TRY(lens.alloc_scratch((size_t)k, s));
+  II2_TRY(out.term_bytes.alloc(tlen, s, 32));
+  II2_TRY(out.term_off.alloc(2, s, 16));
+  II2_TRY(out.post.alloc(kPointCap, s, 16));
+  II2_TRY(out.post_off.alloc(2, s, 16));
+  uint32_t* const tickets = device_tickets();
+  if (!tickets) return II2_ERR_NOMEM;
+  PointArgs a;
+  a.segs = h_segs;
+  a.k = k;
+  a.term = term;
+  a.tlen = tlen;
+  a.rem = rem;
+  a.keep_empty = keep_empty ? 1 : 0;
+  a.src_ptr = ptrs.p;
+  a.src_len = lens.p;
+  a.o_term_bytes = out.term_bytes.p;
+  a.o_term_off = out.term_off.p;
+  a.o_post = out.post.p;
+  a.o_post_off = out.post_off.p;
+  a.h_res = h_res;
+  a.ticket = tickets + 2;
+  h_res[0] = 0;
+  ProfScope scope("k4_point", s);
+  II2_LAUNCH_CHAIN(k4_point_kernel, div_up(k, 8), 256, 0, s, a);
+  return II2_OK;
 }
 
 // ---------------------------------------------------------------- heavy terms (global memory)

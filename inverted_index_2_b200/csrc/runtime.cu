@@ -130,7 +130,7 @@ uint64_t* pinned_scratch() {
   static thread_local uint64_t* p = nullptr;
   if (!p) {
     void* q = nullptr;
-    if (cudaHostAlloc(&q, 256, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&q, 512, cudaHostAllocDefault) != cudaSuccess) return nullptr;  // 64 words
     p = static_cast<uint64_t*>(q);
   }
   return p;

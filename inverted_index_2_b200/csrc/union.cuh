@@ -154,6 +154,15 @@ int k6_emit(const MergePlan& plan, const UnionOut& u, EmitOut& out, cudaStream_t
 int k6_emit_early(const MergePlan& plan, UnionOut& u, uint64_t n_in, uint64_t tb_in, EmitOut& out,
                   cudaStream_t s);
 
+// Read(min == max) as one kernel (k12_union.cu, k4_point_kernel): h_segs / term live in pinned
+// host memory (the kernel reads them in place), h_res = 5 pinned words {status, T, P, postings in,
+// segments holding the term}; status 1 = the result is in `out` (one term or none), 2 = more than
+// 4096 values: take the general path.  Decoded output only.  No synchronisation.
+constexpr uint32_t kPointMaxTerm = 8192;  // term bytes the kernel stages in shared memory
+int k4_point_read(const SegDesc* h_segs, int k, const uint8_t* term, uint32_t tlen,
+                  const RemovedSet& rem, bool keep_empty, EmitOut& out, uint64_t* h_res,
+                  cudaStream_t s);
+
 // First and last term of the merged order (pre-filter min/max, shard.go:176-179).
 // d_out: [0]=len_min [1]=len_max (u32), bytes from +8 (min then max); needs 8 + 2*65536 bytes.
 int k6_minmax(const MergePlan& plan, const UnionOut& u, uint8_t* d_out, cudaStream_t s);

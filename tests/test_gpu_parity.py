@@ -490,7 +490,8 @@ def test_read_range_matches_oracle(engine, orc, merge_path):
 
 
 def test_point_reads(engine, orc, merge_path, monkeypatch):
-    """min == max: on the fused path the call is queued behind the windows kernel without waiting
+    """min == max: one kernel does the whole read (k4_point_kernel, <= 4096 values); failing that,
+    on the fused path the call is queued behind the windows kernel without waiting
     for the windows (at most one instance per segment, postings speculated <= 4096).  A term that
     is everywhere, in one segment, nowhere (between terms, before the first, after the last), the
     empty term; with and without the removed filter; a term whose lists exceed the speculation
@@ -505,12 +506,15 @@ def test_point_reads(engine, orc, merge_path, monkeypatch):
         per_seg[s_i].append((b"big", sorted(set(rng.integers(0, 1 << 20, size=700).tolist()))))    # 6300 > 4096 in
         per_seg[s_i].append((b"mid", sorted(set(rng.integers(0, 1 << 20, size=60).tolist()))))     # ~540 values: deferred
     per_seg[3].append((b"only3", [9, 8, 8, 1]))       # single source: order and duplicates kept
+    per_seg[5].append((b"hollow", []))                # present, no values
+    per_seg[6].append((b"hollow", []))
+    per_seg[7].append((b"solo_big", rng.integers(0, 1 << 20, size=5000).tolist()))   # one source, > 4096
     per_seg[4].append((b"", [4, 2]))                  # the empty term
     segs = [FlatSegment.from_items(sorted(x)) for x in per_seg]
     removed = np.unique(rng.integers(0, 5000, size=800)).astype(np.uint32)
     terms = [b"everywhere", b"only3", b"", b"big", b"mid", b"filler04", b"absent", b"everywhera", b"zzz",
-             b"\x00", b"filler"]
-    for mode in (None, "0"):
+             b"\x00", b"filler", b"hollow", b"solo_big"]
+    for mode in (None, "1", "0"):   # the one-kernel read, the speculative chain, a read like any other
         if mode is None:
             monkeypatch.delenv("II2_POINT_READ", raising=False)
         else:
