@@ -273,6 +273,12 @@ def test_medium_terms_of_many_short_sources(engine, orc, merge_path):
     assert_merge_equal(engine.merge(segs, removed, decoded=True), orc.merge(segs, removed, decoded=True))
     assert_merge_equal(engine.merge(segs, removed, decoded=False), orc.merge(segs, removed, decoded=False),
                        decoded=False)
+    # the same terms as point reads over 420 segments (one kernel: lookups + the CTA union, with
+    # the gather by search; 4096 values is its capacity, d_2049 has more sources than a bucket row)
+    for name, _, _ in plans:
+        assert_read_equal(engine.read_range(segs, name, name, removed=removed),
+                          orc.read_range(segs, name, name, removed=removed))
+        assert_read_equal(engine.read_range(segs, name, name), orc.read_range(segs, name, name))
 
 
 def test_merge_pipelined_by_term_range(engine, orc, monkeypatch):
