@@ -236,21 +236,21 @@ k4_windows(const SegDesc* h_segs, SegDesc* d_segs, SegDesc* h_out,
   __shared__ uint32_t ws[256 / 32 + 2];
   __shared__ __align__(16) uint8_t s_bounds[kBoundsSmem];
   __shared__ bool s_last;
-  const uint8_t* bnd = bounds;
-  if (minlen + maxlen <= kBoundsSmem) {  // (longer bounds were uploaded: read them in place)
-    for (uint32_t i = threadIdx.x; i < minlen + maxlen; i += 256) s_bounds[i] = bounds[i];
-    bnd = s_bounds;
-    __syncthreads();
-  }
   // two warps per segment: one finds the start of the window, the other its end, at the same
   // time (each search is a chain of ~8 dependent loads, which is what this kernel's time is)
   __shared__ uint32_t s_hi[4];
   const int s = blockIdx.x * 4 + (warp_id() >> 1);
   const bool upper = warp_id() & 1u;
   SegDesc sd = {};
+  if (s < k) sd = h_segs[s];  // (requested before the bounds: two reads over the bus at once)
+  const uint8_t* bnd = bounds;
+  if (minlen + maxlen <= kBoundsSmem) {  // (longer bounds were uploaded: read them in place)
+    for (uint32_t i = threadIdx.x; i < minlen + maxlen; i += 256) s_bounds[i] = bounds[i];
+    bnd = s_bounds;
+    __syncthreads();
+  }
   uint32_t found = 0;
   if (s < k) {
-    sd = h_segs[s];
     auto term_vs = [&](uint32_t i, const uint8_t* t, uint32_t nt) {
       const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
       return term_compare(sd.tb + o, n, t, nt);

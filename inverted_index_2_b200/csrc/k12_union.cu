@@ -1436,11 +1436,12 @@ __global__ void __launch_bounds__(256) k4_point_kernel(const PointArgs a) {
   const unsigned lane = lane_id(), w = warp_id();
   // the term: staged from the pinned block once per CTA
   uint8_t* const s_term = reinterpret_cast<uint8_t*>(s_o);
+  const int s = blockIdx.x * 8 + (int)w;
+  SegDesc sd = {};
+  if (s < a.k) sd = a.segs[s];  // (requested before the term: two reads over the bus at once)
   for (uint32_t i = tid; i < a.tlen; i += 256) s_term[i] = a.term[i];
   __syncthreads();
-  const int s = blockIdx.x * 8 + (int)w;
   if (s < a.k) {
-    const SegDesc sd = a.segs[s];
     auto term_vs = [&](uint32_t i) {
       const uint32_t o = __ldg(sd.toff + i), n = __ldg(sd.toff + i + 1) - o;
       return term_compare(sd.tb + o, n, s_term, a.tlen);
