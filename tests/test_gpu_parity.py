@@ -730,13 +730,21 @@ def test_concurrent_callers(engine, orc):
     shard_test.go:236-247): concurrent C-ABI calls from host threads."""
     ws = [synth.make_workload(2000, 4, 30000, universe=1 << 12, seed=100 + i) for i in range(8)]
     exp = [orc.merge(w.segments, w.removed, decoded=True) for w in ws]
+    t = lambda w, i: synth.term_at(w.term_bytes, w.term_off, i)
+    # reads too: a range, a point read (one kernel, "last CTA" tickets and pinned result words per
+    # host thread) and a small range (single-bucket plan, early placement)
+    bounds = [[(t(w, 100), t(w, 900)), (t(w, 555), t(w, 555)), (t(w, 40), t(w, 44))] for w in ws]
+    exp_r = [[orc.read_range(w.segments, lo, hi, removed=w.removed) for lo, hi in b] for w, b in zip(ws, bounds)]
     got = [None] * len(ws)
+    got_r = [None] * len(ws)
     errs = []
 
     def run(i):
         try:
             for _ in range(3):
                 got[i] = engine.merge(ws[i].segments, ws[i].removed, decoded=True)
+                got_r[i] = [engine.read_range(ws[i].segments, lo, hi, removed=ws[i].removed)
+                            for lo, hi in bounds[i]]
         except Exception as e:  # pragma: no cover
             errs.append(e)
     th = [threading.Thread(target=run, args=(i,)) for i in range(len(ws))]
@@ -745,6 +753,9 @@ def test_concurrent_callers(engine, orc):
     assert not errs
     for g, e in zip(got, exp):
         assert_merge_equal(g, e)
+    for gr, er in zip(got_r, exp_r):
+        for g, e in zip(gr, er):
+            assert_read_equal(g, e)
 
 
 # ---------------------------------------------------------------- codec vs oracle
