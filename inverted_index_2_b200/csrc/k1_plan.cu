@@ -486,12 +486,12 @@ int k1_build_plan(MergePlan& plan, const SegDesc* h_segs, uint32_t* sbase, cudaS
   uint64_t want = N / per_bucket;
   // a small call (a narrow range read) is latency-bound: smaller buckets spread it over the SMs
   // (II2_SMALL_BUCKET=<min instances per bucket>, 0 = off)
-  static const uint32_t small_bucket = [] {
+  const uint32_t small_bucket = [] {  // (read per call: tuning runs sweep it inside one process)
     const char* e = getenv("II2_SMALL_BUCKET");
     const long v = e ? atol(e) : 128;
     return (v >= 0 && v <= 1024) ? (uint32_t)v : 128u;
   }();
-  static const uint32_t small_want = [] {  // II2_SMALL_WANT=<buckets a small call is cut into>
+  const uint32_t small_want = [] {  // II2_SMALL_WANT=<buckets a small call is cut into>
     const char* e = getenv("II2_SMALL_WANT");
     const long v = e ? atol(e) : 592;
     return (v >= 1 && v <= 65536) ? (uint32_t)v : 592u;
