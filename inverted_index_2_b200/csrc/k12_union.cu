@@ -17,8 +17,11 @@
 //   - a term present in ONE segment passes through untouched — not sorted, not deduped (survey
 //     Q4); a term present in >= 2 segments becomes the sorted-unique union;
 //   - the filter runs AFTER the union; removed = membership in the sorted removed list.
-// Terms whose lists exceed 256 values go to the multi-CTA global-memory path at the end of
-// this file.  Integer/byte work, HBM-bound by design.
+// Terms whose lists exceed 256 values are passed on through device-side work lists: up to 1024
+// values one warp each (k2_mwarp_kernel), up to 2048 / 4096 one CTA each (k2_medium_kernel<4> /
+// <8>, both built on cta_union_term), beyond that the multi-CTA global-memory path at the end of
+// this file.  k4_point_kernel (a read of ONE term as one kernel) uses the same CTA union.
+// Integer/byte work, HBM-bound by design.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
